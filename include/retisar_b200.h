@@ -1,0 +1,115 @@
+/*
+ * retisar_b200 -- C ABI of the B200-native per-block binaural rendering chain.
+ *
+ * The reference (AppliedAcousticsChalmers/ReTiSAR, pure Python) has no FFI; its boundary for this
+ * path is the duck-typed class API of ReTiSAR/_convolver.py.  Every entry point below names the
+ * reference interface it replaces.  Plain pointers and sizes only; the library links against the
+ * CUDA runtime and nothing else (no torch types).
+ *
+ * Conventions
+ *   - complex arrays are interleaved float pairs (re, im) == numpy complex64, C order
+ *   - "d_" pointers are device pointers on the plan's device, "h_" pointers are host pointers
+ *   - every function returns RTB_OK or an RTB_ERR_* code; rtb_last_error() gives the message of
+ *     the last failure on the calling thread.  The Python layer maps codes to the exceptions the
+ *     reference raises (ValueError / RuntimeError / NotImplementedError).
+ *   - a plan batches S independent render streams (reference: one convolver object per stream,
+ *     ReTiSAR/_jack_renderer.py:467-531 for the benchmark list of convolvers)
+ */
+#ifndef RETISAR_B200_H
+#define RETISAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_OK 0
+#define RTB_ERR_INVALID 1     /* bad argument            -> ValueError          */
+#define RTB_ERR_STATE 2       /* tables not set etc.     -> RuntimeError        */
+#define RTB_ERR_UNSUPPORTED 3 /* not implemented         -> NotImplementedError */
+#define RTB_ERR_CUDA 4        /* CUDA runtime failure    -> RuntimeError        */
+#define RTB_ERR_NOMEM 5       /* allocation failure      -> MemoryError         */
+
+typedef struct rtb_sh_plan rtb_sh_plan;   /* AdjustableShConvolver x S streams */
+typedef struct rtb_ols_plan rtb_ols_plan; /* OverlapSaveConvolver  x S streams */
+
+/* library ------------------------------------------------------------------------------------ */
+int rtb_version(void);
+const char *rtb_last_error(void);
+/* number of visible CUDA devices, or a negative RTB error code */
+int rtb_device_count(void);
+
+/* SH-domain renderer ------------------------------------------------------------------------- */
+/* AdjustableShConvolver.__init__ (_convolver.py:1010-1049) for S batched streams.
+ * block_length B in {32, 64, 128, 256}; n_ears must be 2; n_partitions = number of B-sample
+ * partitions of the HRIR (1 = the reference's only supported case, _filter_set.py:1136-1140). */
+int rtb_sh_plan_create(rtb_sh_plan **plan, int device, int n_streams, int block_length,
+                       int n_channels, int sh_max_order, int n_ears, int n_partitions);
+
+/* prepare_sh_processing (_convolver.py:1071-1120): upload the tables the hot path reads.
+ *   yw     [K][C]       complex  _sh_bases_weighted            (_convolver.py:1097)
+ *   hnm    [P][K][E][F] complex  _filter._irs_blocks_nm, already multiplied with the
+ *                                compensation spectra            (_convolver.py:1206)
+ *   sh_m   [K]          int16    _sh_m                         (_convolver.py:1094)
+ *   rev    [K]          int32    _sh_m_rev_id                  (_convolver.py:1095)
+ *   win_in / win_out [B] float   cross-fade windows (_convolver.py:741-747); NULL = cos^2 default
+ * Resets all per-stream state like the reference (input buffer :1113-1116, last phases :1098). */
+int rtb_sh_plan_set_tables(rtb_sh_plan *plan, const float *yw, const float *hnm,
+                           const int16_t *sh_m, const int32_t *rev, const float *win_in,
+                           const float *win_out);
+
+/* _apply_sh_compensation re-run by update_sh_processing (_convolver.py:1161-1162, :1189-1206):
+ * replace hnm [P][K][E][F] only; per-stream state (overlap buffer, last yaw) is kept. */
+int rtb_sh_plan_update_filter(rtb_sh_plan *plan, const float *hnm);
+
+/* _sources_deg[0,0] (_convolver.py:729) and tracker_dir = +1 HRIR / -1 BRIR (_convolver.py:958) */
+int rtb_sh_plan_set_source(rtb_sh_plan *plan, float source_azim_deg, int tracker_dir);
+/* update_sh_processing: _sh_cur_order (_convolver.py:1159-1160); 0 <= order <= sh_max_order */
+int rtb_sh_plan_set_order(rtb_sh_plan *plan, int sh_cur_order);
+/* Convolver.set_passthrough (_convolver.py:288-305) */
+int rtb_sh_plan_set_passthrough(rtb_sh_plan *plan, int on);
+/* AdjustableShConvolver.set_crossfade (_convolver.py:1318-1341); off clears the "last" state */
+int rtb_sh_plan_set_crossfade(rtb_sh_plan *plan, int on);
+/* _clear_buffers (_convolver.py:774-778) */
+int rtb_sh_plan_reset(rtb_sh_plan *plan);
+
+/* AdjustableShConvolver.filter_block (_convolver.py:1231-1316) for all S streams.
+ *   d_in  [S][C][B] float32, d_yaw_deg [S] float32 (tracker AZIM in degrees, _tracker.py:73-81),
+ *   d_out [S][E][B] float32.  Asynchronous on `cuda_stream` (a cudaStream_t, NULL = default). */
+int rtb_sh_process_block(rtb_sh_plan *plan, const float *d_in, const float *d_yaw_deg,
+                         float *d_out, void *cuda_stream);
+/* Same with host buffers: H2D copy, render, D2H copy, synchronise (the JACK-callback shape of
+ * JackRenderer._process, _jack_renderer.py:296-315). */
+int rtb_sh_process_block_host(rtb_sh_plan *plan, const float *h_in, const float *h_yaw_deg,
+                              float *h_out);
+
+/* introspection: what = RTB_Q_* */
+#define RTB_Q_SYMMETRIC 1   /* 1 if Y_w has the (n,-m) conjugate symmetry (real analysis path) */
+#define RTB_Q_ROWS 2        /* J: real analysis rows per stream                                */
+#define RTB_Q_SIGNALS 3     /* number of complex FFT signals per stream                        */
+#define RTB_Q_LAUNCHES 4    /* kernels launched by this plan so far                            */
+#define RTB_Q_STATE_BYTES 5 /* bytes of per-stream device state                                */
+int rtb_sh_plan_query(rtb_sh_plan *plan, int what, int64_t *value);
+int rtb_sh_plan_destroy(rtb_sh_plan *plan);
+
+/* Uniformly partitioned overlap-save FIR convolver ------------------------------------------- */
+/* OverlapSaveConvolver.__init__ (_convolver.py:454-480): channel-wise FIR, n_in == n_out or
+ * n_in == 1 (mono input broadcast to all filter channels, _convolver.py:588-591). */
+int rtb_ols_plan_create(rtb_ols_plan **plan, int device, int n_streams, int block_length,
+                        int n_in, int n_out, int n_partitions);
+/* filter spectra _irs_blocks_fd [P][n_out][F] complex (FilterSet.calculate_filter_blocks_fd,
+ * _filter_set.py:625-664; the singleton direction axis dropped) */
+int rtb_ols_plan_set_filter(rtb_ols_plan *plan, const float *hfd);
+int rtb_ols_plan_set_passthrough(rtb_ols_plan *plan, int on);
+int rtb_ols_plan_reset(rtb_ols_plan *plan);
+/* OverlapSaveConvolver.filter_block (_convolver.py:524-571): d_in [S][n_in][B] -> d_out [S][n_out][B] */
+int rtb_ols_process_block(rtb_ols_plan *plan, const float *d_in, float *d_out, void *cuda_stream);
+int rtb_ols_process_block_host(rtb_ols_plan *plan, const float *h_in, float *h_out);
+int rtb_ols_plan_query(rtb_ols_plan *plan, int what, int64_t *value);
+int rtb_ols_plan_destroy(rtb_ols_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RETISAR_B200_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of ``libretisar_b200.so`` (C ABI declared in ``include/retisar_b200.h``).
+
+There is deliberately no fallback: if the CUDA library has not been built, importing this module
+raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``retisar_b200/csrc/build.sh``.
+"""
+import ctypes
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libretisar_b200.so")
+
+RTB_OK, RTB_ERR_INVALID, RTB_ERR_STATE, RTB_ERR_UNSUPPORTED, RTB_ERR_CUDA, RTB_ERR_NOMEM = range(6)
+RTB_Q_SYMMETRIC, RTB_Q_ROWS, RTB_Q_SIGNALS, RTB_Q_LAUNCHES, RTB_Q_STATE_BYTES = 1, 2, 3, 4, 5
+
+# every symbol include/retisar_b200.h declares: name -> (restype, argtypes)
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+SIGNATURES = {
+    "rtb_version": (_i, []),
+    "rtb_last_error": (ctypes.c_char_p, []),
+    "rtb_device_count": (_i, []),
+    "rtb_sh_plan_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i]),
+    "rtb_sh_plan_set_tables": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rtb_sh_plan_update_filter": (_i, [_vp, _vp]),
+    "rtb_sh_plan_set_source": (_i, [_vp, ctypes.c_float, _i]),
+    "rtb_sh_plan_set_order": (_i, [_vp, _i]),
+    "rtb_sh_plan_set_passthrough": (_i, [_vp, _i]),
+    "rtb_sh_plan_set_crossfade": (_i, [_vp, _i]),
+    "rtb_sh_plan_reset": (_i, [_vp]),
+    "rtb_sh_process_block": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "rtb_sh_process_block_host": (_i, [_vp, _vp, _vp, _vp]),
+    "rtb_sh_plan_query": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
+    "rtb_sh_plan_destroy": (_i, [_vp]),
+    "rtb_ols_plan_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
+    "rtb_ols_plan_set_filter": (_i, [_vp, _vp]),
+    "rtb_ols_plan_set_passthrough": (_i, [_vp, _i]),
+    "rtb_ols_plan_reset": (_i, [_vp]),
+    "rtb_ols_process_block": (_i, [_vp, _vp, _vp, _vp]),
+    "rtb_ols_process_block_host": (_i, [_vp, _vp, _vp]),
+    "rtb_ols_plan_query": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
+    "rtb_ols_plan_destroy": (_i, [_vp]),
+}
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def _load():
+    if not os.path.isfile(_LIB_PATH):
+        raise RuntimeError(
+            f"CUDA library {_LIB_PATH} has not been built (no CPU fallback exists); run "
+            f"`python -c \"import __graft_entry__ as g; g.build()\"` or retisar_b200/csrc/build.sh"
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+lib = _load()
+
+_EXC = {
+    RTB_ERR_INVALID: ValueError,
+    RTB_ERR_STATE: RuntimeError,
+    RTB_ERR_UNSUPPORTED: NotImplementedError,
+    RTB_ERR_CUDA: RuntimeError,
+    RTB_ERR_NOMEM: MemoryError,
+}
+
+
+def check(rc):
+    """Map an RTB status code to the exception type the reference raises for that condition."""
+    if rc != RTB_OK:
+        msg = lib.rtb_last_error().decode("utf-8", "replace")
+        raise _EXC.get(rc, RuntimeError)(msg)
+
+
+def np_ptr(a):
+    """Pointer to the data of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return ctypes.c_void_p(a.ctypes.data)

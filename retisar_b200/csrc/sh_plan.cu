@@ -1,0 +1,457 @@
+// Host side of the SH-domain renderer: table preparation, per-stream state, launches, C ABI.
+// Reference behaviour: ReTiSAR/_convolver.py AdjustableShConvolver (:978-1341) and the parts of
+// AdjustableFdConvolver / OverlapSaveConvolver it inherits.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "sh_kernels.cuh"
+
+using namespace rtb;
+
+struct rtb_sh_plan {
+    int device = 0;
+    int S = 0, B = 0, C = 0, order = 0, K = 0, E = 2, P = 1;
+    int F = 0, N2 = 0;
+    // derived by set_tables
+    bool tables_set = false;
+    bool symmetric = false;
+    int J = 0, Jpad = 0, JT = 0, TT = 0, n_jchunks = 0, NP = 0;
+    // device memory
+    float *d_rmT = nullptr;       // [C][Jpad]
+    float *d_zring = nullptr;     // [2][S][J][B]
+    float4 *d_htab = nullptr;     // [NP][2][F]
+    ShSignal *d_signals = nullptr;
+    float2 *d_tw = nullptr;       // [N2]
+    float *d_win_in = nullptr, *d_win_out = nullptr;
+    float *d_radlast = nullptr;   // [2][S]
+    // staging for the host-buffer entry point
+    float *d_in = nullptr, *d_yaw = nullptr, *d_out = nullptr;
+    cudaStream_t own_stream = nullptr;
+    // control state (reference attribute it mirrors)
+    int slot = 0;                 // which half of d_zring receives the current block
+    int rad_idx = 0;              // which half of d_radlast holds the previous yaw
+    int cur_order = 0;            // _sh_cur_order
+    int last_order = 0;           // length of _last_sh_azim_nm, as an order
+    bool last_valid = false;      // false <=> _last_sh_azim_nm is all zeros
+    bool crossfade = true;        // _is_crossfade
+    bool passthrough = false;     // _is_passthrough
+    std::vector<int> sig_k1, sig_k2;   // H_nm row consumed by term 1 / term 2 of each signal
+    std::vector<float> sig_sign2;      // (-1)^m folded into term 2
+    float src_azim16 = 0.f;       // _sources_deg[0, 0], already rounded to float16
+    float tracker_dir = 1.f;      // +1 HRIR, -1 BRIR
+    long long launches = 0;
+};
+
+namespace {
+
+float round_to_half(float v) { return __half2float(__float2half_rn(v)); }
+
+int signals_for_order(const rtb_sh_plan *p, int order) {
+    return p->symmetric ? (order + 1) * (order + 2) / 2 : (order + 1) * (order + 1);
+}
+
+template <int JT, int TT>
+void launch_analysis_t(const rtb_sh_plan *p, const float *d_in, float *zcur, cudaStream_t st) {
+    const int n_ttiles = p->B / (32 * TT);
+    const long long tasks = (long long)p->S * n_ttiles * p->n_jchunks;
+    const unsigned grid = (unsigned)((tasks + 3) / 4);
+    sh_analysis_kernel<JT, TT><<<grid, 128, 0, st>>>(d_in, p->d_rmT, zcur, p->S, p->C, p->J,
+                                                     p->Jpad, p->B, n_ttiles, p->n_jchunks);
+}
+
+template <int JT>
+void launch_analysis_j(const rtb_sh_plan *p, const float *d_in, float *zcur, cudaStream_t st) {
+    switch (p->TT) {
+        case 1: launch_analysis_t<JT, 1>(p, d_in, zcur, st); break;
+        case 2: launch_analysis_t<JT, 2>(p, d_in, zcur, st); break;
+        default: launch_analysis_t<JT, 4>(p, d_in, zcur, st); break;
+    }
+}
+
+void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, cudaStream_t st) {
+    switch (p->JT) {
+        case 8: launch_analysis_j<8>(p, d_in, zcur, st); break;
+        case 12: launch_analysis_j<12>(p, d_in, zcur, st); break;
+        case 16: launch_analysis_j<16>(p, d_in, zcur, st); break;
+        case 20: launch_analysis_j<20>(p, d_in, zcur, st); break;
+        case 24: launch_analysis_j<24>(p, d_in, zcur, st); break;
+        case 28: launch_analysis_j<28>(p, d_in, zcur, st); break;
+        default: launch_analysis_j<32>(p, d_in, zcur, st); break;
+    }
+}
+
+void launch_render(const rtb_sh_plan *p, const ShRenderParams &prm, cudaStream_t st) {
+    const unsigned grid = (unsigned)((p->S + 3) / 4);
+    switch (p->N2) {
+        case 64: sh_render_kernel<64><<<grid, 128, 0, st>>>(prm); break;
+        case 128: sh_render_kernel<128><<<grid, 128, 0, st>>>(prm); break;
+        case 256: sh_render_kernel<256><<<grid, 128, 0, st>>>(prm); break;
+        default: sh_render_kernel<512><<<grid, 128, 0, st>>>(prm); break;
+    }
+}
+
+// H table: [NP][2][F] x (ear0.re, ear0.im, ear1.re, ear1.im); hnm is [P=1][K][E=2][F] complex
+std::vector<float4> build_htab(const rtb_sh_plan *p, const float *hnm) {
+    const int F = p->F, NP = (int)p->sig_k1.size();
+    std::vector<float4> htab((size_t)NP * 2 * F, make_float4(0.f, 0.f, 0.f, 0.f));
+    auto HNM = [&](int k, int e, int f, int ri) { return hnm[2 * (((size_t)k * 2 + e) * F + f) + ri]; };
+    for (int q = 0; q < NP; ++q) {
+        const int k1 = p->sig_k1[q], k2 = p->sig_k2[q];
+        const float sg = p->sig_sign2[q];
+        for (int f = 0; f < F; ++f) {
+            htab[((size_t)q * 2) * F + f] = make_float4(HNM(k1, 0, f, 0), HNM(k1, 0, f, 1),
+                                                        HNM(k1, 1, f, 0), HNM(k1, 1, f, 1));
+            if (k2 >= 0)
+                htab[((size_t)q * 2 + 1) * F + f] = make_float4(sg * HNM(k2, 0, f, 0), sg * HNM(k2, 0, f, 1),
+                                                                sg * HNM(k2, 1, f, 0), sg * HNM(k2, 1, f, 1));
+        }
+    }
+    return htab;
+}
+
+void free_tables(rtb_sh_plan *p) {
+    cudaFree(p->d_rmT); p->d_rmT = nullptr;
+    cudaFree(p->d_zring); p->d_zring = nullptr;
+    cudaFree(p->d_htab); p->d_htab = nullptr;
+    cudaFree(p->d_signals); p->d_signals = nullptr;
+    p->tables_set = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtb_sh_plan_create(rtb_sh_plan **out, int device, int n_streams, int block_length,
+                       int n_channels, int sh_max_order, int n_ears, int n_partitions) {
+    if (!out) return fail(RTB_ERR_INVALID, "plan output pointer is NULL");
+    *out = nullptr;
+    if (n_streams < 1) return fail(RTB_ERR_INVALID, "n_streams must be >= 1 (got %d)", n_streams);
+    if (n_channels < 1) return fail(RTB_ERR_INVALID, "n_channels must be >= 1");
+    if (sh_max_order < 0 || sh_max_order > RTB_MAX_ORDER)
+        return fail(RTB_ERR_INVALID, "Invalid value \"%d\" for spherical harmonics order.", sh_max_order);
+    if (n_ears != 2)
+        return fail(RTB_ERR_UNSUPPORTED, "the SH renderer produces exactly 2 ear signals (got %d)", n_ears);
+    if (block_length != 32 && block_length != 64 && block_length != 128 && block_length != 256)
+        return fail(RTB_ERR_UNSUPPORTED, "block length %d not supported by the SH renderer "
+                    "(supported: 32, 64, 128, 256)", block_length);
+    if (n_partitions < 1) return fail(RTB_ERR_INVALID, "n_partitions must be >= 1");
+    if (n_partitions > 1)
+        return fail(RTB_ERR_UNSUPPORTED,
+                    "More than one (%d) blocks would be necessary for loaded filter and partitioned "
+                    "convolution in SH domain is not implemented yet.", n_partitions);
+    int ndev = 0;
+    RTB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(RTB_ERR_INVALID, "no CUDA device %d", device);
+
+    rtb_sh_plan *p = new (std::nothrow) rtb_sh_plan();
+    if (!p) return fail(RTB_ERR_NOMEM, "out of host memory");
+    p->device = device;
+    p->S = n_streams; p->B = block_length; p->C = n_channels; p->order = sh_max_order;
+    p->K = (sh_max_order + 1) * (sh_max_order + 1);
+    p->E = n_ears; p->P = n_partitions;
+    p->F = block_length + 1; p->N2 = 2 * block_length;
+    p->cur_order = p->last_order = sh_max_order;
+
+    DeviceGuard guard(device);
+    cudaError_t err = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_tw, sizeof(float2) * p->N2);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_win_in, sizeof(float) * p->B);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_win_out, sizeof(float) * p->B);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_radlast, sizeof(float) * 2 * p->S);
+    if (err == cudaSuccess) err = cudaMemset(p->d_radlast, 0, sizeof(float) * 2 * p->S);
+    if (err != cudaSuccess) {
+        rtb_sh_plan_destroy(p);
+        return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
+                    "plan allocation failed: %s", cudaGetErrorString(err));
+    }
+    std::vector<float2> tw(p->N2);
+    for (int q = 0; q < p->N2; ++q) {
+        const double a = -2.0 * M_PI * q / p->N2;
+        tw[q] = make_float2((float)cos(a), (float)sin(a));
+    }
+    RTB_CUDA(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * p->N2, cudaMemcpyHostToDevice));
+    *out = p;
+    return RTB_OK;
+}
+
+int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, const int16_t *sh_m,
+                           const int32_t *rev, const float *win_in, const float *win_out) {
+    if (!p || !yw || !hnm || !sh_m || !rev) return fail(RTB_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(p->device);
+    const int K = p->K, C = p->C, F = p->F, B = p->B;
+    auto YW = [&](int k, int c) { return make_float2(yw[2 * ((size_t)k * C + c)], yw[2 * ((size_t)k * C + c) + 1]); };
+
+    // rev must be a permutation of 0..K-1
+    std::vector<int> inv_rev(K, -1);
+    for (int k = 0; k < K; ++k) {
+        if (rev[k] < 0 || rev[k] >= K || inv_rev[rev[k]] >= 0)
+            return fail(RTB_ERR_INVALID, "reverse index list is not a permutation");
+        inv_rev[rev[k]] = k;
+    }
+    for (int k = 0; k < K; ++k)
+        if (std::abs((int)sh_m[k]) > p->order)
+            return fail(RTB_ERR_INVALID, "|sh_m[%d]| = %d exceeds the SH order %d", k, sh_m[k], p->order);
+
+    // Does Y_w have the structure of complex spherical harmonics, rows ordered (n, m = -n..n)
+    // with Y_w[(n,-m)] = (-1)^m conj(Y_w[(n,m)])?  True for both constructions of
+    // FilterSetMiro.get_sh_configuration (_filter_set.py:1271-1278).
+    bool standard = true;
+    for (int n = 0, k = 0; n <= p->order && standard; ++n)
+        for (int m = -n; m <= n; ++m, ++k)
+            if (sh_m[k] != m || rev[k] != n * n + n - m) { standard = false; break; }
+    bool symmetric = standard;
+    if (standard) {
+        double vmax = 0.0, dmax = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double sgn = (sh_m[k] & 1) ? -1.0 : 1.0;
+            for (int c = 0; c < C; ++c) {
+                const float2 a = YW(k, c), b = YW(rev[k], c);
+                vmax = std::max(vmax, (double)std::max(std::fabs(a.x), std::fabs(a.y)));
+                dmax = std::max(dmax, std::fabs(b.x - sgn * a.x));
+                dmax = std::max(dmax, std::fabs(b.y + sgn * a.y));
+            }
+        }
+        symmetric = dmax <= 1e-6 * vmax;
+    }
+
+    // complex FFT signals and the real analysis rows that feed them
+    std::vector<ShSignal> sig;
+    std::vector<int> sig_k1, sig_k2;   // H_nm row used by term 1 / term 2 (-1 = none)
+    std::vector<float> sig_sign2;
+    std::vector<std::vector<float>> rows;  // analysis rows [J][C]
+    auto add_row = [&](int k, bool imag) {
+        std::vector<float> r(C);
+        for (int c = 0; c < C; ++c) r[c] = imag ? YW(k, c).y : YW(k, c).x;
+        rows.push_back(r);
+        return (int)rows.size() - 1;
+    };
+    if (symmetric) {
+        for (int n = 0; n <= p->order; ++n)
+            for (int m = 0; m <= n; ++m) {
+                const int kpos = n * n + n + m, kneg = n * n + n - m;
+                ShSignal s;
+                s.row_re = add_row(kpos, false);
+                s.row_im = m > 0 ? add_row(kpos, true) : -1;
+                s.m1 = -m;                       // consumer k = (n,-m): S[rev k] = bin f
+                s.m2 = m > 0 ? m : RTB_NO_TERM;  // consumer k = (n,+m): S[rev k] = (-1)^m conj(bin N2-f)
+                sig.push_back(s);
+                sig_k1.push_back(kneg);
+                sig_k2.push_back(m > 0 ? kpos : -1);
+                sig_sign2.push_back((m & 1) ? -1.f : 1.f);
+            }
+    } else {
+        for (int k = 0; k < K; ++k) {  // signal k transforms S[rev[k]], consumed by H_nm[k]
+            ShSignal s;
+            s.row_re = add_row(rev[k], false);
+            s.row_im = add_row(rev[k], true);
+            s.m1 = sh_m[k];
+            s.m2 = RTB_NO_TERM;
+            sig.push_back(s);
+            sig_k1.push_back(k);
+            sig_k2.push_back(-1);
+            sig_sign2.push_back(1.f);
+        }
+    }
+    const int J = (int)rows.size(), NP = (int)sig.size();
+
+    // K-A tiling: rows per warp tile (multiple of 4) minimising padded work + per-tile overhead
+    int bestJT = 8, bestCost = 1 << 30;
+    for (int jt = 8; jt <= 32; jt += 4) {
+        const int chunks = (J + jt - 1) / jt, cost = chunks * (jt + 6);
+        if (cost <= bestCost) { bestCost = cost; bestJT = jt; }
+    }
+    const int n_jchunks = (J + bestJT - 1) / bestJT, Jpad = n_jchunks * bestJT;
+    std::vector<float> rmT((size_t)C * Jpad, 0.f);
+    for (int j = 0; j < J; ++j)
+        for (int c = 0; c < C; ++c) rmT[(size_t)c * Jpad + j] = rows[j][c];
+
+    p->sig_k1 = sig_k1; p->sig_k2 = sig_k2; p->sig_sign2 = sig_sign2;
+    std::vector<float4> htab = build_htab(p, hnm);
+
+    // cross-fade windows (_convolver.py:741-747), pre-scaled by the inverse-FFT normalisation
+    std::vector<float> wi(B), wo(B);
+    for (int n = 0; n < B; ++n) {
+        float o, i;
+        if (win_in && win_out) { i = win_in[n]; o = win_out[n]; }
+        else {
+            const double c0 = cos(n * M_PI / (2.0 * (B - 1))), c1 = cos((B - 1 - n) * M_PI / (2.0 * (B - 1)));
+            o = (float)(c0 * c0); i = (float)(c1 * c1);
+        }
+        wi[n] = i / (float)p->N2; wo[n] = o / (float)p->N2;  // N2 is a power of two: exact
+    }
+
+    free_tables(p);
+    const size_t zbytes = sizeof(float) * 2 * (size_t)p->S * J * B;
+    cudaError_t err = cudaMalloc(&p->d_rmT, sizeof(float) * rmT.size());
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_zring, zbytes);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_htab, sizeof(float4) * htab.size());
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_signals, sizeof(ShSignal) * NP);
+    if (err != cudaSuccess) {
+        free_tables(p);
+        return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
+                    "table allocation failed: %s", cudaGetErrorString(err));
+    }
+    RTB_CUDA(cudaMemcpy(p->d_rmT, rmT.data(), sizeof(float) * rmT.size(), cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(p->d_htab, htab.data(), sizeof(float4) * htab.size(), cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(p->d_signals, sig.data(), sizeof(ShSignal) * NP, cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(p->d_win_in, wi.data(), sizeof(float) * B, cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(p->d_win_out, wo.data(), sizeof(float) * B, cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemset(p->d_zring, 0, zbytes));
+    RTB_CUDA(cudaMemset(p->d_radlast, 0, sizeof(float) * 2 * p->S));
+
+    p->symmetric = symmetric;
+    p->J = J; p->Jpad = Jpad; p->JT = bestJT; p->n_jchunks = n_jchunks; p->NP = NP;
+    p->TT = B >= 128 ? 4 : (B == 64 ? 2 : 1);
+    p->slot = 0; p->rad_idx = 0;
+    p->cur_order = p->last_order = p->order;
+    p->last_valid = false;
+    p->tables_set = true;
+    return RTB_OK;
+}
+
+int rtb_sh_plan_update_filter(rtb_sh_plan *p, const float *hnm) {
+    if (!p || !hnm) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (!p->tables_set)
+        return fail(RTB_ERR_STATE, "blocks in spherical harmonics domain have not been calculated yet.");
+    DeviceGuard guard(p->device);
+    std::vector<float4> htab = build_htab(p, hnm);
+    // the renderer may be running on another stream: plain (synchronising) copy, like the
+    // reference's in-place `_irs_blocks_nm *= comp_nm` under a cleared IS_RUNNING
+    RTB_CUDA(cudaDeviceSynchronize());
+    RTB_CUDA(cudaMemcpy(p->d_htab, htab.data(), sizeof(float4) * htab.size(), cudaMemcpyHostToDevice));
+    return RTB_OK;
+}
+
+int rtb_sh_plan_set_source(rtb_sh_plan *p, float source_azim_deg, int tracker_dir) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    if (tracker_dir != 1 && tracker_dir != -1) return fail(RTB_ERR_INVALID, "tracker_dir must be +1 or -1");
+    p->src_azim16 = round_to_half(source_azim_deg);
+    p->tracker_dir = (float)tracker_dir;
+    return RTB_OK;
+}
+
+int rtb_sh_plan_set_order(rtb_sh_plan *p, int order) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    if (order < 0 || order > p->order)
+        return fail(RTB_ERR_INVALID, "value \"%d\" out of bounds, \"set SH processing order\" ignored.", order);
+    p->cur_order = order;
+    return RTB_OK;
+}
+
+int rtb_sh_plan_set_passthrough(rtb_sh_plan *p, int on) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    p->passthrough = on != 0;
+    return RTB_OK;
+}
+
+int rtb_sh_plan_set_crossfade(rtb_sh_plan *p, int on) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    p->crossfade = on != 0;
+    if (!p->crossfade) p->last_valid = false;  // _last_sh_azim_nm.fill(0), _convolver.py:1338-1339
+    return RTB_OK;
+}
+
+int rtb_sh_plan_reset(rtb_sh_plan *p) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    if (!p->tables_set) return RTB_OK;
+    DeviceGuard guard(p->device);
+    // _input_block_td.fill(0); the P == 1 spectra buffers are rewritten every block anyway
+    RTB_CUDA(cudaMemset(p->d_zring, 0, sizeof(float) * 2 * (size_t)p->S * p->J * p->B));
+    return RTB_OK;
+}
+
+int rtb_sh_process_block(rtb_sh_plan *p, const float *d_in, const float *d_yaw_deg, float *d_out,
+                         void *cuda_stream) {
+    if (!p || !d_in || !d_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (!p->tables_set)
+        return fail(RTB_ERR_STATE, "blocks in spherical harmonics domain have not been calculated yet.");
+    if (!d_yaw_deg && !p->passthrough) return fail(RTB_ERR_INVALID, "NULL yaw pointer");
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t zhalf = (size_t)p->S * p->J * p->B;
+    float *zcur = p->d_zring + (size_t)p->slot * zhalf;
+    const float *zprev = p->d_zring + (size_t)(p->slot ^ 1) * zhalf;
+
+    launch_analysis(p, d_in, zcur, st);  // a1/a2: the overlap-save state advances in every mode
+    p->launches++;
+    if (p->passthrough) {
+        const long long total = (long long)p->S * p->E * p->B;
+        sh_passthrough_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_in, d_out, p->S, p->C, p->E, p->B);
+        p->launches++;
+    } else {
+        ShRenderParams prm;
+        prm.zprev = zprev; prm.zcur = zcur;
+        prm.htab = p->d_htab; prm.signals = p->d_signals; prm.tw = p->d_tw;
+        prm.win_in = p->d_win_in; prm.win_out = p->d_win_out;
+        prm.yaw_deg = d_yaw_deg;
+        prm.rad_last_in = p->d_radlast + (size_t)p->rad_idx * p->S;
+        prm.rad_last_out = p->d_radlast + (size_t)(p->rad_idx ^ 1) * p->S;
+        prm.out = d_out;
+        prm.S = p->S; prm.J = p->J; prm.B = p->B;
+        prm.np_cur = signals_for_order(p, p->cur_order);
+        prm.np_last = (p->crossfade && p->last_valid) ? signals_for_order(p, p->last_order) : 0;
+        prm.order_max = p->order;
+        prm.crossfade = p->crossfade ? 1 : 0;
+        prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
+        launch_render(p, prm, st);
+        p->launches++;
+        if (p->crossfade) {  // _last_sh_azim_nm = sh_azim_nm (_convolver.py:1311)
+            p->rad_idx ^= 1;
+            p->last_valid = true;
+            p->last_order = p->cur_order;
+        }
+    }
+    p->slot ^= 1;
+    RTB_CUDA(cudaGetLastError());
+    return RTB_OK;
+}
+
+int rtb_sh_process_block_host(rtb_sh_plan *p, const float *h_in, const float *h_yaw_deg, float *h_out) {
+    if (!p || !h_in || !h_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (!h_yaw_deg && !p->passthrough) return fail(RTB_ERR_INVALID, "NULL yaw pointer");
+    DeviceGuard guard(p->device);
+    const size_t n_in = (size_t)p->S * p->C * p->B, n_out = (size_t)p->S * p->E * p->B;
+    if (!p->d_in) {
+        cudaError_t err = cudaMalloc(&p->d_in, sizeof(float) * n_in);
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_out, sizeof(float) * n_out);
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_yaw, sizeof(float) * p->S);
+        if (err == cudaSuccess) err = cudaMemset(p->d_yaw, 0, sizeof(float) * p->S);
+        if (err != cudaSuccess) return fail(RTB_ERR_NOMEM, "staging allocation failed: %s", cudaGetErrorString(err));
+    }
+    RTB_CUDA(cudaMemcpyAsync(p->d_in, h_in, sizeof(float) * n_in, cudaMemcpyHostToDevice, p->own_stream));
+    if (h_yaw_deg)
+        RTB_CUDA(cudaMemcpyAsync(p->d_yaw, h_yaw_deg, sizeof(float) * p->S, cudaMemcpyHostToDevice, p->own_stream));
+    int rc = rtb_sh_process_block(p, p->d_in, p->d_yaw, p->d_out, p->own_stream);
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaMemcpyAsync(h_out, p->d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost, p->own_stream));
+    RTB_CUDA(cudaStreamSynchronize(p->own_stream));
+    return RTB_OK;
+}
+
+int rtb_sh_plan_query(rtb_sh_plan *p, int what, int64_t *value) {
+    if (!p || !value) return fail(RTB_ERR_INVALID, "NULL argument");
+    switch (what) {
+        case RTB_Q_SYMMETRIC: *value = p->symmetric ? 1 : 0; break;
+        case RTB_Q_ROWS: *value = p->J; break;
+        case RTB_Q_SIGNALS: *value = p->NP; break;
+        case RTB_Q_LAUNCHES: *value = p->launches; break;
+        case RTB_Q_STATE_BYTES: *value = (int64_t)sizeof(float) * (2 * (int64_t)p->J * p->B + 2); break;
+        default: return fail(RTB_ERR_INVALID, "unknown query %d", what);
+    }
+    return RTB_OK;
+}
+
+int rtb_sh_plan_destroy(rtb_sh_plan *p) {
+    if (!p) return RTB_OK;
+    DeviceGuard guard(p->device);
+    free_tables(p);
+    cudaFree(p->d_tw); cudaFree(p->d_win_in); cudaFree(p->d_win_out); cudaFree(p->d_radlast);
+    cudaFree(p->d_in); cudaFree(p->d_yaw); cudaFree(p->d_out);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+    return RTB_OK;
+}
+
+}  // extern "C"
