@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the per-block binaural rendering chain (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c5|c4] [--streams S]
+
+A "step" is one block (256 samples at 48 kHz for c2) of S batched, independent render streams
+with their own head yaw.  One JSON line is printed by rank 0:
+
+  value      real-time streams sustained = stream-blocks per second / (fs / B), whole job,
+             inputs resident in HBM, K steps back to back (device time, max over ranks)
+  e2e        same metric through ``AdjustableShConvolver.filter_block`` with pinned HOST buffers:
+             H2D copy of the block, render, D2H copy of the ear signals inside the timed region
+  roofline   dominant kernel (the render kernel), timed live with CUDA events on its stream
+  cpu_baseline / --impl reference
+             the numpy oracle (a line-by-line restatement of the reference's numpy path, kind
+             "port": the reference is pure Python and cannot travel to the GPU box) on host cores
+"""
+import argparse
+import json
+import os
+
+# the reference pins BLAS / OpenMP to one thread per process (`ReTiSAR/config.py:277-280`,
+# `tools.py:416-460`); must happen before numpy is imported
+for _var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_var, "1")
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "real-time binaural streams @48kHz/256-blk per GPU; p99 block latency"
+UNIT = "realtime_streams"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, one process per host core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Render `n_blocks` blocks of one stream with the oracle; returns seconds per block."""
+    workload, n_blocks, warm, seed = args
+    from oracle import sh_chain as oc
+    from retisar_b200 import synthetic as syn
+    from retisar_b200 import workloads as wl
+
+    tb = wl.sh_tables(workload, hrir_dirs=400)
+    cfg = tb["sh_config"]
+    tb["hrir_set"].calculate_filter_blocks_fd(tb["B"])
+    tb["hrir_set"].calculate_filter_blocks_nm()
+    o = oc.ShOracle(cfg.sh_m, cfg.sh_bases_weighted, tb["hrir_set"].get_filter_blocks_nm(), tb["B"],
+                    tb["order"])
+    x = syn.noise_blocks(8, tb["C"], tb["B"], seed)
+    yaw = syn.yaw_walk(warm + n_blocks, seed + 1)
+    for i in range(warm):
+        o.filter_block(x[i % 8], yaw[i])
+    t0 = time.perf_counter()
+    for i in range(n_blocks):
+        o.filter_block(x[i % 8], yaw[warm + i])
+    return (time.perf_counter() - t0) / n_blocks
+
+
+def cpu_arm(workload, cores, n_blocks, warm=50):
+    """Streams the host sustains in real time with `cores` independent oracle processes."""
+    import multiprocessing as mp
+
+    from retisar_b200 import workloads as wl
+
+    c = wl.CONFIGS[workload]
+    block_period = c["block"] / wl.FS
+    if cores == 1:
+        per_block = [_cpu_worker((workload, n_blocks, warm, 0))]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            per_block = pool.map(_cpu_worker, [(workload, n_blocks, warm, i) for i in range(cores)])
+    streams = sum(block_period / t for t in per_block)
+    return streams, float(np.mean(per_block))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from retisar_b200 import workloads as wl
+
+    cores = os.cpu_count() or 1
+    c = wl.CONFIGS[args.workload]
+    n_blocks = max(200, min(args.steps, 3000))
+    t0 = time.perf_counter()
+    streams, sec_per_block = cpu_arm(args.workload, cores, n_blocks, warm=max(args.warmup, 3))
+    wall = time.perf_counter() - t0
+    sample = (f"{cores} processes x 1 stream x {n_blocks} blocks of the numpy oracle "
+              f"(np.fft, BLAS threads = 1), {sec_per_block * 1e6:.0f} us/block/stream")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": streams, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec_per_block * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {c['desc']}", "streams": cores,
+                   "block_length": c["block"], "fs": wl.FS},
+        "cpu_baseline": {"value": streams, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": streams, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+
+    from retisar_b200 import _capi
+    from retisar_b200 import workloads as wl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S, K, W = args.streams, args.steps, max(args.warmup, 3)
+    tb = wl.sh_tables(args.workload)
+    B, C, E = tb["B"], tb["C"], 2
+    conv = wl.make_renderer(tb, S, device=local_rank)
+    plan = conv._plan
+    block_rate = wl.FS / B  # blocks per second of one real-time stream
+
+    # inputs resident in HBM: a ring of distinct blocks larger than L2 (126 MB), so every timed
+    # step reads its block from DRAM without an explicit flush
+    in_bytes = S * C * B * 4
+    ring = max(4, int(np.ceil(160e6 / in_bytes)) + 1)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    x_ring = torch.randn((ring, S, C, B), generator=gen, device=dev, dtype=torch.float32) * 0.1
+    yaw0 = torch.rand((S,), generator=gen, device=dev) * 360.0
+    yaw_ring = torch.stack([yaw0 + 1.5 * i for i in range(ring)]).contiguous()
+    out = torch.empty((S, E, B), device=dev, dtype=torch.float32)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        plan.process_device(x_ring[i % ring], yaw_ring[i % ring], out, stream)
+
+    # ---- device-resident throughput: W warm-up, then exactly K steps between barriers
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = plan.query(_capi.RTB_Q_LAUNCHES)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        step(W + i)
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = plan.query(_capi.RTB_Q_LAUNCHES) - launches0
+    value = world * S * K / (dev_ms * 1e-3) / block_rate
+
+    # ---- block latency: per-step events, L2 flushed before every step
+    n_lat = min(K, 2000)
+    flush = torch.empty(int(256e6) // 4, device=dev, dtype=torch.float32)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(n_lat)]
+    for i, (a, b) in enumerate(evs):
+        flush.add_(1.0)
+        a.record(stream)
+        step(i)
+        b.record(stream)
+    torch.cuda.synchronize()
+    lat = np.array([a.elapsed_time(b) for a, b in evs])
+    lat_p50, lat_p99, lat_max = (float(np.percentile(lat, q)) for q in (50, 99, 100))
+    lat_p99 = max_over_ranks(lat_p99)
+
+    # ---- per-kernel device time (CUDA events inside the library, on the launching stream)
+    plan.set_profiling(True)
+    k_an, k_re = [], []
+    for i in range(min(K, 200)):
+        flush.add_(1.0)
+        step(i)
+        k_an.append(plan.query(_capi.RTB_Q_ANALYSIS_NS))
+        k_re.append(plan.query(_capi.RTB_Q_RENDER_NS))
+    plan.set_profiling(False)
+    an_us, re_us = float(np.mean(k_an)) / 1e3, float(np.mean(k_re)) / 1e3
+
+    # ---- end to end through the public API with pinned host buffers
+    K_e2e = max(10, min(K, 200))
+    hx = torch.randn((4, S, C, B), dtype=torch.float32).mul_(0.1).pin_memory()
+    hyaw = (torch.rand((4, S)) * 360.0).pin_memory()
+    hx_np, hyaw_np = hx.numpy(), hyaw.numpy()
+    for i in range(3):
+        conv.filter_block(hx_np[i % 4], hyaw_np[i % 4])
+    barrier()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for i in range(K_e2e):
+        y = conv.filter_block(hx_np[i % 4], hyaw_np[i % 4])
+        acc += float(y[0, 0, 0])
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * S * K_e2e / e2e_s / block_rate
+    clocks = sampler.stop() if sampler else None
+
+    # ---- gather one output block from every rank (the only collective; off the timed path)
+    if dist is not None:
+        gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        dist.gather(out, gathered, dst=0)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        J = plan.query(_capi.RTB_Q_ROWS)
+        render_bytes = S * (4 * B * (2 * J + E) + 12)  # z rows of 2 blocks in, ear blocks out, yaw
+        analysis_bytes = S * 4 * B * (C + J)
+        chain_bytes = S * wl.chain_bytes_per_stream_block(C, B, E)
+        chain_flops = S * wl.chain_flops_per_stream_block(C, tb["K"], B, E)
+        achieved = render_bytes / (re_us * 1e-6) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {tb['desc']}", "streams_per_gpu": S,
+                       "block_length": B, "fs": wl.FS, "sh_order": tb["order"], "channels": C,
+                       "crossfade": True, "input_ring_blocks": ring,
+                       "l2_policy": f"inputs cycle through a {ring * in_bytes / 1e6:.0f} MB ring "
+                                    f"(> 126 MB L2); latency steps flush L2 with a 256 MB write"},
+            "p99_block_latency_ms": lat_p99, "p50_block_latency_ms": lat_p50,
+            "max_block_latency_ms": lat_max, "block_period_ms": 1e3 / block_rate,
+            "latency_steps": n_lat,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * C * B * 4 + S * 4,
+                    "d2h_bytes_per_step": S * E * B * 4, "steps": K_e2e,
+                    "ms_per_step": e2e_s / K_e2e * 1e3,
+                    "api": "AdjustableShConvolver.filter_block(numpy pinned [S,C,B], yaw[S])"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "sh_render_kernel", "achieved": achieved,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": render_bytes, "us_per_launch": re_us},
+            "kernels": {"sh_analysis_kernel": {"us": an_us, "bytes": analysis_bytes,
+                                               "GBps": analysis_bytes / (an_us * 1e-6) / 1e9},
+                        "sh_render_kernel": {"us": re_us, "bytes": render_bytes,
+                                             "GBps": achieved}},
+            "chain": {"bytes_per_step": chain_bytes, "flops_per_step": chain_flops,
+                      "GBps": chain_bytes / (dev_ms / K * 1e-3) / 1e9,
+                      "TFLOPs_reference_formulation": chain_flops / (dev_ms / K * 1e-3) / 1e12},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb_streams, cb_sec = cpu_arm(args.workload, 1, 1500)
+            line["cpu_baseline"] = {
+                "value": cb_streams, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"1 stream x 1500 blocks of the numpy oracle on one host core "
+                          f"({cb_sec * 1e6:.0f} us/block); host has {os.cpu_count()} cores"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c4"])
+    ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

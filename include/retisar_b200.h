@@ -90,7 +90,12 @@ int rtb_sh_process_block_host(rtb_sh_plan *plan, const float *h_in, const float 
 #define RTB_Q_SIGNALS 3     /* number of complex FFT signals per stream                        */
 #define RTB_Q_LAUNCHES 4    /* kernels launched by this plan so far                            */
 #define RTB_Q_STATE_BYTES 5 /* bytes of per-stream device state                                */
+#define RTB_Q_ANALYSIS_NS 6 /* device time of the last block's analysis kernel (profiling on)  */
+#define RTB_Q_RENDER_NS 7   /* device time of the last block's render kernel   (profiling on)  */
 int rtb_sh_plan_query(rtb_sh_plan *plan, int what, int64_t *value);
+/* record CUDA events around each kernel of process_block (measurement aid, no reference
+ * counterpart; the reference reports load through JACK, _jack_client.py:869-895) */
+int rtb_sh_plan_set_profiling(rtb_sh_plan *plan, int on);
 int rtb_sh_plan_destroy(rtb_sh_plan *plan);
 
 /* Uniformly partitioned overlap-save FIR convolver ------------------------------------------- */

@@ -11,6 +11,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 
 RTB_OK, RTB_ERR_INVALID, RTB_ERR_STATE, RTB_ERR_UNSUPPORTED, RTB_ERR_CUDA, RTB_ERR_NOMEM = range(6)
 RTB_Q_SYMMETRIC, RTB_Q_ROWS, RTB_Q_SIGNALS, RTB_Q_LAUNCHES, RTB_Q_STATE_BYTES = 1, 2, 3, 4, 5
+RTB_Q_ANALYSIS_NS, RTB_Q_RENDER_NS = 6, 7
 
 # every symbol include/retisar_b200.h declares: name -> (restype, argtypes)
 _c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -31,6 +32,7 @@ SIGNATURES = {
     "rtb_sh_process_block": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "rtb_sh_process_block_host": (_i, [_vp, _vp, _vp, _vp]),
     "rtb_sh_plan_query": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
+    "rtb_sh_plan_set_profiling": (_i, [_vp, _i]),
     "rtb_sh_plan_destroy": (_i, [_vp]),
     "rtb_ols_plan_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
     "rtb_ols_plan_set_filter": (_i, [_vp, _vp]),

@@ -1,0 +1,395 @@
+"""Block-wise convolvers -- host-side mirror of ``ReTiSAR/_convolver.py`` over the CUDA library.
+
+Class names, the factory, method signatures and error behaviour follow the reference so that
+``JackRenderer`` (``_jack_renderer.py``) and ``_run_benchmark`` can use these classes unchanged;
+the arithmetic of ``filter_block`` runs in ``libretisar_b200.so`` (no CPU path exists).
+
+Extension over the reference: one convolver object may carry ``n_streams`` independent render
+streams.  ``filter_block`` then takes ``[n_streams; channels; block]`` blocks (numpy on the host
+or torch tensors on the device) and, for the binaural renderer, one yaw angle per stream.
+"""
+from copy import copy
+
+import numpy as np
+
+from . import config
+from ._filter_set import FilterSetMiro, FilterSetMultiChannel, FilterSetSofa, FilterSetSsr  # noqa: F401
+from ._tracker import HeadTracker
+from .plans import OlsPlan, ShPlan
+from . import sph
+
+
+def _is_torch_tensor(x):
+    return type(x).__module__.startswith("torch")
+
+
+class Convolver(object):
+    """Base class and factory (reference ``Convolver``, ``_convolver.py:144-433``)."""
+
+    @staticmethod
+    def create_instance_by_filter_set(filter_set, block_length=None, source_positions=None,
+                                      shared_tracker_data=None, n_streams=1, device=None):
+        """Pick the convolver class for a filter set (``_convolver.py:165-218``)."""
+        if not block_length:
+            convolver = Convolver(filter_set)
+        elif type(filter_set) == FilterSetMultiChannel:
+            convolver = OverlapSaveConvolver(filter_set, block_length, n_streams=n_streams,
+                                             device=device)
+        elif type(filter_set) == FilterSetSsr:
+            convolver = AdjustableFdConvolver(filter_set, block_length, source_positions,
+                                              shared_tracker_data)
+        elif filter_set.get_sh_configuration().arir_config:
+            convolver = OverlapSaveConvolver(filter_set, block_length, n_streams=n_streams,
+                                             device=device)
+        else:
+            convolver = AdjustableShConvolver(filter_set, block_length, source_positions,
+                                              shared_tracker_data, n_streams=n_streams,
+                                              device=device)
+        if config.IS_DEBUG_MODE and type(convolver) is not AdjustableShConvolver:
+            convolver._debug_filter_block(len(source_positions) if source_positions else 0)
+        return convolver
+
+    def __init__(self, filter_set):
+        self._filter = filter_set
+        self._is_passthrough = False
+        self._rfft = None  # kept for attribute compatibility; transforms run on the GPU
+        self._irfft = None
+        if type(self) is Convolver:
+            self._filter.calculate_filter_blocks_fd(None)
+
+    def __str__(self):
+        return f"[ID={id(self)}, _filter={self._filter}, _is_passthrough={self._is_passthrough}]"
+
+    def _clear_buffers(self):
+        """Zero all signal state (``_convolver.py:257-259``)."""
+
+    def init_fft_optimize(self, logger=None):
+        """The reference plans its FFTW transforms here (``_convolver.py:261-286``); the CUDA
+        plans are complete once the tables are uploaded, so this only reports."""
+        msg = "skipping FFTW DFT optimization (transforms run in CUDA kernels)."
+        logger.info(msg) if logger else print(msg)
+
+    def set_passthrough(self, new_state=None):
+        """Toggle / set bypass (``_convolver.py:288-305``)."""
+        self._is_passthrough = (not self._is_passthrough) if new_state is None else bool(new_state)
+        self._apply_passthrough()
+        return self._is_passthrough
+
+    def _apply_passthrough(self):
+        pass
+
+    def _debug_filter_block(self, input_count, is_generate_noise=False):
+        """Push one dirac (or noise) block through ``filter_block`` (``_convolver.py:307-361``)."""
+        if not input_count:
+            input_count = self.get_input_channel_count()
+        dtype = self._filter.get_dirac_td().dtype
+        if is_generate_noise:
+            ip = (np.random.default_rng(0).standard_normal((input_count, self._block_length)) * 0.1
+                  ).astype(dtype)
+        else:
+            ip = np.zeros((input_count, self._block_length), dtype=dtype)
+            ip[:, 0] = 1
+        return self.filter_block(ip)
+
+    def filter_block(self, input_td):
+        """Un-buffered circular convolution of the reference base class (``_convolver.py:363-399``).
+        It is documented there as "not recommended" and is not on the render path; only the
+        pause protocol (``None`` in, ``None`` out) is kept."""
+        if input_td is None:
+            if not config.IS_RUNNING.is_set():
+                self._clear_buffers()
+            return None
+        raise NotImplementedError(
+            "the un-buffered base `Convolver` has no CUDA implementation; pass a block length")
+
+    def get_input_channel_count(self):
+        """``_convolver.py:402-412``"""
+        shape = self._filter._irs_td.shape
+        return shape[1] if self._filter._is_hpcf else shape[0]
+
+    def get_output_channel_count(self):
+        """``_convolver.py:414-422``"""
+        return self._filter._irs_td.shape[0] * self._filter._irs_td.shape[1]
+
+    def _get_current_filters_fd(self):
+        if self._is_passthrough:
+            return self._filter.get_dirac_blocks_fd()
+        return self._filter.get_filter_blocks_fd()
+
+
+class OverlapSaveConvolver(Convolver):
+    """Uniformly partitioned overlap-save FIR convolver (``_convolver.py:436-669``).
+
+    Channel-wise: output channel i is input channel i (or the single input channel, which the
+    reference broadcasts, ``:588-591``) convolved with filter channel i.
+    """
+
+    def __init__(self, filter_set, block_length, n_streams=1, device=None):
+        super().__init__(filter_set=filter_set)
+        self._block_length = block_length
+        self._n_streams = int(n_streams)
+        self._device = config.CUDA_DEVICE if device is None else device
+        self._filter.calculate_filter_blocks_fd(self._block_length)
+        self._plan = None
+        if type(self) is OverlapSaveConvolver:
+            hfd = self._filter.get_filter_blocks_fd()  # [P, 1, Cout, F]
+            n_out = hfd.shape[-2]
+            self._n_in = n_out  # rows of `_input_block_td` (`_convolver.py:477-480`)
+            self._plan = OlsPlan(self._n_streams, block_length, n_out, n_out, hfd.shape[0],
+                                 device=self._device)
+            self._plan.set_filter(hfd[:, 0])
+
+    def __copy__(self):
+        """Independent clone for ``JackRendererBenchmark.add_convolver`` (``_convolver.py:482-491``);
+        unlike the reference's clones this one does not share signal buffers."""
+        _filter = copy(self._filter)
+        new = type(self)(_filter, self._block_length, n_streams=self._n_streams, device=self._device)
+        new.set_passthrough(self._is_passthrough)
+        return new
+
+    def __str__(self):
+        return (f"[{super().__str__()[1:-1]}, _block_length={self._block_length}, "
+                f"_n_streams={self._n_streams}]")
+
+    def _clear_buffers(self):
+        if self._plan is not None:
+            self._plan.reset()
+
+    def _apply_passthrough(self):
+        if self._plan is not None:
+            self._plan.set_passthrough(self._is_passthrough)
+
+    def filter_block(self, input_block_td):
+        """One block through the partitioned convolver (``_convolver.py:524-571``).
+
+        input [channels; B] or [1; B] (mono, broadcast) -> output [channels; B]; with
+        ``n_streams > 1`` both carry a leading stream axis.  torch CUDA tensors are processed
+        in place on the device and a device tensor is returned.
+        """
+        if input_block_td is None:
+            return Convolver.filter_block(self, None)
+        plan = self._plan
+        if _is_torch_tensor(input_block_td):
+            import torch
+
+            x = input_block_td.reshape(plan.S, -1, plan.B)
+            if x.shape[1] == 1 and plan.n_in > 1:
+                x = x.expand(plan.S, plan.n_in, plan.B).contiguous()
+            out = torch.empty((plan.S, plan.n_out, plan.B), dtype=torch.float32, device=x.device)
+            plan.process_device(x.contiguous(), out, torch.cuda.current_stream(x.device))
+            return out if input_block_td.dim() == 3 else out[0]
+        x = np.asarray(input_block_td, dtype=np.float32)
+        batched = x.ndim == 3
+        x = x.reshape(plan.S, -1, plan.B)
+        if x.shape[1] == 1 and plan.n_in > 1:
+            x = np.broadcast_to(x, (plan.S, plan.n_in, plan.B))
+        out = plan.process_host(x)
+        return out if batched else out[0]
+
+
+class AdjustableFdConvolver(OverlapSaveConvolver):
+    """HRIR/BRIR-switching renderer (``_convolver.py:672-975``).
+
+    Only the parts the SH renderer inherits are implemented (source positions, tracker access,
+    cross-fade windows and switches); direction-switched partitioned rendering itself is listed
+    as a later row in SURVEY.md section 8f.
+    """
+
+    def __init__(self, filter_set, block_length, source_positions, shared_tracker_data,
+                 n_streams=1, device=None):
+        super().__init__(filter_set=filter_set, block_length=block_length, n_streams=n_streams,
+                         device=device)
+        self._is_crossfade = True
+        if not source_positions:
+            raise ValueError(
+                "no virtual source positions (according to playback file channel count) given.")
+        self._tracker_deg = shared_tracker_data
+        self._sources_deg = np.array(source_positions, dtype=np.float16)
+        # cos^2 windows, evaluated exactly like `_convolver.py:741-747`
+        rdtype = self._filter.get_dirac_td().dtype
+        w = np.arange(self._block_length, dtype=rdtype)
+        self._window_out_td = np.square(np.cos(w * np.pi / (2 * (self._block_length - 1))))
+        self._window_in_td = np.flip(self._window_out_td).copy()
+
+    def filter_block(self, input_block_td):
+        if input_block_td is None:
+            return Convolver.filter_block(self, None)
+        raise NotImplementedError("direction-switched HRIR/BRIR rendering is not built yet")
+
+    def set_crossfade(self, new_state=None):
+        """``_convolver.py:868-892``"""
+        self._is_crossfade = (not self._is_crossfade) if new_state is None else bool(new_state)
+        return self._is_crossfade
+
+    def get_input_channel_count(self):
+        return self._sources_deg.shape[0]
+
+    def get_output_channel_count(self):
+        return self._filter._irs_td.shape[1]
+
+
+class AdjustableShConvolver(AdjustableFdConvolver):
+    """Binaural renderer in the spherical-harmonics domain (``_convolver.py:978-1341``)."""
+
+    def __init__(self, filter_set, block_length, source_positions, shared_tracker_data,
+                 n_streams=1, device=None):
+        super().__init__(filter_set, block_length, source_positions, shared_tracker_data,
+                         n_streams=n_streams, device=device)
+        if self._sources_deg.shape[0] > 1:
+            raise NotImplementedError(
+                "more then one virtual source position given, which is not supported yet.")
+        self._sh_m = None
+        self._sh_m_rev_id = None
+        self._sh_cur_order = None
+        self._sh_bases_weighted = None
+        self._comp = None
+        self._comp_arir_config = None
+        self._comp_mrf_limit = None
+        self._comp_nm_override = None
+
+    def __copy__(self):
+        """The reference raises here ("not tested", ``_convolver.py:1051-1060``); this returns an
+        independent renderer with the same tables and switches."""
+        new = type(self)(copy(self._filter), self._block_length,
+                         [tuple(float(v) for v in self._sources_deg[0])], self._tracker_deg,
+                         n_streams=self._n_streams, device=self._device)
+        if self._plan is not None:
+            new._install_tables(self._sh_m, self._sh_bases_weighted, self._comp,
+                                self._comp_arir_config, self._comp_mrf_limit,
+                                self._comp_nm_override, recompute=False)
+            new.set_crossfade(self._is_crossfade)
+            new.set_passthrough(self._is_passthrough)
+            if self._sh_cur_order != self._filter._sh_max_order:
+                new.update_sh_processing(self._sh_cur_order)
+        return new
+
+    def __str__(self):
+        return (f"[{super().__str__()[1:-1]}, _sh_cur_order={self._sh_cur_order}, "
+                f"_is_crossfade={self._is_crossfade}]")
+
+    # -- set-up -------------------------------------------------------------------------------
+    def prepare_sh_processing(self, input_sh_config, mrf_limit_db, compensation_type,
+                              logger=None, comp_nm=None):
+        """Everything that can be computed before real-time operation (``_convolver.py:1071-1120``).
+
+        comp_nm (extension): ready-made compensation spectra [K; 1; F] multiplied into the HRIR
+        coefficients instead of those ``Compensation.generate_by_type`` would design.
+        """
+        from ._compensation import Compensation
+
+        comp = [compensation_type, Compensation.Type.MRF]
+        self._install_tables(input_sh_config.sh_m, input_sh_config.sh_bases_weighted, comp,
+                             input_sh_config.arir_config, mrf_limit_db, comp_nm, logger=logger)
+        if config.IS_DEBUG_MODE:
+            self._debug_filter_block(input_count=self._sh_bases_weighted.shape[-1])
+
+    def _install_tables(self, sh_m, sh_bases_weighted, comp, arir_config, mrf_limit_db, comp_nm,
+                        logger=None, recompute=True):
+        order = self._filter._sh_max_order
+        self._sh_m = np.array(sh_m).copy()
+        self._sh_m_rev_id = sph.reverse_mn_ids(order)
+        self._sh_cur_order = order
+        self._sh_bases_weighted = np.array(sh_bases_weighted).copy()
+        self._comp = comp
+        self._comp_arir_config = arir_config
+        self._comp_mrf_limit = mrf_limit_db
+        self._comp_nm_override = comp_nm
+        if recompute:
+            self._apply_sh_compensation(is_plot=True, logger=logger, upload=False)
+        hnm = self._filter.get_filter_blocks_nm()
+        n_ch = self._sh_bases_weighted.shape[-1]
+        self._plan = ShPlan(self._n_streams, self._block_length, n_ch, order, hnm.shape[-2],
+                            hnm.shape[0], device=self._device)
+        self._plan.set_tables(self._sh_bases_weighted, hnm, self._sh_m, self._sh_m_rev_id,
+                              self._window_in_td, self._window_out_td)
+        self._plan.set_source(float(self._sources_deg[0, 0]), 1 if self._filter._is_hrir else -1)
+        self._plan.set_crossfade(self._is_crossfade)
+        self._plan.set_passthrough(self._is_passthrough)
+
+    def update_sh_processing(self, sh_new_order, logger=None):
+        """Change the rendering order at run time (``_convolver.py:1123-1168``)."""
+        max_order = self._filter._sh_max_order
+        sh_new_order = max_order if sh_new_order is None else int(sh_new_order)
+        if not 0 <= sh_new_order <= max_order:
+            msg = f'value "{sh_new_order}" out of bounds, "set SH processing order" ignored.'
+            logger.error(msg) if logger else print(msg)
+            return
+        if self._sh_cur_order == sh_new_order:
+            return sh_new_order
+        was_running = config.IS_RUNNING.is_set()
+        config.IS_RUNNING.clear()
+        self._sh_cur_order = sh_new_order
+        self._apply_sh_compensation(is_plot=False, logger=logger)
+        self._plan.set_order(sh_new_order)
+        if was_running:
+            config.IS_RUNNING.set()
+        return sh_new_order
+
+    def _apply_sh_compensation(self, is_plot=True, logger=None, upload=True):
+        """(Re)build `_irs_blocks_nm` = SH-transformed HRIR x compensation spectra
+        (``_convolver.py:1171-1220``) and hand it to the device plan."""
+        from ._compensation import Compensation
+
+        self._filter.calculate_filter_blocks_nm()
+        if self._comp_nm_override is not None:
+            comp_nm = self._comp_nm_override
+        else:
+            comp_nm = Compensation.generate_by_type(
+                compensation_types=self._comp, filter_set=self._filter,
+                arir_config=self._comp_arir_config, amp_limit_db=self._comp_mrf_limit,
+                nfft=None, nfft_padded=2 * self._block_length,
+                sh_cur_order=self._sh_cur_order, logger=logger)
+        self._filter._irs_blocks_nm *= comp_nm
+        if upload and self._plan is not None:
+            self._plan.update_filter(self._filter._irs_blocks_nm)
+
+    # -- run time -----------------------------------------------------------------------------
+    def _clear_buffers(self):
+        if self._plan is not None:
+            self._plan.reset()
+
+    def _apply_passthrough(self):
+        if self._plan is not None:
+            self._plan.set_passthrough(self._is_passthrough)
+
+    def set_crossfade(self, new_state=None):
+        """``_convolver.py:1318-1341``: switching off also forgets the previous rotation."""
+        super().set_crossfade(new_state)
+        if self._plan is not None:
+            self._plan.set_crossfade(self._is_crossfade)
+        return self._is_crossfade
+
+    def get_input_channel_count(self):
+        """Array channels once prepared (``_convolver.py:1222-1229``)."""
+        if self._sh_bases_weighted is None:
+            return super().get_input_channel_count()
+        return self._sh_bases_weighted.shape[-1]
+
+    def filter_block(self, input_block_td, yaw_deg=None):
+        """Render one block (``_convolver.py:1231-1316``).
+
+        input [channels; B] float32 -> [2; B] float32 (a fresh, writable array).  The head yaw is
+        read from the shared tracker array (index ``AZIM``, degrees) unless ``yaw_deg`` is given.
+        Batched: input [n_streams; channels; B] with ``yaw_deg`` [n_streams]; torch CUDA tensors
+        stay on the device.
+        """
+        if input_block_td is None:
+            return Convolver.filter_block(self, None)
+        if self._plan is None:
+            raise RuntimeError(self._filter._ERROR_MSG_NM)
+        plan = self._plan
+        if yaw_deg is None:
+            azim = self._tracker_deg[HeadTracker.DataIndex.AZIM] if self._tracker_deg is not None else 0.0
+            yaw_deg = np.full(plan.S, azim, dtype=np.float32)
+        if _is_torch_tensor(input_block_td):
+            import torch
+
+            x = input_block_td.reshape(plan.S, plan.C, plan.B).contiguous()
+            if not _is_torch_tensor(yaw_deg):
+                yaw_deg = torch.as_tensor(np.asarray(yaw_deg, dtype=np.float32), device=x.device)
+            out = torch.empty((plan.S, plan.E, plan.B), dtype=torch.float32, device=x.device)
+            plan.process_device(x, yaw_deg.contiguous(), out, torch.cuda.current_stream(x.device))
+            return out if input_block_td.dim() == 3 else out[0]
+        x = np.asarray(input_block_td, dtype=np.float32)
+        out = plan.process_host(x.reshape(plan.S, plan.C, plan.B), yaw_deg)
+        return out if x.ndim == 3 else out[0]

@@ -1,0 +1,458 @@
+"""FIR filter sets feeding the convolvers -- host-side mirror of ``ReTiSAR/_filter_set.py``.
+
+Same class names, attribute names and array layouts as the reference, because the convolvers
+and ``JackRenderer`` reach into them (``_irs_td``, ``_irs_blocks_fd``, ``_irs_blocks_nm``,
+``_dirac_td``, ``_is_hpcf`` ...).  Everything here runs once at set-up time
+on the host; the per-block work happens in the CUDA library.
+
+Layouts (reference ``_filter_set.py:40-55``, ``:921-924``):
+  _irs_td          [directions; output channels; samples]
+  _irs_blocks_fd   [partitions P; directions; output channels; F = block_length + 1]  complex
+  _irs_blocks_nm   [P; K = (order + 1)^2; output channels; F]                         complex
+"""
+import os
+import sys
+from collections import namedtuple
+from enum import Enum, auto
+
+import numpy as np
+
+from . import sph
+
+SphericalGrid = namedtuple("SphericalGrid", ["azimuth", "colatitude", "radius", "weight"])
+ArrayConfiguration = namedtuple(
+    "ArrayConfiguration",
+    ["array_radius", "array_type", "transducer_type", "scatter_radius", "dual_radius"],
+)
+ArrayConfiguration.__new__.__defaults__ = (None, None)
+
+
+def _as_type(value, enum_cls):
+    """String / enum member / None -> enum member (reference `tools.transform_into_type`)."""
+    if value is None or isinstance(value, enum_cls):
+        return value
+    name = str(value).strip("'\" ").upper()
+    if name in ("", "NONE"):
+        return None
+    try:
+        return enum_cls[name]
+    except KeyError:
+        raise ValueError(f'unknown parameter "{value}", see `{enum_cls.__name__}` for reference!')
+
+
+def _log(logger, msg, warn=False):
+    if logger:
+        (logger.warning if warn else logger.info)(msg)
+    else:
+        print(f"[WARNING]  {msg}" if warn else msg, file=sys.stderr if warn else sys.stdout)
+
+
+def _read_audio(path, dtype):
+    """(samples x channels array, fs) of a WAV file."""
+    try:
+        import soundfile
+
+        return soundfile.read(path, dtype=dtype)
+    except ImportError:
+        from scipy.io import wavfile
+
+        fs, data = wavfile.read(path)
+        if np.issubdtype(data.dtype, np.integer):
+            data = data / float(np.iinfo(data.dtype).max + 1)
+        data = np.asarray(data, dtype=dtype)
+        return (data[:, np.newaxis] if data.ndim == 1 else data), fs
+
+
+def read_miro_struct(path, channel="irChOne"):
+    """MIRO measurement struct (``.mat``) -> (signal [channels; samples], fs, grid, array config).
+
+    Restates ``sound_field_analysis.io.read_miro_struct`` (call sites ``_filter_set.py:982-1055``).
+    """
+    from scipy.io import loadmat
+
+    try:
+        mat = loadmat(path)
+    except FileNotFoundError:
+        raise ValueError(f'file "{path}" not found')
+    if channel not in mat:
+        raise ValueError(f'channel "{channel}" not contained in "{path}"')
+    signal = np.atleast_2d(np.squeeze(mat[channel])).T
+    fs = int(np.squeeze(mat["fs"]))
+    colat = np.squeeze(mat["colatitude"] if "colatitude" in mat else mat["elevation"]).astype(float)
+    if (colat < 0).any():  # stored as elevation
+        colat = np.pi / 2 - colat
+    grid = SphericalGrid(
+        np.squeeze(mat["azimuth"]).astype(float), colat,
+        np.squeeze(mat["radius"]).astype(float), np.squeeze(mat["quadWeight"]).astype(float),
+    )
+    array_type = "rigid" if int(np.squeeze(mat.get("scatterer", 1))) else "open"
+    config = ArrayConfiguration(grid.radius, array_type, "omni", None, None)
+    return signal, fs, grid, config
+
+
+class FilterSet(object):
+    """Base filter set (reference ``FilterSet``, ``_filter_set.py:15-755``)."""
+
+    class Type(Enum):
+        """Identifiers of the supported filter-set kinds (``_filter_set.py:57-141``)."""
+
+        FIR_MULTICHANNEL = auto()
+        HPCF_FIR = auto()
+        HRIR_SSR = auto()
+        BRIR_SSR = auto()
+        HRIR_MIRO = auto()
+        ARIR_MIRO = auto()
+        AS_MIRO = auto()
+        HRIR_SOFA = auto()
+        ARIR_SOFA = auto()
+
+    _ERROR_MSG_FD = "blocks in frequency domain have not been calculated yet."
+    _ERROR_MSG_NM = "blocks in spherical harmonics domain have not been calculated yet."
+
+    @staticmethod
+    def create_instance_by_type(file_name, file_type, sh_max_order=None, sh_is_enforce_pinv=False):
+        """Factory (``_filter_set.py:146-213``); `None` for a missing name / type."""
+        kind = _as_type(file_type, FilterSet.Type)
+        if kind is None or file_name is None:
+            return None
+        if isinstance(file_name, str) and (
+            file_name.strip("'\"") == "" or file_name.upper() == "NONE"
+        ):
+            return None
+        T = FilterSet.Type
+        if kind == T.FIR_MULTICHANNEL:
+            return FilterSetMultiChannel(file_name=file_name, is_hrir=False)
+        if kind == T.HPCF_FIR:
+            return FilterSetMultiChannel(file_name=file_name, is_hrir=False, is_hpcf=True)
+        if kind in (T.HRIR_SSR, T.BRIR_SSR):
+            return FilterSetSsr(file_name=file_name, is_hrir=kind == T.HRIR_SSR)
+        sh_args = dict(sh_max_order=sh_max_order, sh_is_enforce_pinv=sh_is_enforce_pinv)
+        if kind in (T.HRIR_MIRO, T.ARIR_MIRO, T.AS_MIRO):
+            return FilterSetMiro(file_name=file_name, is_hrir=kind == T.HRIR_MIRO, **sh_args)
+        return FilterSetSofa(file_name=file_name, is_hrir=kind == T.HRIR_SOFA, **sh_args)
+
+    def __init__(self, file_name, is_hrir, is_hpcf=False):
+        self._file_name = file_name
+        self._is_hrir = is_hrir
+        self._is_hpcf = is_hpcf
+        self._points_azim_deg = None
+        self._points_elev_deg = None
+        self._fs = None
+        self._irs_td = None
+        self._irs_blocks_fd = None
+        self._dirac_td = None
+        self._dirac_blocks_fd = None
+        self._irs_orig_shape = None
+
+    def __str__(self):
+        fd = None if self._irs_blocks_fd is None else self._irs_blocks_fd.shape
+        td = None if self._irs_td is None else self._irs_td.shape
+        return (f"[ID={id(self)}, _file_name={self._describe_source()}, _fs={self._fs}, "
+                f"_irs_td=shape{td}, _irs_blocks_fd=shape{fd}]")
+
+    def _describe_source(self):
+        if isinstance(self._file_name, str):
+            return os.path.relpath(self._file_name)
+        return f"GENERATED{getattr(self._file_name, 'shape', '')}"
+
+    # -- loading and conditioning (`_filter_set.py:254-356`) ---------------------------------
+    def load(self, block_length, is_single_precision, logger=None, ir_trunc_db=None,
+             check_fs=None, is_prevent_resampling=False, is_prevent_logging=False,
+             is_normalize=False, is_normalize_individually=False):
+        if not is_prevent_logging:
+            _log(logger, f"loading filter {self._describe_source()}")
+        self._load(dtype=np.float32 if is_single_precision else np.float64)
+        if not self._is_hrir:
+            self._points_azim_deg = self._points_elev_deg = None
+        if ir_trunc_db:
+            self._truncate(logger=logger, cutoff_db=ir_trunc_db, block_length=block_length)
+        if not self._fs and check_fs:
+            self._fs = check_fs
+        elif check_fs and check_fs != self._fs:
+            self._resample(logger, check_fs, is_prevent_resampling)
+        if is_normalize_individually or is_normalize:
+            self._normalize(logger=logger, is_individually=is_normalize_individually)
+        self._irs_orig_shape = self._irs_td.shape
+        self._zero_pad(block_length=block_length)
+        self._dirac_td = np.zeros(self._irs_td.shape[-2:], dtype=self._irs_td.dtype)
+        self._dirac_td[:, 0] = 1.0
+
+    def _load(self, dtype):
+        raise NotImplementedError(f'chosen filter type "{type(self)}" is not implemented yet.')
+
+    def _generate_plot_name(self, block_length, logger=None):
+        """Name used for exported plots (``_filter_set.py:358-385``)."""
+        if isinstance(self._file_name, np.ndarray):
+            name = "GENERATED," + str(self._file_name.shape).strip("()").replace(" ", "")
+        else:
+            name = (os.path.basename(os.path.dirname(self._file_name)) + "_"
+                    + os.path.basename(self._file_name).rsplit(".")[0])
+        return f"{logger.name if logger else self.__module__}_{name}_{block_length}"
+
+    def _truncate(self, logger, cutoff_db, block_length):
+        """Cut the IRs where all channels decayed `cutoff_db` below the global peak, rounded up
+        to whole blocks (``_filter_set.py:436-500``)."""
+        if not cutoff_db:
+            return
+        if cutoff_db > 0:
+            raise ValueError("data IR truncation level of greater than 0 given.")
+        data = self._irs_td.copy()
+        data[data == 0] = 1e-12
+        etc_db = 20 * np.log10(np.abs(data))
+        above = np.nonzero(etc_db > cutoff_db + etc_db.max())
+        n_keep = above[-1].max() + 1
+        n_total = self._irs_td.shape[-1]
+        if n_keep >= n_total or (n_keep // block_length + 1) * block_length >= n_total:
+            return
+        _log(logger, f"truncating data length from {n_total} to {n_keep} samples "
+                     f"(cutoff {cutoff_db} dB)", warn=True)
+        self._irs_td = data[:, :, :n_keep].copy()
+
+    def _resample(self, logger, target_fs, is_prevent_resampling=False):
+        """The reference resamples with libsamplerate (``_filter_set.py:502-565``), which is not
+        available here; a sampling-rate mismatch is therefore an error."""
+        if self._fs == target_fs:
+            return
+        msg = f"resampling data from {self._fs} Hz to {target_fs} Hz"
+        if is_prevent_resampling:
+            raise ValueError(f"prevented {msg}")
+        raise NotImplementedError(f"{msg} is not supported (libsamplerate unavailable)")
+
+    def _normalize(self, logger, is_individually=False, target_amp=1.0):
+        """Peak normalisation (``_filter_set.py:567-597``)."""
+        mag = np.abs(self._irs_td)
+        peak = mag.max(axis=(-1, -2), keepdims=True) if is_individually else mag.max()
+        self._irs_td *= target_amp / peak
+
+    def _zero_pad(self, block_length):
+        """Pad with zeros to a whole number (>= 1) of blocks (``_filter_set.py:599-623``)."""
+        if not block_length:
+            return
+        taps = self._irs_td.shape[2]
+        n_blocks = max(-(-taps // block_length), 1)
+        if n_blocks * block_length == taps:
+            return
+        padded = np.zeros(self._irs_td.shape[:2] + (n_blocks * block_length,), dtype=self._irs_td.dtype)
+        padded[:, :, :taps] = self._irs_td
+        self._irs_td = padded
+
+    # -- partition spectra (`_filter_set.py:625-664`) ---------------------------------------
+    def calculate_filter_blocks_fd(self, block_length):
+        """Split the IRs into blocks and transform each (zero-padded to twice its length)."""
+        if not block_length:
+            block_length = self._irs_td.shape[-1]
+        n_blocks = self._irs_td.shape[-1] // block_length
+        parts = self._irs_td[..., : n_blocks * block_length].reshape(
+            self._irs_td.shape[:2] + (n_blocks, block_length))
+        spectra = np.fft.rfft(parts, 2 * block_length, axis=-1)  # [dirs, E, P, F]
+        spectra = np.moveaxis(spectra, 2, 0)
+        cdtype = np.complex64 if self._irs_td.dtype == np.float32 else np.complex128
+        self._irs_blocks_fd = np.ascontiguousarray(spectra.astype(cdtype))
+        self._dirac_blocks_fd = np.zeros_like(self._irs_blocks_fd)[:, :1]
+        self._dirac_blocks_fd[0] = 1.0
+
+    def get_dirac_td(self):
+        return self._dirac_td
+
+    def get_dirac_blocks_fd(self):
+        if self._dirac_blocks_fd is None:
+            raise RuntimeError(FilterSet._ERROR_MSG_FD)
+        return self._dirac_blocks_fd
+
+    def get_filter_td(self, azim_deg=0.0, elev_deg=0.0):
+        return self._irs_td[self._get_index_from_rotation(azim_deg, elev_deg)]
+
+    def get_filter_blocks_fd(self, azim_deg=0.0, elev_deg=0.0):
+        if self._irs_blocks_fd is None:
+            raise RuntimeError(FilterSet._ERROR_MSG_FD)
+        return self._irs_blocks_fd[:, self._get_index_from_rotation(azim_deg, elev_deg)]
+
+    def _get_index_from_rotation(self, azim_deg, elev_deg):
+        raise NotImplementedError(f'chosen filter type "{type(self)}" is not implemented yet.')
+
+
+class FilterSetMultiChannel(FilterSet):
+    """Channel-wise FIR filters without directions (``_filter_set.py:758-840``)."""
+
+    def _load(self, dtype):
+        if isinstance(self._file_name, str):
+            data, self._fs = _read_audio(self._file_name, dtype)
+            self._irs_td = data.T
+        elif isinstance(self._file_name, np.ndarray):
+            self._irs_td = self._file_name
+            self._fs = None
+        else:
+            raise TypeError(f'unknown parameter type "{type(self._file_name)}".')
+        if self._irs_td.ndim < 3:
+            self._irs_td = self._irs_td[np.newaxis, :]
+        self._points_azim_deg = np.zeros(1, dtype=np.int16)
+        self._points_elev_deg = np.zeros_like(self._points_azim_deg)
+
+    def get_filter_blocks_fd(self, azim_deg=0.0, elev_deg=0.0):
+        if self._irs_blocks_fd is None:
+            raise RuntimeError(FilterSet._ERROR_MSG_FD)
+        return self._irs_blocks_fd
+
+    def _get_index_from_rotation(self, azim_deg, elev_deg):
+        return 0
+
+
+class FilterSetSsr(FilterSet):
+    """360 horizontal HRIR / BRIR pairs, SoundScapeRenderer layout (``_filter_set.py:843-899``)."""
+
+    def _load(self, dtype):
+        if not isinstance(self._file_name, str):
+            raise TypeError(f'unknown parameter type "{type(self._file_name)}".')
+        data, self._fs = _read_audio(self._file_name, dtype)
+        left, right = data[:, 0:-1:2].T, data[:, 1::2].T
+        self._irs_td = np.ascontiguousarray(np.stack((left, right), axis=1))
+        self._points_azim_deg = np.linspace(0, 360, self._irs_td.shape[0], endpoint=False,
+                                            dtype=np.int16)
+        self._points_elev_deg = np.zeros_like(self._points_azim_deg)
+
+    def _get_index_from_rotation(self, azim_deg, elev_deg):
+        return int(-azim_deg)  # left-handed SSR grid, rounded towards zero
+
+
+class FilterSetMiro(FilterSet):
+    """HRIR or array IR set on a spherical grid, MIRO format (``_filter_set.py:902-1280``)."""
+
+    def __init__(self, file_name, is_hrir, sh_max_order=None, sh_is_enforce_pinv=False):
+        super().__init__(file_name=file_name, is_hrir=is_hrir)
+        self._sh_max_order = sh_max_order
+        self._sh_is_enforce_pinv = sh_is_enforce_pinv
+        self._irs_grid = None
+        self._irs_blocks_nm = None
+        self._arir_config = None
+
+    @classmethod
+    def from_arrays(cls, irs_td, azimuth, colatitude, weight, sh_max_order, is_hrir, fs=48000,
+                    sh_is_enforce_pinv=False, array_radius=0.042, array_type="rigid"):
+        """Extension: a set from in-memory arrays (the reference only reads files).
+
+        irs_td [directions; ears; samples] for an HRIR, [1; channels; samples] for an array set.
+        Call ``load()`` afterwards as for a file-backed set.
+        """
+        obj = cls("GENERATED", is_hrir, sh_max_order, sh_is_enforce_pinv)
+        obj._arrays = dict(irs_td=np.asarray(irs_td), azimuth=azimuth, colatitude=colatitude,
+                           weight=weight, fs=fs, array_radius=array_radius, array_type=array_type)
+        return obj
+
+    def _describe_source(self):
+        return "GENERATED" if hasattr(self, "_arrays") else super()._describe_source()
+
+    def _generate_plot_name(self, block_length, logger=None):
+        if hasattr(self, "_arrays"):
+            return f"{logger.name if logger else self.__module__}_GENERATED_{block_length}"
+        return super()._generate_plot_name(block_length, logger)
+
+    def _set_grid(self, azimuth, colatitude, radius, weight, dtype):
+        self._irs_grid = SphericalGrid(
+            np.asarray(azimuth, dtype=dtype), np.asarray(colatitude, dtype=dtype),
+            np.asarray(radius, dtype=dtype),
+            None if weight is None else np.asarray(weight, dtype=dtype))
+        if self._is_hrir:
+            self._points_azim_deg = np.rad2deg(self._irs_grid.azimuth)
+            self._points_elev_deg = 90 - np.rad2deg(self._irs_grid.colatitude)
+
+    def _load(self, dtype):
+        if hasattr(self, "_arrays"):
+            a = self._arrays
+            self._irs_td = np.ascontiguousarray(a["irs_td"], dtype=dtype)
+            self._fs = int(a["fs"])
+            self._set_grid(a["azimuth"], a["colatitude"], a["array_radius"], a["weight"], dtype)
+            if not self._is_hrir:
+                r = np.asarray(a["array_radius"], dtype=dtype)
+                self._arir_config = ArrayConfiguration(r, a["array_type"], "omni", r, None)
+            return
+        if not isinstance(self._file_name, str):
+            raise TypeError(f'unknown parameter type "{type(self._file_name)}".')
+        if self._is_hrir:
+            sig_l, fs_l, grid, _ = read_miro_struct(self._file_name, "irChOne")
+            sig_r, fs_r, grid_r, _ = read_miro_struct(self._file_name, "irChTwo")
+            if fs_l != fs_r:
+                raise ValueError("mismatch in left and right ear sampling frequency.")
+            if any(not np.array_equal(a, b) for a, b in zip(grid, grid_r)):
+                raise ValueError("mismatch in left and right ear sampling grid.")
+            self._irs_td = np.stack((sig_l, sig_r), axis=1)
+            fs = fs_l
+        else:
+            sig, fs, grid, cfg = read_miro_struct(self._file_name)
+            self._irs_td = sig[np.newaxis, :]
+            self._arir_config = ArrayConfiguration(
+                *(np.asarray(v, dtype=dtype) if isinstance(v, np.ndarray) else v for v in cfg))
+        self._irs_td = np.ascontiguousarray(self._irs_td, dtype=dtype)
+        self._fs = int(fs)
+        self._set_grid(grid.azimuth, grid.colatitude, grid.radius, grid.weight, dtype)
+
+    def calculate_filter_blocks_nm(self):
+        """SH transform of the HRIR partition spectra (``_filter_set.py:1093-1149``).
+
+        Like the reference this refuses filters longer than one block unless
+        ``allow_partitions`` was set on the instance (extension used by the partitioned renderer).
+        """
+        if self._irs_blocks_fd is None:
+            raise RuntimeError(FilterSet._ERROR_MSG_FD)
+        n_blocks = self._irs_blocks_fd.shape[0]
+        if n_blocks > 1 and not getattr(self, "allow_partitions", False):
+            raise NotImplementedError(
+                f"More than one ({n_blocks}) blocks would be necessary for loaded filter and "
+                f"partitioned convolution in SH domain is not implemented yet.")
+        yw = self.get_sh_configuration().sh_bases_weighted  # [K, directions]
+        # [P, dirs, E, F] -> [P, K, E, F]
+        nm = np.einsum("kd,pdef->pkef", yw, self._irs_blocks_fd)
+        self._irs_blocks_nm = np.ascontiguousarray(nm.astype(self._irs_blocks_fd.dtype))
+
+    def _get_index_from_rotation(self, azim_deg, elev_deg):
+        """Closest stored direction (``_filter_set.py:1151-1186``)."""
+        az = self._points_azim_deg
+        i = min(az.searchsorted(azim_deg, side="left" if azim_deg >= 0 else "right"), az.shape[0] - 1)
+        same_az = np.where(az == az[i])[0]
+        j = min(self._points_elev_deg[same_az].searchsorted(elev_deg), same_az.shape[0] - 1)
+        return same_az[j]
+
+    def get_filter_blocks_fd(self, azim_deg=0.0, elev_deg=0.0):
+        if self._is_hrir:
+            return super().get_filter_blocks_fd(azim_deg, elev_deg)
+        if self._irs_blocks_fd is None:
+            raise RuntimeError(FilterSet._ERROR_MSG_FD)
+        return self._irs_blocks_fd
+
+    def get_filter_blocks_nm(self):
+        if self._irs_blocks_nm is None:
+            raise RuntimeError(FilterSet._ERROR_MSG_NM)
+        return self._irs_blocks_nm
+
+    def get_sh_configuration(self):
+        """Weighted SH basis of the sampling grid (``_filter_set.py:1237-1280``)."""
+        if self._sh_max_order is None or self._sh_max_order < 0:
+            raise ValueError(f'Invalid value "{self._sh_max_order}" for spherical harmonics order.')
+        cdtype = np.complex64 if self._irs_td.dtype == np.float32 else np.complex128
+        sh_m = sph.mn_arrays(self._sh_max_order)[0].astype(np.int16)
+        bases = sph.sph_harm_all(self._sh_max_order, self._irs_grid.azimuth,
+                                 self._irs_grid.colatitude).astype(cdtype)
+        if self._sh_is_enforce_pinv or self._irs_grid.weight is None:
+            weighted = np.linalg.pinv(bases)
+        else:
+            weighted = np.conj(bases).T * (4 * np.pi * self._irs_grid.weight)
+        return FilterSetShConfig(sh_m, weighted, self._arir_config)
+
+
+class FilterSetShConfig(namedtuple("FilterSetShConfig", ["sh_m", "sh_bases_weighted", "arir_config"])):
+    """What the renderer needs to know about the array (``_filter_set.py:1283-1313``)."""
+
+    __slots__ = ()
+
+    def __str__(self):
+        return (f"[sh_m=shape{self.sh_m.shape}, sh_bases_weighted=shape"
+                f"{self.sh_bases_weighted.shape}, arir_config={self.arir_config}]")
+
+
+class FilterSetSofa(FilterSetMiro):
+    """SOFA files (``_filter_set.py:1316-1527``) need a netCDF reader, which this environment
+    lacks; the class exists so that type checks and the factory behave like the reference."""
+
+    def _load(self, dtype):
+        if hasattr(self, "_arrays"):
+            return super()._load(dtype)
+        raise NotImplementedError("reading SOFA files requires a netCDF reader (not available)")

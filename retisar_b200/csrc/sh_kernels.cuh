@@ -19,64 +19,148 @@
 namespace rtb {
 
 // ---------------------------------------------------------------------------------------------
-// K-A: batched real GEMM, one warp per (stream, 32*TT samples, JT rows) tile, no shared memory:
-// x is read once per tile with coalesced vector loads, the analysis matrix through broadcast
-// loads that stay L1-resident.
+// K-A: z[j][t] = sum_c Rm[j][c] x[c][t], the HBM-bound kernel of the chain.
+//
+// Persistent CTAs stream the input tiles [C][TW] of their streams into a ring of shared-memory
+// stages with cp.async.bulk (TMA bulk copy, completion counted on an mbarrier), so that several
+// tiles are in flight per SM regardless of occupancy.  Each warp then computes a (4*JTH rows) x
+// (64 samples) tile with an SGEMM-style register micro-tile: lane = (row group jr = lane/8,
+// column group tc = lane%8) owns JTH rows x 8 samples (two float4 runs, 32 samples apart, so that
+// both the shared-memory reads and the global stores of a quarter warp are contiguous 128 bytes).
+// The analysis matrix chunk is read as [C][32] (each row group padded to 8) from shared memory
+// when all chunks fit, otherwise through the read-only L1 path.
 // ---------------------------------------------------------------------------------------------
-template <int TT> struct VecT;
-template <> struct VecT<1> { using type = float; };
-template <> struct VecT<2> { using type = float2; };
-template <> struct VecT<4> { using type = float4; };
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 
-template <int JT, int TT>
+#define RTB_AN_MAX_STAGES 4
+
+template <int JTH, int NRUN, bool R_SMEM>
 __global__ void __launch_bounds__(128)
 sh_analysis_kernel(const float *__restrict__ x,    // [S][C][B]
-                   const float *__restrict__ rmT,  // [C][Jpad] analysis matrix, transposed
+                   const float *__restrict__ rmP,  // [n_jchunks][C][32] packed analysis matrix
                    float *__restrict__ zcur,       // [S][J][B]
-                   int S, int C, int J, int Jpad, int B, int n_ttiles, int n_jchunks) {
-    using V = typename VecT<TT>::type;
-    const int lane = threadIdx.x & 31;
-    const long long task = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-    const long long total = (long long)S * n_ttiles * n_jchunks;
-    if (task >= total) return;
-    const int jc = (int)(task % n_jchunks);
-    const long long rest = task / n_jchunks;
-    const int tt = (int)(rest % n_ttiles);
-    const int s = (int)(rest / n_ttiles);
-    const int t0 = tt * 32 * TT + lane * TT;
-    const int j0 = jc * JT;
-
-    const float *xp = x + (size_t)s * C * B + t0;
-    const float *rp = rmT + j0;
-    float acc[JT][TT];
-#pragma unroll
-    for (int j = 0; j < JT; ++j)
-#pragma unroll
-        for (int i = 0; i < TT; ++i) acc[j][i] = 0.f;
-
-#pragma unroll 4
-    for (int c = 0; c < C; ++c) {
-        V xv = __ldg(reinterpret_cast<const V *>(xp + (size_t)c * B));
-        const float *xs = reinterpret_cast<const float *>(&xv);
-        float r[JT];
-#pragma unroll
-        for (int j4 = 0; j4 < JT / 4; ++j4) {
-            float4 rv = __ldg(reinterpret_cast<const float4 *>(rp + (size_t)c * Jpad) + j4);
-            r[4 * j4] = rv.x; r[4 * j4 + 1] = rv.y; r[4 * j4 + 2] = rv.z; r[4 * j4 + 3] = rv.w;
-        }
-#pragma unroll
-        for (int j = 0; j < JT; ++j)
-#pragma unroll
-            for (int i = 0; i < TT; ++i) acc[j][i] = fmaf(r[j], xs[i], acc[j][i]);
+                   int S, int C, int J, int B, int TW, int n_jchunks, int stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[RTB_AN_MAX_STAGES], empty_bar[RTB_AN_MAX_STAGES];
+    float *tiles = reinterpret_cast<float *>(smem_raw);
+    const int tile_elems = C * TW;
+    float *rsm = tiles + (size_t)stages * tile_elems;  // [n_jchunks][C][32] when R_SMEM
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jr = lane >> 3, tc = lane & 7;
+    const int n_wtiles = B / TW;  // tiles per stream
+    const long long n_tiles_total = (long long)S * n_wtiles;
+    const long long my_tiles = (n_tiles_total - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (R_SMEM) {
+        const int n4 = n_jchunks * C * 8;
+        for (int i = threadIdx.x; i < n4; i += 128)
+            reinterpret_cast<float4 *>(rsm)[i] = __ldg(reinterpret_cast<const float4 *>(rmP) + i);
+    }
+    __syncthreads();
+
+    auto issue = [&](long long it) {  // warp 0: bulk copies of tile `it` into its stage
+        const long long tile = blockIdx.x + it * gridDim.x;
+        const int st = (int)(it % stages);
+        const long long s = tile / n_wtiles;
+        const int t0 = (int)(tile % n_wtiles) * TW;
+        if (lane == 0) mbar_expect_tx(&full_bar[st], (unsigned)(tile_elems * sizeof(float)));
+        __syncwarp();
+        const float *src = x + ((size_t)s * C) * B + t0;
+        float *dst = tiles + (size_t)st * tile_elems;
+        if (TW == B) {  // the whole [C][B] block of the stream is contiguous
+            if (lane == 0) bulk_copy_g2s(dst, src, (unsigned)(tile_elems * sizeof(float)), &full_bar[st]);
+        } else {
+            for (int c = lane; c < C; c += 32)
+                bulk_copy_g2s(dst + (size_t)c * TW, src + (size_t)c * B, (unsigned)(TW * sizeof(float)), &full_bar[st]);
+        }
+    };
+    if (warp == 0)
+        for (int i = 0; i < stages && i < my_tiles; ++i) issue(i);
+
+    constexpr int WT = 32 * NRUN, NX = 4 * NRUN;  // samples per warp tile / per lane
+    const int n_tsub = TW / WT;
+    const int n_tasks = n_tsub * n_jchunks;
+    for (long long it = 0; it < my_tiles; ++it) {
+        const int st = (int)(it % stages);
+        mbar_wait(&full_bar[st], (unsigned)((it / stages) & 1));
+        const long long tile = blockIdx.x + it * gridDim.x;
+        const long long s = tile / n_wtiles;
+        const int tbase = (int)(tile % n_wtiles) * TW;
+        const float *xs = tiles + (size_t)st * tile_elems;
+        for (int task = warp; task < n_tasks; task += 4) {
+            const int jc = task / n_tsub, ts = task % n_tsub;
+            const int tl = ts * WT + tc * 4;  // first run; the second starts 32 samples later
+            const float *rp = (R_SMEM ? rsm : rmP) + (size_t)jc * C * 32 + jr * 8;
+            float acc[JTH][NX];
 #pragma unroll
-    for (int j = 0; j < JT; ++j) {
-        if (j0 + j < J) {
-            V v;
-            float *vs = reinterpret_cast<float *>(&v);
+            for (int j = 0; j < JTH; ++j)
 #pragma unroll
-            for (int i = 0; i < TT; ++i) vs[i] = acc[j][i];
-            *reinterpret_cast<V *>(zcur + ((size_t)s * J + j0 + j) * B + t0) = v;
+                for (int i = 0; i < NX; ++i) acc[j][i] = 0.f;
+#pragma unroll 4
+            for (int c = 0; c < C; ++c) {
+                float xv[NX];
+#pragma unroll
+                for (int q = 0; q < NRUN; ++q) {
+                    const float4 xa = *reinterpret_cast<const float4 *>(xs + (size_t)c * TW + tl + 32 * q);
+                    xv[4 * q] = xa.x; xv[4 * q + 1] = xa.y; xv[4 * q + 2] = xa.z; xv[4 * q + 3] = xa.w;
+                }
+                float r[8];
+                const float4 *rq = reinterpret_cast<const float4 *>(rp + (size_t)c * 32);
+                const float4 r0 = R_SMEM ? rq[0] : __ldg(rq);
+                r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
+                if (JTH > 4) {
+                    const float4 r1 = R_SMEM ? rq[1] : __ldg(rq + 1);
+                    r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+                }
+#pragma unroll
+                for (int j = 0; j < JTH; ++j)
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) acc[j][i] = fmaf(r[j], xv[i], acc[j][i]);
+            }
+            const int jbase = jc * 4 * JTH + jr * JTH;
+#pragma unroll
+            for (int j = 0; j < JTH; ++j) {
+                if (jbase + j < J) {
+                    float *zp = zcur + ((size_t)s * J + jbase + j) * B + tbase + tl;
+#pragma unroll
+                    for (int q = 0; q < NRUN; ++q)
+                        *reinterpret_cast<float4 *>(zp + 32 * q) =
+                            make_float4(acc[j][4 * q], acc[j][4 * q + 1], acc[j][4 * q + 2], acc[j][4 * q + 3]);
+                }
+            }
+        }
+        // release the stage (one arrival per warp); warp 0 refills it once all four have left,
+        // the other warps run ahead into the next stage
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+        if (warp == 0 && it + stages < my_tiles) {
+            mbar_wait(&empty_bar[st], (unsigned)((it / stages) & 1));
+            issue(it + stages);
         }
     }
 }
@@ -139,199 +223,11 @@ __device__ __forceinline__ float2 phase_of(const float2 *cs, int m) {
     return make_float2(v.x, m < 0 ? v.y : -v.y);
 }
 
-template <int N2>
-__global__ void __launch_bounds__(128)
-sh_render_kernel(const ShRenderParams prm) {
-    using Cfg = FftCfg<N2>;
-    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS;
-    constexpr int B = N2 / 2, F = B + 1;
-    constexpr unsigned FULL = 0xffffffffu;
+}  // namespace rtb
 
-    __shared__ float2 s_tw[N2];
-    __shared__ float2 s_buf[4][GROUPS * Cfg::REGION];
-    __shared__ float2 s_cs[4][2][RTB_MAX_ORDER + 1];
+#include "sh_render.cuh"
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane / G, l = lane % G;
-    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
-    __syncthreads();
-
-    const int s = blockIdx.x * 4 + warp;
-    if (s >= prm.S) return;
-    float2 *buf = s_buf[warp] + grp * Cfg::REGION;
-    const int partner = (G - l) & (G - 1);
-
-    // rotation phases for the current and the previous yaw (a4)
-    const float rad_cur = yaw_deg_to_rad16(prm.yaw_deg[s], prm.tracker_dir, prm.src_azim16);
-    const float rad_last = prm.rad_last_in[s];
-    if (lane <= prm.order_max) {
-        float sn, cs;
-        sincosf((float)lane * rad_cur, &sn, &cs);
-        s_cs[warp][0][lane] = make_float2(cs, sn);
-        sincosf((float)lane * rad_last, &sn, &cs);
-        s_cs[warp][1][lane] = make_float2(cs, sn);
-    }
-    __syncwarp();
-    if (prm.crossfade && lane == 0) prm.rad_last_out[s] = rad_cur;
-
-    // accumulators: [bin slot][cur ear0, cur ear1, last ear0, last ear1]
-    float2 acc[HB + 1][4];
-#pragma unroll
-    for (int u = 0; u <= HB; ++u)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[u][q] = make_float2(0.f, 0.f);
-
-    const size_t zoff = (size_t)s * prm.J * B;
-    const int np = max(prm.np_cur, prm.np_last);
-    for (int p0 = 0; p0 < np; p0 += GROUPS) {
-        const int p = p0 + grp;
-        const bool valid = p < np;
-        ShSignal sg = prm.signals[valid ? p : 0];
-        // ---- a1: overlap-save buffer (previous | current block) of the complex signal
-        float2 X[EPL];
-        {
-            const float *re_prev = prm.zprev + zoff + (size_t)sg.row_re * B + l;
-            const float *re_cur = prm.zcur + zoff + (size_t)sg.row_re * B + l;
-#pragma unroll
-            for (int u = 0; u < HB; ++u) {
-                X[u].x = valid ? __ldg(re_prev + G * u) : 0.f;
-                X[u + HB].x = valid ? __ldg(re_cur + G * u) : 0.f;
-            }
-            if (valid && sg.row_im >= 0) {
-                const float *im_prev = prm.zprev + zoff + (size_t)sg.row_im * B + l;
-                const float *im_cur = prm.zcur + zoff + (size_t)sg.row_im * B + l;
-#pragma unroll
-                for (int u = 0; u < HB; ++u) {
-                    X[u].y = __ldg(im_prev + G * u);
-                    X[u + HB].y = __ldg(im_cur + G * u);
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < EPL; ++u) X[u].y = 0.f;
-            }
-        }
-        warp_fft<N2, false>(X, buf, s_tw, l);
-
-        // ---- a3-a5: HRIR multiply, rotation, sum over SH coefficients
-        const bool in_cur = valid && p < prm.np_cur, in_last = valid && p < prm.np_last;
-        float2 ph1c = make_float2(0.f, 0.f), ph1l = ph1c, ph2c = ph1c, ph2l = ph1c;
-        const bool has2 = sg.m2 != RTB_NO_TERM;
-        if (in_cur) {
-            ph1c = phase_of(s_cs[warp][0], sg.m1);
-            if (has2) ph2c = phase_of(s_cs[warp][0], sg.m2);
-        }
-        if (in_last) {
-            ph1l = phase_of(s_cs[warp][1], sg.m1);
-            if (has2) ph2l = phase_of(s_cs[warp][1], sg.m2);
-        }
-        const float4 *h1 = prm.htab + (size_t)(valid ? p : 0) * 2 * F;
-        const float4 *h2 = h1 + F;
-#pragma unroll
-        for (int u = 0; u <= HB; ++u) {
-            const int f = (u < HB) ? (l + G * u) : B;  // slot HB is the Nyquist bin (lane 0 only)
-            const float2 zf = X[u];
-            {
-                const float4 h = __ldg(h1 + f);
-                const float2 tc = cmul(ph1c, zf), tl = cmul(ph1l, zf);
-                cfma(acc[u][0], make_float2(h.x, h.y), tc);
-                cfma(acc[u][1], make_float2(h.z, h.w), tc);
-                cfma(acc[u][2], make_float2(h.x, h.y), tl);
-                cfma(acc[u][3], make_float2(h.z, h.w), tl);
-            }
-            // element N2-f: slot EPL-1-u of the partner lane (lane 0: own slot EPL-u, bin 0: itself)
-            float2 zp;
-            if (u < HB) {
-                zp.x = __shfl_sync(FULL, X[EPL - 1 - u].x, partner, G);
-                zp.y = __shfl_sync(FULL, X[EPL - 1 - u].y, partner, G);
-                if (l == 0) zp = (u == 0) ? X[0] : X[(EPL - u) % EPL];
-            } else {
-                zp = X[HB];
-            }
-            if (has2) {  // uniform inside a group; groups diverge only on the shuffle-free part
-                const float4 h = __ldg(h2 + f);
-                const float2 zc = make_float2(zp.x, -zp.y);
-                const float2 tc = cmul(ph2c, zc), tl = cmul(ph2l, zc);
-                cfma(acc[u][0], make_float2(h.x, h.y), tc);
-                cfma(acc[u][1], make_float2(h.z, h.w), tc);
-                cfma(acc[u][2], make_float2(h.x, h.y), tl);
-                cfma(acc[u][3], make_float2(h.z, h.w), tl);
-            }
-        }
-    }
-
-    // transforms that ran side by side in one warp each hold a partial sum
-#pragma unroll
-    for (int off = G; off < 32; off <<= 1) {
-#pragma unroll
-        for (int u = 0; u <= HB; ++u)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                acc[u][q].x += __shfl_xor_sync(FULL, acc[u][q].x, off);
-                acc[u][q].y += __shfl_xor_sync(FULL, acc[u][q].y, off);
-            }
-    }
-
-    // ---- a6, a7: Hermitian extension, inverse FFT of (left + i right), discard, cross-fade.
-    // With G < 32 the current-yaw pair is transformed by group 0 and the previous-yaw pair by
-    // group 1 at the same time; with G == 32 the warp does them one after the other.
-    float2 ycur[HB], ylast[HB];
-    constexpr int NITER = (GROUPS >= 2) ? 1 : 2;
-#pragma unroll
-    for (int it = 0; it < NITER; ++it) {
-        const bool use_last = (GROUPS >= 2) ? (grp == 1) : (it == 1);
-        float2 X[EPL], V[HB];
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-            float2 eL = use_last ? acc[u][2] : acc[u][0];
-            float2 eR = use_last ? acc[u][3] : acc[u][1];
-            if (u == 0 && l == 0) { eL.y = 0.f; eR.y = 0.f; }  // irfft ignores Im of the DC bin
-            X[u] = make_float2(eL.x - eR.y, eL.y + eR.x);      // Z(f)    = L + i R
-            V[u] = make_float2(eL.x + eR.y, eR.x - eL.y);      // Z(N2-f) = conj(L) + i conj(R)
-        }
-        const float2 nyq = make_float2(use_last ? acc[HB][2].x : acc[HB][0].x,
-                                       use_last ? acc[HB][3].x : acc[HB][1].x);
-#pragma unroll
-        for (int u2 = HB; u2 < EPL; ++u2) {
-            float2 x;
-            x.x = __shfl_sync(FULL, V[EPL - 1 - u2].x, partner, G);
-            x.y = __shfl_sync(FULL, V[EPL - 1 - u2].y, partner, G);
-            if (l == 0) x = (u2 == HB) ? nyq : V[(EPL - u2) % HB];
-            X[u2] = x;
-        }
-        warp_fft<N2, true>(X, buf, s_tw, l);
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-            if (GROUPS >= 2 || it == 0) ycur[u] = X[u + HB];
-            if (GROUPS >= 2 || it == 1) ylast[u] = X[u + HB];
-        }
-    }
-    if (GROUPS >= 2) {  // bring the previous-yaw block from group 1 to group 0
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-            ylast[u].x = __shfl_sync(FULL, ylast[u].x, (lane + G) & 31);
-            ylast[u].y = __shfl_sync(FULL, ylast[u].y, (lane + G) & 31);
-        }
-    }
-    if (grp == 0) {
-        float *o = prm.out + (size_t)s * 2 * B;
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-            const int n = l + G * u;
-            float yl, yr;
-            if (prm.crossfade) {
-                const float wi = __ldg(prm.win_in + n), wo = __ldg(prm.win_out + n);
-                yl = ycur[u].x * wi + ylast[u].x * wo;
-                yr = ycur[u].y * wi + ylast[u].y * wo;
-            } else {
-                const float sc = 1.0f / (float)N2;
-                yl = ycur[u].x * sc;
-                yr = ycur[u].y * sc;
-            }
-            o[n] = yl;
-            o[B + n] = yr;
-        }
-    }
-}
+namespace rtb {
 
 // a10: passthrough.  irfft(rfft(buffer))[B:] is the current block itself, so the first E input
 // channels are copied to the ears (_convolver.py:558-562); missing channels stay silent.

@@ -2,7 +2,9 @@
 // Reference behaviour: ReTiSAR/_convolver.py AdjustableShConvolver (:978-1341) and the parts of
 // AdjustableFdConvolver / OverlapSaveConvolver it inherits.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -18,6 +20,9 @@ struct rtb_sh_plan {
     bool tables_set = false;
     bool symmetric = false;
     int J = 0, Jpad = 0, JT = 0, TT = 0, n_jchunks = 0, NP = 0;
+    // bulk-copy analysis kernel: tile width, pipeline depth, grid, dynamic smem (0 = not usable)
+    int an_TW = 0, an_stages = 0, an_grid = 0, an_smem = 0, an_nrun = 2;
+    bool an_rsmem = true;
     // device memory
     float *d_rmT = nullptr;       // [C][Jpad]
     float *d_zring = nullptr;     // [2][S][J][B]
@@ -42,6 +47,10 @@ struct rtb_sh_plan {
     float src_azim16 = 0.f;       // _sources_deg[0, 0], already rounded to float16
     float tracker_dir = 1.f;      // +1 HRIR, -1 BRIR
     long long launches = 0;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profiling = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool ev_valid = false;
 };
 
 namespace {
@@ -52,33 +61,36 @@ int signals_for_order(const rtb_sh_plan *p, int order) {
     return p->symmetric ? (order + 1) * (order + 2) / 2 : (order + 1) * (order + 1);
 }
 
-template <int JT, int TT>
+template <int JTH, int NRUN, bool R_SMEM>
 void launch_analysis_t(const rtb_sh_plan *p, const float *d_in, float *zcur, cudaStream_t st) {
-    const int n_ttiles = p->B / (32 * TT);
-    const long long tasks = (long long)p->S * n_ttiles * p->n_jchunks;
-    const unsigned grid = (unsigned)((tasks + 3) / 4);
-    sh_analysis_kernel<JT, TT><<<grid, 128, 0, st>>>(d_in, p->d_rmT, zcur, p->S, p->C, p->J,
-                                                     p->Jpad, p->B, n_ttiles, p->n_jchunks);
+    static bool attr_set = false;  // once per instantiation
+    if (!attr_set) {
+        cudaFuncSetAttribute(sh_analysis_kernel<JTH, NRUN, R_SMEM>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_set = true;
+    }
+    sh_analysis_kernel<JTH, NRUN, R_SMEM><<<p->an_grid, 128, p->an_smem, st>>>(
+        d_in, p->d_rmT, zcur, p->S, p->C, p->J, p->B, p->an_TW, p->n_jchunks, p->an_stages);
 }
 
-template <int JT>
+template <int JTH>
 void launch_analysis_j(const rtb_sh_plan *p, const float *d_in, float *zcur, cudaStream_t st) {
-    switch (p->TT) {
-        case 1: launch_analysis_t<JT, 1>(p, d_in, zcur, st); break;
-        case 2: launch_analysis_t<JT, 2>(p, d_in, zcur, st); break;
-        default: launch_analysis_t<JT, 4>(p, d_in, zcur, st); break;
+    if (p->an_nrun == 1) {
+        if (p->an_rsmem) launch_analysis_t<JTH, 1, true>(p, d_in, zcur, st);
+        else launch_analysis_t<JTH, 1, false>(p, d_in, zcur, st);
+    } else {
+        if (p->an_rsmem) launch_analysis_t<JTH, 2, true>(p, d_in, zcur, st);
+        else launch_analysis_t<JTH, 2, false>(p, d_in, zcur, st);
     }
 }
 
 void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, cudaStream_t st) {
     switch (p->JT) {
-        case 8: launch_analysis_j<8>(p, d_in, zcur, st); break;
-        case 12: launch_analysis_j<12>(p, d_in, zcur, st); break;
-        case 16: launch_analysis_j<16>(p, d_in, zcur, st); break;
-        case 20: launch_analysis_j<20>(p, d_in, zcur, st); break;
-        case 24: launch_analysis_j<24>(p, d_in, zcur, st); break;
-        case 28: launch_analysis_j<28>(p, d_in, zcur, st); break;
-        default: launch_analysis_j<32>(p, d_in, zcur, st); break;
+        case 4: launch_analysis_j<4>(p, d_in, zcur, st); break;
+        case 5: launch_analysis_j<5>(p, d_in, zcur, st); break;
+        case 6: launch_analysis_j<6>(p, d_in, zcur, st); break;
+        case 7: launch_analysis_j<7>(p, d_in, zcur, st); break;
+        default: launch_analysis_j<8>(p, d_in, zcur, st); break;
     }
 }
 
@@ -256,16 +268,19 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     }
     const int J = (int)rows.size(), NP = (int)sig.size();
 
-    // K-A tiling: rows per warp tile (multiple of 4) minimising padded work + per-tile overhead
-    int bestJT = 8, bestCost = 1 << 30;
-    for (int jt = 8; jt <= 32; jt += 4) {
-        const int chunks = (J + jt - 1) / jt, cost = chunks * (jt + 6);
-        if (cost <= bestCost) { bestCost = cost; bestJT = jt; }
+    // K-A tiling: a warp tile has 4 row groups of JTH rows; choose JTH minimising padded work
+    // plus a per-chunk overhead, then pack the analysis matrix as [chunk][C][4 groups x 8]
+    int bestJT = 4, bestCost = 1 << 30;
+    for (int jth = 4; jth <= 8; ++jth) {
+        const int chunks = (J + 4 * jth - 1) / (4 * jth), cost = chunks * (4 * jth + 4);
+        if (cost <= bestCost) { bestCost = cost; bestJT = jth; }
     }
-    const int n_jchunks = (J + bestJT - 1) / bestJT, Jpad = n_jchunks * bestJT;
-    std::vector<float> rmT((size_t)C * Jpad, 0.f);
-    for (int j = 0; j < J; ++j)
-        for (int c = 0; c < C; ++c) rmT[(size_t)c * Jpad + j] = rows[j][c];
+    const int n_jchunks = (J + 4 * bestJT - 1) / (4 * bestJT), Jpad = n_jchunks * 4 * bestJT;
+    std::vector<float> rmT((size_t)n_jchunks * C * 32, 0.f);
+    for (int j = 0; j < J; ++j) {
+        const int jc = j / (4 * bestJT), jr = (j % (4 * bestJT)) / bestJT, jj = j % bestJT;
+        for (int c = 0; c < C; ++c) rmT[((size_t)jc * C + c) * 32 + jr * 8 + jj] = rows[j][c];
+    }
 
     p->sig_k1 = sig_k1; p->sig_k2 = sig_k2; p->sig_sign2 = sig_sign2;
     std::vector<float4> htab = build_htab(p, hnm);
@@ -303,7 +318,30 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
 
     p->symmetric = symmetric;
     p->J = J; p->Jpad = Jpad; p->JT = bestJT; p->n_jchunks = n_jchunks; p->NP = NP;
-    p->TT = B >= 128 ? 4 : (B == 64 ? 2 : 1);
+    {   // bulk-copy pipeline of the analysis kernel: widest tile that leaves room for >= 2 stages
+        const size_t rbytes = (size_t)n_jchunks * C * 32 * sizeof(float);
+        p->an_rsmem = rbytes <= 48 * 1024;
+        const size_t budget = 200 * 1024 - (p->an_rsmem ? rbytes : 0);
+        p->an_TW = 0;
+        for (int nrun = (B >= 64 ? 2 : 1); nrun >= 1 && !p->an_TW; --nrun) {
+            p->an_nrun = nrun;
+            for (int tw = B; tw >= 32 * nrun; tw /= 2)
+                if (2 * (size_t)C * tw * sizeof(float) <= budget) { p->an_TW = tw; break; }
+        }
+        if (!p->an_TW) p->an_TW = 32;
+        const size_t tile = (size_t)C * p->an_TW * sizeof(float);
+        if (2 * tile > budget)
+            return fail(RTB_ERR_UNSUPPORTED, "%d array channels do not fit the analysis kernel's tiles", C);
+        size_t stage_budget = 68 * 1024;  // three CTAs per SM when the tiles are small
+        if (const char *env = getenv("RTB_AN_STAGE_KB")) stage_budget = (size_t)atoi(env) * 1024;
+        p->an_stages = (int)std::min<size_t>(RTB_AN_MAX_STAGES, std::max<size_t>(2, stage_budget / tile));
+        p->an_smem = (int)(p->an_stages * tile + (p->an_rsmem ? rbytes : 0));
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device);
+        const int ctas_per_sm = std::max(1, std::min(4, (int)((224 * 1024) / (p->an_smem + 2048))));
+        const long long tiles = (long long)p->S * (B / p->an_TW);
+        p->an_grid = (int)std::min<long long>(tiles, (long long)n_sm * ctas_per_sm);
+    }
     p->slot = 0; p->rad_idx = 0;
     p->cur_order = p->last_order = p->order;
     p->last_valid = false;
@@ -353,6 +391,16 @@ int rtb_sh_plan_set_crossfade(rtb_sh_plan *p, int on) {
     return RTB_OK;
 }
 
+int rtb_sh_plan_set_profiling(rtb_sh_plan *p, int on) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    DeviceGuard guard(p->device);
+    if (on && !p->ev[0])
+        for (auto &e : p->ev) RTB_CUDA(cudaEventCreate(&e));
+    p->profiling = on != 0;
+    p->ev_valid = false;
+    return RTB_OK;
+}
+
 int rtb_sh_plan_reset(rtb_sh_plan *p) {
     if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
     if (!p->tables_set) return RTB_OK;
@@ -374,8 +422,10 @@ int rtb_sh_process_block(rtb_sh_plan *p, const float *d_in, const float *d_yaw_d
     float *zcur = p->d_zring + (size_t)p->slot * zhalf;
     const float *zprev = p->d_zring + (size_t)(p->slot ^ 1) * zhalf;
 
+    if (p->profiling) cudaEventRecord(p->ev[0], st);
     launch_analysis(p, d_in, zcur, st);  // a1/a2: the overlap-save state advances in every mode
     p->launches++;
+    if (p->profiling) cudaEventRecord(p->ev[1], st);
     if (p->passthrough) {
         const long long total = (long long)p->S * p->E * p->B;
         sh_passthrough_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_in, d_out, p->S, p->C, p->E, p->B);
@@ -403,6 +453,7 @@ int rtb_sh_process_block(rtb_sh_plan *p, const float *d_in, const float *d_yaw_d
             p->last_order = p->cur_order;
         }
     }
+    if (p->profiling) { cudaEventRecord(p->ev[2], st); p->ev_valid = true; }
     p->slot ^= 1;
     RTB_CUDA(cudaGetLastError());
     return RTB_OK;
@@ -438,6 +489,17 @@ int rtb_sh_plan_query(rtb_sh_plan *p, int what, int64_t *value) {
         case RTB_Q_SIGNALS: *value = p->NP; break;
         case RTB_Q_LAUNCHES: *value = p->launches; break;
         case RTB_Q_STATE_BYTES: *value = (int64_t)sizeof(float) * (2 * (int64_t)p->J * p->B + 2); break;
+        case RTB_Q_ANALYSIS_NS:
+        case RTB_Q_RENDER_NS: {
+            if (!p->profiling || !p->ev_valid) return fail(RTB_ERR_STATE, "profiling is off or no block was processed");
+            DeviceGuard guard(p->device);
+            RTB_CUDA(cudaEventSynchronize(p->ev[2]));
+            float ms = 0.f;
+            const int i = what == RTB_Q_ANALYSIS_NS ? 0 : 1;
+            RTB_CUDA(cudaEventElapsedTime(&ms, p->ev[i], p->ev[i + 1]));
+            *value = (int64_t)(ms * 1e6);
+            break;
+        }
         default: return fail(RTB_ERR_INVALID, "unknown query %d", what);
     }
     return RTB_OK;
@@ -450,6 +512,7 @@ int rtb_sh_plan_destroy(rtb_sh_plan *p) {
     cudaFree(p->d_tw); cudaFree(p->d_win_in); cudaFree(p->d_win_out); cudaFree(p->d_radlast);
     cudaFree(p->d_in); cudaFree(p->d_yaw); cudaFree(p->d_out);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
     return RTB_OK;
 }

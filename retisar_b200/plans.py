@@ -95,6 +95,9 @@ class ShPlan:
         check(lib.rtb_sh_plan_query(self._h, what, ctypes.byref(v)))
         return v.value
 
+    def set_profiling(self, on):
+        check(lib.rtb_sh_plan_set_profiling(self._h, int(bool(on))))
+
     def process_host(self, x, yaw_deg, out=None):
         """x [S,C,B] float32 host, yaw_deg [S] float32 host -> out [S,E,B] float32 host."""
         x = np.ascontiguousarray(x, dtype=np.float32)

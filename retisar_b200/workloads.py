@@ -1,0 +1,72 @@
+"""Synthetic render-chain configurations of BASELINE.json, shared by
+``bench.py`` and the tests.  All data is seeded and generated in memory."""
+import numpy as np
+
+from . import synthetic as syn
+from ._filter_set import FilterSetMiro
+
+FS = 48000
+
+# name -> (array grid, SH order, block length, HRIR taps, description)
+CONFIGS = {
+    "c2": dict(grid="em32", order=4, block=256, hrir_taps=128,
+               desc="Eigenmike em32 (32 ch), SH order 4, 256-sample block, 128-tap KU100-shaped HRIR"),
+    "c5": dict(grid="le110", order=8, block=256, hrir_taps=128,
+               desc="Lebedev 110-point array, SH order 8, 256-sample block, 128-tap HRIR"),
+    "c4": dict(grid="rnd434", order=12, block=64, hrir_taps=64,
+               desc="434-point array, SH order 12 (169 coeffs), 64-sample low-latency block"),
+}
+
+
+def _grid(name):
+    if name == "rnd434":  # no 434-point grid ships with the reference: pseudo-random + pinv
+        az, co = syn.random_sphere_grid(434, 434)
+        return az, co, None
+    return syn.load_array_grid(name)
+
+
+def sh_tables(name, hrir_dirs=2702, seed=7):
+    """Filter sets and tables of one configuration.
+
+    Returns dict(array_set, hrir_set, sh_config, comp_nm, B, order, C, K, F): the HRIR set is
+    "KU100-shaped" (2702 directions, the reference's default set ``config.py:48``) on a seeded
+    pseudo-random grid with pinv weights (SOFA sets carry none); compensation = identity.
+    """
+    c = CONFIGS[name]
+    B, order = c["block"], c["order"]
+    az, co, w = _grid(c["grid"])
+    array_set = FilterSetMiro.from_arrays(np.zeros((1, len(az), B), np.float32), az, co, w, order,
+                                          is_hrir=False)
+    array_set.load(B, True, is_prevent_logging=True)
+    haz, hco = syn.random_sphere_grid(hrir_dirs, seed)
+    hrir_set = FilterSetMiro.from_arrays(
+        syn.decaying_noise_irs((hrir_dirs, 2, c["hrir_taps"]), seed + 1), haz, hco, None, order,
+        is_hrir=True)
+    hrir_set.load(B, True, is_prevent_logging=True)
+    K, F = (order + 1) ** 2, B + 1
+    return dict(array_set=array_set, hrir_set=hrir_set, sh_config=array_set.get_sh_configuration(),
+                comp_nm=np.ones((K, 1, F), np.complex64), B=B, order=order, C=len(az), K=K, F=F,
+                desc=c["desc"])
+
+
+def make_renderer(tables, n_streams, device=None):
+    """``AdjustableShConvolver`` for `n_streams` batched streams, prepared and ready to run."""
+    from ._convolver import Convolver
+
+    conv = Convolver.create_instance_by_filter_set(
+        tables["hrir_set"], tables["B"], [(0, 0)], None, n_streams=n_streams, device=device)
+    conv.prepare_sh_processing(tables["sh_config"], 0, None, comp_nm=tables["comp_nm"])
+    return conv
+
+
+def chain_bytes_per_stream_block(C, B, E=2):
+    """Compulsory HBM bytes of the whole chain per stream and block:
+    read current block + read previous-block overlap state + write output + yaw."""
+    return 4 * B * (2 * C + E) + 12
+
+
+def chain_flops_per_stream_block(C, K, B, E=2):
+    """fp32 flops of the reference formulation per stream and block."""
+    F, N2 = B + 1, 2 * B
+    fft = 2.5 * N2 * np.log2(N2)
+    return C * fft + 8 * K * C * F + 6 * K * E * F + 2 * 8 * K * E * F + 2 * E * fft + 3 * E * B
