@@ -111,7 +111,8 @@ int rtb_ols_plan_reset(rtb_ols_plan *plan);
 /* OverlapSaveConvolver.filter_block (_convolver.py:524-571): d_in [S][n_in][B] -> d_out [S][n_out][B] */
 int rtb_ols_process_block(rtb_ols_plan *plan, const float *d_in, float *d_out, void *cuda_stream);
 int rtb_ols_process_block_host(rtb_ols_plan *plan, const float *h_in, float *h_out);
-int rtb_ols_plan_query(rtb_ols_plan *plan, int what, int64_t *value);
+int rtb_ols_plan_query(rtb_ols_plan *plan, int what, int64_t *value); /* RTB_Q_LAUNCHES, _STATE_BYTES, _RENDER_NS */
+int rtb_ols_plan_set_profiling(rtb_ols_plan *plan, int on);
 int rtb_ols_plan_destroy(rtb_ols_plan *plan);
 
 #ifdef __cplusplus

@@ -41,6 +41,7 @@ SIGNATURES = {
     "rtb_ols_process_block": (_i, [_vp, _vp, _vp, _vp]),
     "rtb_ols_process_block_host": (_i, [_vp, _vp, _vp]),
     "rtb_ols_plan_query": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
+    "rtb_ols_plan_set_profiling": (_i, [_vp, _i]),
     "rtb_ols_plan_destroy": (_i, [_vp]),
 }
 

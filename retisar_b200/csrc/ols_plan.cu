@@ -1,21 +1,392 @@
-// Uniformly partitioned overlap-save FIR convolver (reference: OverlapSaveConvolver,
-// ReTiSAR/_convolver.py:436-669).  Implementation pending: entry points report RTB_ERR_UNSUPPORTED.
-#include "rtb_common.cuh"
+// Uniformly partitioned overlap-save FIR convolver for S batched streams (reference:
+// OverlapSaveConvolver, ReTiSAR/_convolver.py:436-669; used for the ARIR pre-renderer, the
+// headphone compensation filter and the reference's own benchmark).
+//
+// Formulation.  The reference keeps an OUTPUT-side queue: every block adds H[p] * X_t into queue
+// slot p for all partitions p and emits slot 0 (:602-622, :645-665).  The filters are time
+// invariant, so the same output is y_t = irfft( sum_p H[p] * X_(t-p) ): an INPUT-side delay line of
+// the last P input spectra.  That needs one spectrum write plus P spectrum reads per block instead
+// of P read-modify-writes, i.e. half the HBM traffic for 2-in/2-out and ~Cout times less for the
+// mono-in ARIR case, and it is what this kernel implements (the "FDL kernel" of the north star).
+// Passthrough (:558-562) overrides queue slot 0 with X_t and adds nothing to later slots; here the
+// block is flagged so that later sums skip it.
+//
+// One warp owns a pair of output channels of one stream: a single complex FFT transforms both
+// real overlap-save buffers (or the mono buffer), the multiply-accumulate over the delay line
+// runs in registers on the bins the lane owns, and one complex inverse FFT returns both channels.
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "fft_warp.cuh"
 
 using namespace rtb;
 
+namespace {
+
+struct OlsParams {
+    const float *x;            // [S][Cin][B] current input block
+    const float *xprev;        // [S][Cin][B] previous input block (state, read side)
+    float *xnext;              // [S][Cin][B] state, write side (ping-pong)
+    float2 *hist;              // [S][P][Cin][Fp] delay line of input spectra, ring over P
+    const float2 *hfd;         // [P][Cout][Fp] filter partition spectra
+    unsigned char *incl;       // [P] ring slot takes part in later sums (0 after a passthrough block)
+    const float2 *tw;          // [N2]
+    float *out;                // [S][Cout][B]
+    int S, Cin, Cout, P, Fp, slot, passthrough;
+};
+
+template <int N2>
+__global__ void __launch_bounds__(128)
+ols_fdl_kernel(const OlsParams prm) {
+    using Cfg = FftCfg<N2>;
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS;
+    constexpr int B = N2 / 2;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    __shared__ float2 s_tw[N2];
+    __shared__ __align__(16) float2 s_buf[4][GROUPS * Cfg::REGION];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, l = lane % G;
+    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+    __syncthreads();
+
+    const int npairs = (prm.Cout + 1) / 2;
+    const long long task = ((long long)blockIdx.x * 4 + warp) * GROUPS + grp;
+    const bool valid = task < (long long)prm.S * npairs;
+    // a warp whose groups are all out of range has nothing to do (uniform exit)
+    if (((long long)blockIdx.x * 4 + warp) * GROUPS >= (long long)prm.S * npairs) return;
+    const int s = valid ? (int)(task / npairs) : 0;
+    const int pair = valid ? (int)(task % npairs) : 0;
+    const int co0 = 2 * pair, co1 = 2 * pair + 1;
+    const bool has1 = co1 < prm.Cout;
+    const bool mono = prm.Cin == 1 && prm.Cout > 1;
+    const int ci0 = mono ? 0 : co0, ci1 = mono ? 0 : co1;
+    float2 *buf = s_buf[warp] + grp * Cfg::REGION;
+    const int partner = (G - l) & (G - 1);
+
+    // ---- a1: overlap-save buffers (previous | current block) of both channels, one complex FFT
+    float2 X[EPL];
+    {
+        const size_t r0 = ((size_t)s * prm.Cin + ci0) * B + l;
+        const size_t r1 = ((size_t)s * prm.Cin + ci1) * B + l;
+        const bool second = valid && has1 && !mono;
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            X[u].x = valid ? prm.xprev[r0 + G * u] : 0.f;
+            X[u + HB].x = valid ? prm.x[r0 + G * u] : 0.f;
+            X[u].y = second ? prm.xprev[r1 + G * u] : 0.f;
+            X[u + HB].y = second ? prm.x[r1 + G * u] : 0.f;
+        }
+        // state: the current block becomes the previous one (written once per input channel)
+        if (valid && (!mono || pair == 0)) {
+#pragma unroll
+            for (int u = 0; u < HB; ++u) {
+                prm.xnext[r0 + G * u] = X[u + HB].x;
+                if (second) prm.xnext[r1 + G * u] = X[u + HB].y;
+            }
+        }
+    }
+    warp_fft<N2, false>(X, buf, s_tw, l);
+
+    // separate the two real signals on the bins this lane owns: slot u <-> bin l + G*u, slot HB
+    // is the Nyquist bin (lane 0)
+    float2 X0[HB + 1], X1[HB + 1];
+#pragma unroll
+    for (int u = 0; u <= HB; ++u) {
+        const float2 zf = X[u];
+        float2 zp;
+        if (u < HB) {
+            zp.x = __shfl_sync(FULL, X[EPL - 1 - u].x, partner, G);
+            zp.y = __shfl_sync(FULL, X[EPL - 1 - u].y, partner, G);
+            if (l == 0) zp = (u == 0) ? X[0] : X[(EPL - u) % EPL];
+        } else {
+            zp = X[HB];
+        }
+        // Z = A + iB with A, B Hermitian: A(f) = (Z(f) + conj Z(-f)) / 2, B(f) = (Z(f) - conj Z(-f)) / 2i
+        X0[u] = make_float2(0.5f * (zf.x + zp.x), 0.5f * (zf.y - zp.y));
+        X1[u] = mono ? X0[u] : make_float2(0.5f * (zf.y + zp.y), 0.5f * (zp.x - zf.x));
+    }
+
+    // delay line: store X_t, then accumulate sum_p H[p] * X_(t-p)
+    const int Fp = prm.Fp;
+    const bool own_nyq = (l == 0);
+    if (valid && (!mono || pair == 0)) {
+        float2 *h0 = prm.hist + (((size_t)s * prm.P + prm.slot) * prm.Cin + ci0) * Fp;
+        float2 *h1 = prm.hist + (((size_t)s * prm.P + prm.slot) * prm.Cin + ci1) * Fp;
+#pragma unroll
+        for (int u = 0; u <= HB; ++u) {
+            const int f = l + G * u;
+            if (u < HB || own_nyq) {
+                h0[f] = X0[u];
+                if (has1 && !mono) h1[f] = X1[u];
+            }
+        }
+    }
+    float2 Y0[HB + 1], Y1[HB + 1];
+    if (prm.passthrough) {  // queue slot 0 := X_t (_convolver.py:558-562)
+#pragma unroll
+        for (int u = 0; u <= HB; ++u) { Y0[u] = X0[u]; Y1[u] = X1[u]; }
+    } else {
+        const float2 *g0 = prm.hfd + (size_t)co0 * Fp;
+        const float2 *g1 = prm.hfd + (size_t)(has1 ? co1 : co0) * Fp;
+#pragma unroll
+        for (int u = 0; u <= HB; ++u) {
+            const int f = l + G * u;
+            const bool ok = valid && (u < HB || own_nyq);
+            const float2 a = ok ? __ldg(g0 + f) : make_float2(0.f, 0.f);
+            const float2 b = ok ? __ldg(g1 + f) : make_float2(0.f, 0.f);
+            Y0[u] = cmul(a, X0[u]);
+            Y1[u] = cmul(b, X1[u]);
+        }
+        int hs = prm.slot;
+        for (int p = 1; p < prm.P; ++p) {
+            hs = (hs == 0) ? prm.P - 1 : hs - 1;
+            if (!prm.incl[hs]) continue;  // uniform: that block ran in passthrough
+            const float2 *x0 = prm.hist + (((size_t)s * prm.P + hs) * prm.Cin + ci0) * Fp;
+            const float2 *x1 = prm.hist + (((size_t)s * prm.P + hs) * prm.Cin + ci1) * Fp;
+            const float2 *gp0 = g0 + (size_t)p * prm.Cout * Fp;
+            const float2 *gp1 = g1 + (size_t)p * prm.Cout * Fp;
+            float2 xa[HB + 1], xb[HB + 1], ga[HB + 1], gb[HB + 1];
+#pragma unroll
+            for (int u = 0; u <= HB; ++u) {
+                const int f = l + G * u;
+                const bool ok = valid && (u < HB || own_nyq);
+                xa[u] = ok ? __ldcs(x0 + f) : make_float2(0.f, 0.f);
+                ga[u] = ok ? __ldg(gp0 + f) : make_float2(0.f, 0.f);
+                if (!mono) xb[u] = (ok && has1) ? __ldcs(x1 + f) : make_float2(0.f, 0.f);
+                gb[u] = (ok && has1) ? __ldg(gp1 + f) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u <= HB; ++u) {
+                cfma(Y0[u], ga[u], xa[u]);
+                cfma(Y1[u], gb[u], mono ? xa[u] : xb[u]);
+            }
+        }
+    }
+
+    // ---- a6: Hermitian extension of (Y0 + i Y1), inverse FFT, keep the second half
+    {
+        float2 V[HB];
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            float2 eL = Y0[u], eR = has1 ? Y1[u] : make_float2(0.f, 0.f);
+            if (u == 0 && l == 0) { eL.y = 0.f; eR.y = 0.f; }
+            X[u] = make_float2(eL.x - eR.y, eL.y + eR.x);
+            V[u] = make_float2(eL.x + eR.y, eR.x - eL.y);
+        }
+        const float2 nyq = make_float2(Y0[HB].x, has1 ? Y1[HB].x : 0.f);
+#pragma unroll
+        for (int u2 = HB; u2 < EPL; ++u2) {
+            float2 x;
+            x.x = __shfl_sync(FULL, V[EPL - 1 - u2].x, partner, G);
+            x.y = __shfl_sync(FULL, V[EPL - 1 - u2].y, partner, G);
+            if (l == 0) x = (u2 == HB) ? nyq : V[(EPL - u2) % HB];
+            X[u2] = x;
+        }
+    }
+    __syncwarp();
+    warp_fft<N2, true>(X, buf, s_tw, l);
+    if (valid) {
+        const float sc = 1.0f / (float)N2;
+        float *o0 = prm.out + ((size_t)s * prm.Cout + co0) * B + l;
+        float *o1 = prm.out + ((size_t)s * prm.Cout + (has1 ? co1 : co0)) * B + l;
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            o0[G * u] = X[u + HB].x * sc;
+            if (has1) o1[G * u] = X[u + HB].y * sc;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) prm.incl[prm.slot] = prm.passthrough ? 0 : 1;
+}
+
+}  // namespace
+
+struct rtb_ols_plan {
+    int device = 0;
+    int S = 0, B = 0, Cin = 0, Cout = 0, P = 0, F = 0, Fp = 0, N2 = 0;
+    bool filter_set = false;
+    float *d_xstate = nullptr;   // [2][S][Cin][B]
+    float2 *d_hist = nullptr;    // [S][P][Cin][Fp]
+    float2 *d_hfd = nullptr;     // [P][Cout][Fp]
+    unsigned char *d_incl = nullptr;
+    float2 *d_tw = nullptr;
+    float *d_in = nullptr, *d_out = nullptr;  // staging of the host entry point
+    cudaStream_t own_stream = nullptr;
+    int slot = 0, par = 0;
+    bool passthrough = false;
+    long long launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool ev_valid = false;
+};
+
+namespace {
+size_t hist_elems(const rtb_ols_plan *p) { return (size_t)p->S * p->P * p->Cin * p->Fp; }
+size_t state_elems(const rtb_ols_plan *p) { return (size_t)p->S * p->Cin * p->B; }
+}  // namespace
+
 extern "C" {
 
-int rtb_ols_plan_create(rtb_ols_plan **plan, int, int, int, int, int, int) {
-    if (plan) *plan = nullptr;
-    return fail(RTB_ERR_UNSUPPORTED, "partitioned overlap-save convolver not built yet");
+int rtb_ols_plan_create(rtb_ols_plan **out, int device, int n_streams, int block_length, int n_in,
+                        int n_out, int n_partitions) {
+    if (!out) return fail(RTB_ERR_INVALID, "plan output pointer is NULL");
+    *out = nullptr;
+    if (n_streams < 1 || n_out < 1 || n_partitions < 1)
+        return fail(RTB_ERR_INVALID, "n_streams, n_out and n_partitions must be >= 1");
+    if (n_in != n_out && n_in != 1)
+        return fail(RTB_ERR_INVALID, "channel-wise convolver: n_in must equal n_out or be 1 (got %d, %d)", n_in, n_out);
+    if (block_length != 32 && block_length != 64 && block_length != 128 && block_length != 256)
+        return fail(RTB_ERR_UNSUPPORTED, "block length %d not supported (supported: 32, 64, 128, 256)", block_length);
+    int ndev = 0;
+    RTB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(RTB_ERR_INVALID, "no CUDA device %d", device);
+    rtb_ols_plan *p = new (std::nothrow) rtb_ols_plan();
+    if (!p) return fail(RTB_ERR_NOMEM, "out of host memory");
+    p->device = device; p->S = n_streams; p->B = block_length; p->Cin = n_in; p->Cout = n_out;
+    p->P = n_partitions; p->F = block_length + 1; p->Fp = (p->F + 3) / 4 * 4; p->N2 = 2 * block_length;
+    DeviceGuard guard(device);
+    cudaError_t err = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_xstate, sizeof(float) * 2 * state_elems(p));
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_hist, sizeof(float2) * hist_elems(p));
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_hfd, sizeof(float2) * (size_t)p->P * p->Cout * p->Fp);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_incl, p->P);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_tw, sizeof(float2) * p->N2);
+    if (err != cudaSuccess) {
+        rtb_ols_plan_destroy(p);
+        return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
+                    "plan allocation failed: %s", cudaGetErrorString(err));
+    }
+    std::vector<float2> tw(p->N2);
+    for (int q = 0; q < p->N2; ++q) {
+        const double a = -2.0 * M_PI * q / p->N2;
+        tw[q] = make_float2((float)cos(a), (float)sin(a));
+    }
+    RTB_CUDA(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * p->N2, cudaMemcpyHostToDevice));
+    *out = p;
+    return rtb_ols_plan_reset(p);
 }
-int rtb_ols_plan_set_filter(rtb_ols_plan *, const float *) { return fail(RTB_ERR_UNSUPPORTED, "not built yet"); }
-int rtb_ols_plan_set_passthrough(rtb_ols_plan *, int) { return fail(RTB_ERR_UNSUPPORTED, "not built yet"); }
-int rtb_ols_plan_reset(rtb_ols_plan *) { return fail(RTB_ERR_UNSUPPORTED, "not built yet"); }
-int rtb_ols_process_block(rtb_ols_plan *, const float *, float *, void *) { return fail(RTB_ERR_UNSUPPORTED, "not built yet"); }
-int rtb_ols_process_block_host(rtb_ols_plan *, const float *, float *) { return fail(RTB_ERR_UNSUPPORTED, "not built yet"); }
-int rtb_ols_plan_query(rtb_ols_plan *, int, int64_t *) { return fail(RTB_ERR_UNSUPPORTED, "not built yet"); }
-int rtb_ols_plan_destroy(rtb_ols_plan *) { return RTB_OK; }
+
+int rtb_ols_plan_set_filter(rtb_ols_plan *p, const float *hfd) {
+    if (!p || !hfd) return fail(RTB_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(p->device);
+    std::vector<float2> h((size_t)p->P * p->Cout * p->Fp, make_float2(0.f, 0.f));
+    for (int q = 0; q < p->P; ++q)
+        for (int c = 0; c < p->Cout; ++c)
+            for (int f = 0; f < p->F; ++f) {
+                const size_t i = ((size_t)q * p->Cout + c) * p->F + f;
+                h[((size_t)q * p->Cout + c) * p->Fp + f] = make_float2(hfd[2 * i], hfd[2 * i + 1]);
+            }
+    RTB_CUDA(cudaDeviceSynchronize());
+    RTB_CUDA(cudaMemcpy(p->d_hfd, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+    p->filter_set = true;
+    return RTB_OK;
+}
+
+int rtb_ols_plan_set_passthrough(rtb_ols_plan *p, int on) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    p->passthrough = on != 0;
+    return RTB_OK;
+}
+
+int rtb_ols_plan_reset(rtb_ols_plan *p) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    DeviceGuard guard(p->device);
+    // _input_block_td.fill(0); _blocks_fd.fill(0)  (_convolver.py:500-505)
+    RTB_CUDA(cudaMemset(p->d_xstate, 0, sizeof(float) * 2 * state_elems(p)));
+    RTB_CUDA(cudaMemset(p->d_hist, 0, sizeof(float2) * hist_elems(p)));
+    RTB_CUDA(cudaMemset(p->d_incl, 0, p->P));
+    return RTB_OK;
+}
+
+int rtb_ols_process_block(rtb_ols_plan *p, const float *d_in, float *d_out, void *cuda_stream) {
+    if (!p || !d_in || !d_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (!p->filter_set) return fail(RTB_ERR_STATE, "blocks in frequency domain have not been calculated yet.");
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    OlsParams prm;
+    prm.x = d_in;
+    prm.xprev = p->d_xstate + (size_t)p->par * state_elems(p);
+    prm.xnext = p->d_xstate + (size_t)(p->par ^ 1) * state_elems(p);
+    prm.hist = p->d_hist; prm.hfd = p->d_hfd; prm.incl = p->d_incl; prm.tw = p->d_tw; prm.out = d_out;
+    prm.S = p->S; prm.Cin = p->Cin; prm.Cout = p->Cout; prm.P = p->P; prm.Fp = p->Fp;
+    prm.slot = p->slot; prm.passthrough = p->passthrough ? 1 : 0;
+    const long long pairs = (long long)p->S * ((p->Cout + 1) / 2);
+    if (p->profiling) cudaEventRecord(p->ev[0], st);
+    switch (p->N2) {
+        case 64: ols_fdl_kernel<64><<<(unsigned)((pairs + 15) / 16), 128, 0, st>>>(prm); break;
+        case 128: ols_fdl_kernel<128><<<(unsigned)((pairs + 7) / 8), 128, 0, st>>>(prm); break;
+        case 256: ols_fdl_kernel<256><<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(prm); break;
+        default: ols_fdl_kernel<512><<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(prm); break;
+    }
+    if (p->profiling) { cudaEventRecord(p->ev[1], st); p->ev_valid = true; }
+    p->launches++;
+    p->slot = (p->slot + 1) % p->P;
+    p->par ^= 1;
+    RTB_CUDA(cudaGetLastError());
+    return RTB_OK;
+}
+
+int rtb_ols_process_block_host(rtb_ols_plan *p, const float *h_in, float *h_out) {
+    if (!p || !h_in || !h_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(p->device);
+    const size_t n_in = state_elems(p), n_out = (size_t)p->S * p->Cout * p->B;
+    if (!p->d_in) {
+        cudaError_t err = cudaMalloc(&p->d_in, sizeof(float) * n_in);
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_out, sizeof(float) * n_out);
+        if (err != cudaSuccess) return fail(RTB_ERR_NOMEM, "staging allocation failed: %s", cudaGetErrorString(err));
+    }
+    RTB_CUDA(cudaMemcpyAsync(p->d_in, h_in, sizeof(float) * n_in, cudaMemcpyHostToDevice, p->own_stream));
+    int rc = rtb_ols_process_block(p, p->d_in, p->d_out, p->own_stream);
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaMemcpyAsync(h_out, p->d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost, p->own_stream));
+    RTB_CUDA(cudaStreamSynchronize(p->own_stream));
+    return RTB_OK;
+}
+
+int rtb_ols_plan_set_profiling(rtb_ols_plan *p, int on) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    DeviceGuard guard(p->device);
+    if (on && !p->ev[0])
+        for (auto &e : p->ev) RTB_CUDA(cudaEventCreate(&e));
+    p->profiling = on != 0;
+    p->ev_valid = false;
+    return RTB_OK;
+}
+
+int rtb_ols_plan_query(rtb_ols_plan *p, int what, int64_t *value) {
+    if (!p || !value) return fail(RTB_ERR_INVALID, "NULL argument");
+    switch (what) {
+        case RTB_Q_LAUNCHES: *value = p->launches; break;
+        case RTB_Q_STATE_BYTES:
+            *value = (int64_t)sizeof(float2) * p->P * p->Cin * p->Fp + (int64_t)sizeof(float) * 2 * p->Cin * p->B;
+            break;
+        case RTB_Q_RENDER_NS: {
+            if (!p->profiling || !p->ev_valid) return fail(RTB_ERR_STATE, "profiling is off or no block was processed");
+            DeviceGuard guard(p->device);
+            RTB_CUDA(cudaEventSynchronize(p->ev[1]));
+            float ms = 0.f;
+            RTB_CUDA(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]));
+            *value = (int64_t)(ms * 1e6);
+            break;
+        }
+        default: return fail(RTB_ERR_INVALID, "unknown query %d", what);
+    }
+    return RTB_OK;
+}
+
+int rtb_ols_plan_destroy(rtb_ols_plan *p) {
+    if (!p) return RTB_OK;
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_xstate); cudaFree(p->d_hist); cudaFree(p->d_hfd); cudaFree(p->d_incl); cudaFree(p->d_tw);
+    cudaFree(p->d_in); cudaFree(p->d_out);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    delete p;
+    return RTB_OK;
+}
 
 }  // extern "C"

@@ -150,6 +150,9 @@ class OlsPlan:
         check(lib.rtb_ols_plan_query(self._h, what, ctypes.byref(v)))
         return v.value
 
+    def set_profiling(self, on):
+        check(lib.rtb_ols_plan_set_profiling(self._h, int(bool(on))))
+
     def process_host(self, x, out=None):
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.shape != (self.S, self.n_in, self.B):
