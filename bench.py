@@ -183,12 +183,10 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from retisar_b200.distributed import gather_streams, max_over_ranks as _max
+
     def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max(v, device=dev)
 
     S, K, W = args.streams, args.steps, max(args.warmup, 3)
     tb = wl.sh_tables(args.workload)
@@ -273,9 +271,9 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if sampler else None
 
     # ---- gather one output block from every rank (the only collective; off the timed path)
-    if dist is not None:
-        gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
-        dist.gather(out, gathered, dst=0)
+    gathered = gather_streams(out, dst=0)
+    if rank == 0 and dist is not None:
+        assert gathered.shape[0] == world * S and bool(torch.isfinite(gathered).all())
 
     if rank == 0:
         peaks = {}

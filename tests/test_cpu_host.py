@@ -1,0 +1,207 @@
+"""CPU-side tests: C ABI export check, host mirror of the filter sets against the reference
+goldens, the float16 yaw recipe the kernels implement, multi-rank plumbing over gloo."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    """The .so loads without a GPU and exports exactly what include/retisar_b200.h declares."""
+    import ctypes
+
+    from retisar_b200 import _capi
+
+    header = open(os.path.join(ROOT, "include", "retisar_b200.h")).read()
+    declared = set(re.findall(r"\b(rtb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(_capi.library_path())
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    assert _capi.lib.rtb_version() >= 100
+
+
+def test_no_product_module_imports_the_oracle():
+    pkg = os.path.join(ROOT, "retisar_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+@pytest.mark.parametrize("name", ["tables_em32_n4", "tables_le110_n8_pinv", "tables_rnd50_n3"])
+def test_filter_set_tables_match_reference(name):
+    """FilterSetMiro.get_sh_configuration / calculate_filter_blocks_fd / _nm vs the reference
+    (fp32 tables; summation order differs, tolerance 1e-6 of the table peak)."""
+    from retisar_b200._filter_set import FilterSetMiro
+
+    g = load_golden(name)
+    B, order = int(g["B"]), int(g["order"])
+    w = g["w"] if g["w"].size else None
+    arr = FilterSetMiro.from_arrays(np.zeros((1, len(g["az"]), B), np.float32), g["az"], g["co"], w,
+                                    order, is_hrir=False, sh_is_enforce_pinv=bool(g["enforce_pinv"]))
+    arr.load(B, True, is_prevent_logging=True)
+    cfg = arr.get_sh_configuration()
+    assert np.array_equal(cfg.sh_m, g["sh_m"]) and cfg.sh_m.dtype == np.int16
+    assert cfg.sh_bases_weighted.dtype == np.complex64
+    np.testing.assert_allclose(cfg.sh_bases_weighted, g["Yw"], atol=1e-6 * np.abs(g["Yw"]).max())
+    assert cfg.arir_config is not None
+
+    h = FilterSetMiro.from_arrays(g["hrir_td"], g["hrir_az"], g["hrir_co"], None, order, is_hrir=True)
+    h.load(B, True, is_prevent_logging=True)
+    assert list(h._irs_td.shape) == list(g["hrir_td_padded_shape"])
+    assert h.get_dirac_td().shape == h._irs_td.shape[-2:] and h.get_dirac_td()[0, 0] == 1
+    with pytest.raises(RuntimeError):
+        h.get_dirac_blocks_fd()
+    h.calculate_filter_blocks_fd(B)
+    np.testing.assert_allclose(h._irs_blocks_fd, g["hrir_blocks_fd"], atol=1e-6)
+    assert h.get_dirac_blocks_fd().shape == h._irs_blocks_fd[:, :1].shape
+    with pytest.raises(RuntimeError):
+        h.get_filter_blocks_nm()
+    h.calculate_filter_blocks_nm()
+    np.testing.assert_allclose(h.get_filter_blocks_nm(), g["hrir_blocks_nm"],
+                               atol=1e-6 * np.abs(g["hrir_blocks_nm"]).max())
+    assert h.get_sh_configuration().arir_config is None
+
+
+def test_filter_set_factory_and_errors():
+    from retisar_b200 import FilterSet
+    from retisar_b200._filter_set import (FilterSetMiro, FilterSetMultiChannel, FilterSetSofa,
+                                          FilterSetSsr)
+
+    assert FilterSet.create_instance_by_type(None, "FIR_MULTICHANNEL") is None
+    assert FilterSet.create_instance_by_type("NONE", "HRIR_SSR") is None
+    assert FilterSet.create_instance_by_type("x.wav", None) is None
+    irs = np.zeros((2, 300), np.float32)
+    irs[:, 0] = 1
+    fs = FilterSet.create_instance_by_type(irs, FilterSet.Type.FIR_MULTICHANNEL)
+    assert type(fs) is FilterSetMultiChannel and not fs._is_hpcf
+    assert FilterSet.create_instance_by_type(irs, "HPCF_FIR")._is_hpcf
+    assert type(FilterSet.create_instance_by_type("a.wav", "BRIR_SSR")) is FilterSetSsr
+    assert type(FilterSet.create_instance_by_type("a.mat", "AS_MIRO", 4)) is FilterSetMiro
+    assert type(FilterSet.create_instance_by_type("a.sofa", "HRIR_SOFA", 4)) is FilterSetSofa
+    with pytest.raises(ValueError):
+        FilterSet.create_instance_by_type("a.wav", "NO_SUCH_TYPE")
+    fs.load(block_length=128, is_single_precision=True, is_prevent_logging=True)
+    assert fs._irs_td.shape == (1, 2, 384) and fs._irs_orig_shape == (1, 2, 300)  # zero padded
+    fs.calculate_filter_blocks_fd(128)
+    assert fs.get_filter_blocks_fd().shape == (3, 1, 2, 129)
+    with pytest.raises(TypeError):
+        FilterSetSsr(3.0, True)._load(np.float32)
+    with pytest.raises(ValueError):
+        FilterSetMiro("x", True, sh_max_order=None).get_sh_configuration()
+    # longer than one block: SH-domain partitions are refused like the reference
+    g = load_golden("tables_rnd50_n3")
+    h = FilterSetMiro.from_arrays(np.zeros((24, 2, 200), np.float32), g["hrir_az"], g["hrir_co"],
+                                  None, 3, is_hrir=True)
+    h.load(64, True, is_prevent_logging=True)
+    h.calculate_filter_blocks_fd(64)
+    with pytest.raises(NotImplementedError):
+        h.calculate_filter_blocks_nm()
+    # truncation: decayed tail is cut to whole blocks
+    t = FilterSet.create_instance_by_type(
+        (np.exp(-np.arange(4096) / 50.0)[None] * np.ones((2, 1))).astype(np.float32), "FIR_MULTICHANNEL")
+    t.load(block_length=256, is_single_precision=True, is_prevent_logging=True, ir_trunc_db=-60)
+    assert t._irs_td.shape[-1] == 512
+
+
+def test_miro_struct_reader(tmp_path):
+    from scipy.io import savemat
+
+    from retisar_b200._filter_set import FilterSetMiro
+
+    n = 12
+    rng = np.random.default_rng(0)
+    savemat(tmp_path / "arr.mat", dict(
+        fs=np.array([[48000]], np.uint16), azimuth=rng.uniform(0, 6, (1, n)),
+        colatitude=rng.uniform(0.1, 3, (1, n)), quadWeight=np.full((1, n), 1.0 / n),
+        radius=np.array([[0.042]]), scatterer=np.array([[1]], np.uint8),
+        irChOne=rng.standard_normal((100, n)).astype(np.float32)))
+    fs = FilterSetMiro(str(tmp_path / "arr.mat"), is_hrir=False, sh_max_order=2)
+    fs.load(64, True, is_prevent_logging=True)
+    assert fs._irs_td.shape == (1, n, 128) and fs._fs == 48000
+    cfg = fs.get_sh_configuration()
+    assert cfg.sh_bases_weighted.shape == (9, n) and cfg.arir_config.array_type == "rigid"
+
+
+def test_yaw_recipe_in_float32_matches_reference_float16_chain():
+    """The CUDA kernel evaluates the float16 chain with float32 ops + round-to-half
+    (sh_kernels.cuh: yaw_deg_to_rad16).  Same arithmetic in numpy vs the reference's values."""
+    g = load_golden("yaw_chain")
+
+    def rn16(v):
+        return np.float32(np.float16(v))
+
+    with np.errstate(all="ignore"):
+        for tag, src, direction in (("hrir", 0.0, 1.0), ("src", float(g["src_azim"]), 1.0),
+                                    ("brir", 0.0, -1.0)):
+            src16 = rn16(np.float32(src))
+            for i, t in enumerate(g["yaw"]):
+                a = rn16(np.float32(direction) * np.float32(t))
+                a = rn16(a + src16)
+                a = rn16(a + np.float32(360.0))
+                r = np.fmod(a, np.float32(360.0))
+                if r != 0 and r < 0:
+                    r = r + np.float32(360.0)
+                r = rn16(r)
+                ref_az = np.float32(g[f"az_{tag}"][i])
+                assert (np.isnan(r) and np.isnan(ref_az)) or r == ref_az, (t, r, ref_az)
+                rad = rn16(r * np.float32(0.017453292519943295))
+                ph = g[f"ph_{tag}"][i]
+                m = g["sh_m"].astype(np.float32)
+                if np.isnan(rad):
+                    assert np.all(np.isnan(ph.real))
+                    continue
+                np.testing.assert_allclose(ph.real, np.cos(m * rad), atol=3e-7)
+                np.testing.assert_allclose(ph.imag, -np.sin(m * rad), atol=3e-7)
+
+
+def test_stream_shard_partitions_all_streams():
+    from retisar_b200.distributed import stream_shard
+
+    for total, world in ((8192, 8), (1000, 3), (5, 8), (1, 1)):
+        ranges = [stream_shard(total, world, r) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [b - a for a, b in ranges]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        stream_shard(4, 2, 2)
+
+
+def _gloo_worker(rank, world, port, results):
+    import torch
+    import torch.distributed as dist
+
+    from retisar_b200.distributed import gather_streams, max_over_ranks, stream_shard
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a, b = stream_shard(5, world, rank)
+        block = torch.arange(a, b, dtype=torch.float32).reshape(-1, 1, 1).repeat(1, 2, 4)
+        full = gather_streams(block, dst=0)
+        worst = max_over_ranks(1.0 + rank)
+        if rank == 0:
+            results["gathered"] = full[:, 0, 0].tolist()
+            results["max"] = worst
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gather_and_timing_over_gloo():
+    """world_size 2 on CPU: every stream id arrives exactly once at rank 0; timings reduce to max."""
+    import torch.multiprocessing as mp
+
+    mgr = mp.get_context("spawn").Manager()
+    results = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port, results), nprocs=2, join=True)
+    assert results["gathered"] == [0.0, 1.0, 2.0, 3.0, 4.0]
+    assert results["max"] == 2.0
