@@ -12,6 +12,8 @@
 
 using namespace rtb;
 
+#define RTB_MAX_CHUNKS 4
+
 struct rtb_sh_plan {
     int device = 0;
     int S = 0, B = 0, C = 0, order = 0, K = 0, E = 2, P = 1;
@@ -33,7 +35,8 @@ struct rtb_sh_plan {
     float *d_radlast = nullptr;   // [2][S]
     // staging for the host-buffer entry point
     float *d_in = nullptr, *d_yaw = nullptr, *d_out = nullptr;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, d2h_stream = nullptr, k_stream = nullptr;
+    cudaEvent_t chunk_ev[2 * RTB_MAX_CHUNKS] = {};
     // control state (reference attribute it mirrors)
     int slot = 0;                 // which half of d_zring receives the current block
     int rad_idx = 0;              // which half of d_radlast holds the previous yaw
@@ -62,40 +65,42 @@ int signals_for_order(const rtb_sh_plan *p, int order) {
 }
 
 template <int JTH, int NRUN, bool R_SMEM>
-void launch_analysis_t(const rtb_sh_plan *p, const float *d_in, float *zcur, cudaStream_t st) {
+void launch_analysis_t(const rtb_sh_plan *p, const float *d_in, float *zcur, int count, cudaStream_t st) {
     static bool attr_set = false;  // once per instantiation
     if (!attr_set) {
         cudaFuncSetAttribute(sh_analysis_kernel<JTH, NRUN, R_SMEM>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_set = true;
     }
-    sh_analysis_kernel<JTH, NRUN, R_SMEM><<<p->an_grid, 128, p->an_smem, st>>>(
-        d_in, p->d_rmT, zcur, p->S, p->C, p->J, p->B, p->an_TW, p->n_jchunks, p->an_stages);
+    const long long tiles = (long long)count * (p->B / p->an_TW);
+    const int grid = (int)std::min<long long>(tiles, (long long)p->an_grid);
+    sh_analysis_kernel<JTH, NRUN, R_SMEM><<<grid, 128, p->an_smem, st>>>(
+        d_in, p->d_rmT, zcur, count, p->C, p->J, p->B, p->an_TW, p->n_jchunks, p->an_stages);
 }
 
 template <int JTH>
-void launch_analysis_j(const rtb_sh_plan *p, const float *d_in, float *zcur, cudaStream_t st) {
+void launch_analysis_j(const rtb_sh_plan *p, const float *d_in, float *zcur, int count, cudaStream_t st) {
     if (p->an_nrun == 1) {
-        if (p->an_rsmem) launch_analysis_t<JTH, 1, true>(p, d_in, zcur, st);
-        else launch_analysis_t<JTH, 1, false>(p, d_in, zcur, st);
+        if (p->an_rsmem) launch_analysis_t<JTH, 1, true>(p, d_in, zcur, count, st);
+        else launch_analysis_t<JTH, 1, false>(p, d_in, zcur, count, st);
     } else {
-        if (p->an_rsmem) launch_analysis_t<JTH, 2, true>(p, d_in, zcur, st);
-        else launch_analysis_t<JTH, 2, false>(p, d_in, zcur, st);
+        if (p->an_rsmem) launch_analysis_t<JTH, 2, true>(p, d_in, zcur, count, st);
+        else launch_analysis_t<JTH, 2, false>(p, d_in, zcur, count, st);
     }
 }
 
-void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, cudaStream_t st) {
+void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int count, cudaStream_t st) {
     switch (p->JT) {
-        case 4: launch_analysis_j<4>(p, d_in, zcur, st); break;
-        case 5: launch_analysis_j<5>(p, d_in, zcur, st); break;
-        case 6: launch_analysis_j<6>(p, d_in, zcur, st); break;
-        case 7: launch_analysis_j<7>(p, d_in, zcur, st); break;
-        default: launch_analysis_j<8>(p, d_in, zcur, st); break;
+        case 4: launch_analysis_j<4>(p, d_in, zcur, count, st); break;
+        case 5: launch_analysis_j<5>(p, d_in, zcur, count, st); break;
+        case 6: launch_analysis_j<6>(p, d_in, zcur, count, st); break;
+        case 7: launch_analysis_j<7>(p, d_in, zcur, count, st); break;
+        default: launch_analysis_j<8>(p, d_in, zcur, count, st); break;
     }
 }
 
 void launch_render(const rtb_sh_plan *p, const ShRenderParams &prm, cudaStream_t st) {
-    const unsigned grid = (unsigned)((p->S + 3) / 4);
+    const unsigned grid = (unsigned)((prm.S + 3) / 4);
     switch (p->N2) {
         case 64: sh_render_kernel<64><<<grid, 128, 0, st>>>(prm); break;
         case 128: sh_render_kernel<128><<<grid, 128, 0, st>>>(prm); break;
@@ -339,8 +344,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device);
         const int ctas_per_sm = std::max(1, std::min(4, (int)((224 * 1024) / (p->an_smem + 2048))));
-        const long long tiles = (long long)p->S * (B / p->an_TW);
-        p->an_grid = (int)std::min<long long>(tiles, (long long)n_sm * ctas_per_sm);
+        p->an_grid = n_sm * ctas_per_sm;  // persistent CTAs; capped by the tile count at launch
     }
     p->slot = 0; p->rad_idx = 0;
     p->cur_order = p->last_order = p->order;
@@ -410,6 +414,52 @@ int rtb_sh_plan_reset(rtb_sh_plan *p) {
     return RTB_OK;
 }
 
+namespace {
+
+// kernels for streams [s0, s0 + count) of the current block; in/yaw/out point at stream s0
+void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const float *d_yaw_deg,
+                  float *d_out, cudaStream_t st) {
+    const size_t zhalf = (size_t)p->S * p->J * p->B, zo = (size_t)s0 * p->J * p->B;
+    float *zcur = p->d_zring + (size_t)p->slot * zhalf + zo;
+    const float *zprev = p->d_zring + (size_t)(p->slot ^ 1) * zhalf + zo;
+    launch_analysis(p, d_in, zcur, count, st);  // a1/a2: the overlap-save state advances in every mode
+    p->launches++;
+    if (p->profiling && s0 == 0) cudaEventRecord(p->ev[1], st);
+    if (p->passthrough) {
+        const long long total = (long long)count * p->E * p->B;
+        sh_passthrough_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_in, d_out, count, p->C, p->E, p->B);
+    } else {
+        ShRenderParams prm;
+        prm.zprev = zprev; prm.zcur = zcur;
+        prm.htab = p->d_htab; prm.signals = p->d_signals; prm.tw = p->d_tw;
+        prm.win_in = p->d_win_in; prm.win_out = p->d_win_out;
+        prm.yaw_deg = d_yaw_deg;
+        prm.rad_last_in = p->d_radlast + (size_t)p->rad_idx * p->S + s0;
+        prm.rad_last_out = p->d_radlast + (size_t)(p->rad_idx ^ 1) * p->S + s0;
+        prm.out = d_out;
+        prm.S = count; prm.J = p->J; prm.B = p->B;
+        prm.np_cur = signals_for_order(p, p->cur_order);
+        prm.np_last = (p->crossfade && p->last_valid) ? signals_for_order(p, p->last_order) : 0;
+        prm.order_max = p->order;
+        prm.crossfade = p->crossfade ? 1 : 0;
+        prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
+        launch_render(p, prm, st);
+    }
+    p->launches++;
+}
+
+// block boundary: flip the ping-pong state once all ranges of the block are enqueued
+void advance_block(rtb_sh_plan *p) {
+    if (!p->passthrough && p->crossfade) {  // _last_sh_azim_nm = sh_azim_nm (_convolver.py:1311)
+        p->rad_idx ^= 1;
+        p->last_valid = true;
+        p->last_order = p->cur_order;
+    }
+    p->slot ^= 1;
+}
+
+}  // namespace
+
 int rtb_sh_process_block(rtb_sh_plan *p, const float *d_in, const float *d_yaw_deg, float *d_out,
                          void *cuda_stream) {
     if (!p || !d_in || !d_out) return fail(RTB_ERR_INVALID, "NULL argument");
@@ -418,66 +468,59 @@ int rtb_sh_process_block(rtb_sh_plan *p, const float *d_in, const float *d_yaw_d
     if (!d_yaw_deg && !p->passthrough) return fail(RTB_ERR_INVALID, "NULL yaw pointer");
     DeviceGuard guard(p->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const size_t zhalf = (size_t)p->S * p->J * p->B;
-    float *zcur = p->d_zring + (size_t)p->slot * zhalf;
-    const float *zprev = p->d_zring + (size_t)(p->slot ^ 1) * zhalf;
-
     if (p->profiling) cudaEventRecord(p->ev[0], st);
-    launch_analysis(p, d_in, zcur, st);  // a1/a2: the overlap-save state advances in every mode
-    p->launches++;
-    if (p->profiling) cudaEventRecord(p->ev[1], st);
-    if (p->passthrough) {
-        const long long total = (long long)p->S * p->E * p->B;
-        sh_passthrough_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_in, d_out, p->S, p->C, p->E, p->B);
-        p->launches++;
-    } else {
-        ShRenderParams prm;
-        prm.zprev = zprev; prm.zcur = zcur;
-        prm.htab = p->d_htab; prm.signals = p->d_signals; prm.tw = p->d_tw;
-        prm.win_in = p->d_win_in; prm.win_out = p->d_win_out;
-        prm.yaw_deg = d_yaw_deg;
-        prm.rad_last_in = p->d_radlast + (size_t)p->rad_idx * p->S;
-        prm.rad_last_out = p->d_radlast + (size_t)(p->rad_idx ^ 1) * p->S;
-        prm.out = d_out;
-        prm.S = p->S; prm.J = p->J; prm.B = p->B;
-        prm.np_cur = signals_for_order(p, p->cur_order);
-        prm.np_last = (p->crossfade && p->last_valid) ? signals_for_order(p, p->last_order) : 0;
-        prm.order_max = p->order;
-        prm.crossfade = p->crossfade ? 1 : 0;
-        prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
-        launch_render(p, prm, st);
-        p->launches++;
-        if (p->crossfade) {  // _last_sh_azim_nm = sh_azim_nm (_convolver.py:1311)
-            p->rad_idx ^= 1;
-            p->last_valid = true;
-            p->last_order = p->cur_order;
-        }
-    }
+    launch_range(p, 0, p->S, d_in, d_yaw_deg, d_out, st);
     if (p->profiling) { cudaEventRecord(p->ev[2], st); p->ev_valid = true; }
-    p->slot ^= 1;
+    advance_block(p);
     RTB_CUDA(cudaGetLastError());
     return RTB_OK;
 }
 
 int rtb_sh_process_block_host(rtb_sh_plan *p, const float *h_in, const float *h_yaw_deg, float *h_out) {
     if (!p || !h_in || !h_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (!p->tables_set)
+        return fail(RTB_ERR_STATE, "blocks in spherical harmonics domain have not been calculated yet.");
     if (!h_yaw_deg && !p->passthrough) return fail(RTB_ERR_INVALID, "NULL yaw pointer");
     DeviceGuard guard(p->device);
-    const size_t n_in = (size_t)p->S * p->C * p->B, n_out = (size_t)p->S * p->E * p->B;
+    const size_t in_per = (size_t)p->C * p->B, out_per = (size_t)p->E * p->B;
     if (!p->d_in) {
-        cudaError_t err = cudaMalloc(&p->d_in, sizeof(float) * n_in);
-        if (err == cudaSuccess) err = cudaMalloc(&p->d_out, sizeof(float) * n_out);
+        cudaError_t err = cudaMalloc(&p->d_in, sizeof(float) * p->S * in_per);
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_out, sizeof(float) * p->S * out_per);
         if (err == cudaSuccess) err = cudaMalloc(&p->d_yaw, sizeof(float) * p->S);
         if (err == cudaSuccess) err = cudaMemset(p->d_yaw, 0, sizeof(float) * p->S);
+        if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking);
+        if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&p->k_stream, cudaStreamNonBlocking);
+        for (auto &e : p->chunk_ev)
+            if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         if (err != cudaSuccess) return fail(RTB_ERR_NOMEM, "staging allocation failed: %s", cudaGetErrorString(err));
     }
-    RTB_CUDA(cudaMemcpyAsync(p->d_in, h_in, sizeof(float) * n_in, cudaMemcpyHostToDevice, p->own_stream));
+    // Software pipeline over chunks of streams on three streams: input copies run back to back,
+    // the kernels of chunk i overlap the copy of chunk i+1, and result copies go the other way
+    // over the full-duplex link.
+    cudaStream_t st_in = p->own_stream, st_k = p->k_stream, st_out = p->d2h_stream;
     if (h_yaw_deg)
-        RTB_CUDA(cudaMemcpyAsync(p->d_yaw, h_yaw_deg, sizeof(float) * p->S, cudaMemcpyHostToDevice, p->own_stream));
-    int rc = rtb_sh_process_block(p, p->d_in, p->d_yaw, p->d_out, p->own_stream);
-    if (rc != RTB_OK) return rc;
-    RTB_CUDA(cudaMemcpyAsync(h_out, p->d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost, p->own_stream));
-    RTB_CUDA(cudaStreamSynchronize(p->own_stream));
+        RTB_CUDA(cudaMemcpyAsync(p->d_yaw, h_yaw_deg, sizeof(float) * p->S, cudaMemcpyHostToDevice, st_in));
+    // Measured on B200 (PCIe Gen5 x16): the input copy is ~97 % of the step and runs at 42-45 GB/s
+    // either way, so chunking buys nothing and costs event overhead; default is a single chunk.
+    int n_chunks = 1;
+    if (const char *env = getenv("RTB_HOST_CHUNKS")) n_chunks = std::max(1, std::min(RTB_MAX_CHUNKS, atoi(env)));
+    n_chunks = std::min(n_chunks, std::max(1, p->S / 256));
+    const int per = (p->S + n_chunks - 1) / n_chunks;
+    for (int c = 0, s0 = 0; s0 < p->S; ++c, s0 += per) {
+        const int count = std::min(per, p->S - s0);
+        RTB_CUDA(cudaMemcpyAsync(p->d_in + s0 * in_per, h_in + s0 * in_per, sizeof(float) * count * in_per,
+                                 cudaMemcpyHostToDevice, st_in));
+        RTB_CUDA(cudaEventRecord(p->chunk_ev[2 * c], st_in));
+        RTB_CUDA(cudaStreamWaitEvent(st_k, p->chunk_ev[2 * c], 0));
+        launch_range(p, s0, count, p->d_in + s0 * in_per, p->d_yaw + s0, p->d_out + s0 * out_per, st_k);
+        RTB_CUDA(cudaEventRecord(p->chunk_ev[2 * c + 1], st_k));
+        RTB_CUDA(cudaStreamWaitEvent(st_out, p->chunk_ev[2 * c + 1], 0));
+        RTB_CUDA(cudaMemcpyAsync(h_out + s0 * out_per, p->d_out + s0 * out_per, sizeof(float) * count * out_per,
+                                 cudaMemcpyDeviceToHost, st_out));
+    }
+    advance_block(p);
+    RTB_CUDA(cudaStreamSynchronize(p->d2h_stream));
+    RTB_CUDA(cudaGetLastError());
     return RTB_OK;
 }
 
@@ -512,6 +555,9 @@ int rtb_sh_plan_destroy(rtb_sh_plan *p) {
     cudaFree(p->d_tw); cudaFree(p->d_win_in); cudaFree(p->d_win_out); cudaFree(p->d_radlast);
     cudaFree(p->d_in); cudaFree(p->d_yaw); cudaFree(p->d_out);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
+    if (p->k_stream) cudaStreamDestroy(p->k_stream);
+    for (auto &e : p->chunk_ev) if (e) cudaEventDestroy(e);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
     return RTB_OK;
