@@ -1,15 +1,147 @@
-"""SH-domain compensation spectra (reference ``ReTiSAR/_compensation.py``) -- set-up time only.
+"""SH-domain compensation spectra -- set-up-time mirror of ``ReTiSAR/_compensation.py``.
 
-The render path consumes a table ``comp_nm [K; 1; F]`` that is multiplied once into the HRIR SH
-coefficients (``_convolver.py:1195-1206``).  The filter designs themselves (modal radial filters,
-spherical head filter, SH tapering; ``_compensation.py:556-733``) are a later row of the scope
-table; until they exist callers supply ``comp_nm`` to
-``AdjustableShConvolver.prepare_sh_processing``.
+``Compensation.generate_by_type`` returns the table ``comp_nm [K; 1; F]`` that
+``AdjustableShConvolver._apply_sh_compensation`` multiplies once into the HRIR SH coefficients
+(``_convolver.py:1195-1206``); nothing here runs per block.
+
+The bookkeeping (type parsing, once-only application, filter-length budget,
+``_compensation.py:182-374``) and the pure-numpy weights (SHT repeat, SDS / EDS masks,
+``:693-833``) follow the reference.  The filter *designs* live in the third-party package
+``sound_field_analysis`` (``gen.radial_filter_fullspec``, ``process.rfi``,
+``gen.spherical_head_filter_spec``, ``gen.tapering_window``, ``gen.delay_fd``,
+``utils.zero_pad_fd``; call sites ``:586, 595, 659, 670, 713, 505``), which is absent from the
+reference tree and from this environment.  They are restated here from the cited papers
+(Bernschuetz et al. 2011 soft-limited radial filters; Ben-Hur et al. 2017 spherical head filter;
+Hold et al. 2019 tapering): PARITY UNPINNED for the design values -- no reference test or
+fixture covers them.
 """
+import re
+import sys
 from enum import Enum
 
+import numpy as np
+from scipy.special import spherical_jn, spherical_yn
 
+from . import sph
+
+SPEED_OF_SOUND = 343.0
+
+
+# ------------------------------------------------------------------------------------------------
+# restated sound_field_analysis pieces
+# ------------------------------------------------------------------------------------------------
+def _kr(freqs, radius):
+    return 2 * np.pi * freqs * radius / SPEED_OF_SOUND
+
+
+def _sph_hankel2(n, x, derivative=False):
+    return spherical_jn(n, x, derivative) - 1j * spherical_yn(n, x, derivative)
+
+
+def mode_strength(order, kr_mic, array_type="rigid", transducer_type="omni", kr_scatter=None):
+    """b_n(kr) without the 4 pi factor (``sfa.gen.array_extrapolation``, normalised)."""
+    kr_mic = np.asarray(kr_mic, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        if array_type == "open":
+            if transducer_type == "cardioid":
+                b = spherical_jn(order, kr_mic) - 1j * spherical_jn(order, kr_mic, True)
+            else:
+                b = spherical_jn(order, kr_mic).astype(np.complex128)
+        else:
+            krs = kr_mic if kr_scatter is None else np.asarray(kr_scatter, dtype=np.float64)
+            b = spherical_jn(order, kr_mic) - (
+                spherical_jn(order, krs, True) / _sph_hankel2(order, krs, True)
+            ) * _sph_hankel2(order, kr_mic)
+    b = (1j ** order) * b
+    # kr -> 0: j_0 -> 1, everything else -> 0 (the Hankel quotient is 0/inf there)
+    limit = 1.0 if order == 0 else 0.0
+    return np.where(np.isfinite(b), b, limit)
+
+
+def radial_filter_fullspec(max_order, nfft, fs, array_configuration, amp_max_db=40):
+    """Soft-limited modal radial filters d_n(f) = L(|b_n|) / b_n, size [max_order + 1; nfft/2 + 1]."""
+    freqs = np.linspace(0, fs / 2, int(nfft / 2 + 1))
+    radius = float(np.mean(array_configuration.array_radius))
+    scatter = array_configuration.scatter_radius
+    kr_s = None if scatter is None else _kr(freqs, float(np.mean(scatter)))
+    amp_max = 10 ** (amp_max_db / 20)
+    out = np.zeros((max_order + 1, freqs.size), dtype=np.complex128)
+    for n in range(max_order + 1):
+        b = mode_strength(n, _kr(freqs, radius), array_configuration.array_type,
+                          array_configuration.transducer_type, kr_s)
+        b = np.where(b == 0, 1e-12, b)
+        limiting = 2 * amp_max / np.pi * np.abs(b) * np.arctan(np.pi / (2 * amp_max * np.abs(b)))
+        out[n] = limiting / b
+    return out
+
+
+def rfi(filter_fd, kernel_size=None):
+    """Radial filter improvement: DC estimate, causal shift, Hann window to `kernel_size` taps.
+
+    Returns (spectra, kernel_size, delay_samples) like ``sfa.process.rfi``.
+    """
+    source_size = (filter_fd.shape[-1] - 1) * 2
+    kernel_size = int(kernel_size) if kernel_size else source_size // 2
+    if kernel_size > source_size:
+        raise ValueError("kernel size must not exceed the source filter length")
+    fd = filter_fd.copy()
+    fd[..., 0] = np.abs(fd[..., 1])  # DC bin: magnitude of its neighbour, zero phase
+    td = np.fft.irfft(fd, axis=-1)
+    delay = kernel_size // 2
+    td = np.roll(td, delay, axis=-1)[..., :kernel_size]
+    td = td * np.hanning(kernel_size)
+    return np.fft.rfft(td, axis=-1), kernel_size, delay
+
+
+def tapering_window(max_order):
+    """Half-sided Hann weights per SH degree (Hold et al. 2019)."""
+    weights = np.hanning(2 * ((max_order + 1) // 2) + 1)
+    weights = weights[-((max_order - 1) // 2) - 1:] if max_order > 0 else weights[-1:]
+    weights = weights if max_order > 0 else np.ones(1)
+    return np.concatenate([np.ones(max_order - len(weights) + 1), weights])
+
+
+def spherical_head_filter_spec(max_order, nfft, fs, radius, is_tapering=False):
+    """Global equalisation of SH order truncation on a rigid sphere (Ben-Hur et al. 2017)."""
+    freqs = np.linspace(0, fs / 2, int(nfft / 2 + 1))
+    kr = _kr(freqs, float(np.mean(radius)))
+    full_order = max(int(np.ceil(kr[-1])), max_order)
+
+    def pressure_on_sphere(order, weights):
+        total = np.zeros_like(kr)
+        for n in range(order + 1):
+            total += weights[n] * (2 * n + 1) * np.abs(mode_strength(n, kr)) ** 2
+        return np.sqrt(total)
+
+    w = tapering_window(max_order) if is_tapering else np.ones(max_order + 1)
+    g = pressure_on_sphere(full_order, np.ones(full_order + 1)) / pressure_on_sphere(max_order, w)
+    g[~np.isfinite(g)] = 1.0
+    g[0] = g[1]
+    return g.astype(np.complex128)
+
+
+def delay_fd(target_length_fd, delay_samples):
+    omega = np.linspace(0, 0.5, target_length_fd)
+    return np.exp(-2j * np.pi * omega * delay_samples)
+
+
+def zero_pad_fd(data_fd, target_length_td):
+    td = np.fft.irfft(data_fd, axis=-1)
+    return np.fft.rfft(td, n=target_length_td, axis=-1)
+
+
+# ------------------------------------------------------------------------------------------------
 class Compensation(object):
+    """Generation of the compensation table (reference ``Compensation``)."""
+
+    _TYPES_STR_SEP = r",.;:|/\-+"
+    _TYPES_REQUESTED = []
+    _TYPES_APPLIED = []
+    _NFFT_USED = None
+    _IS_PLOT = False  # plotting is out of scope
+    _SHF_NFFT = [40, 256]
+    _MRF_NFFT = [90, -1]
+
     class Type(Enum):
         """Identifiers as in ``_compensation.py:45-180`` (long names are aliases)."""
 
@@ -25,10 +157,163 @@ class Compensation(object):
         SECTORIAL_DEGREE_SELECTION = SDS
         EDS = "EQUATORIAL_DEGREE_SELECTION"
         EQUATORIAL_DEGREE_SELECTION = EDS
+        AMF = "ALIASING_MITIGATION_FILTER"
+        ALIASING_MITIGATION_FILTER = AMF
+        MLS = "MAGNITUDE_LEAST_SQUARES"
+        MAGNITUDE_LEAST_SQUARES = MLS
 
     @staticmethod
-    def generate_by_type(compensation_types, filter_set, arir_config, amp_limit_db, nfft,
-                         nfft_padded, sh_cur_order=None, logger=None):
-        raise NotImplementedError(
-            "compensation filter design is not built yet; pass `comp_nm` to "
-            "`prepare_sh_processing` (identity: numpy.ones((K, 1, F)))")
+    def reset_config(is_plot=False):
+        """Forget what was applied so far (``_compensation.py:165-179``)."""
+        Compensation._TYPES_REQUESTED = []
+        Compensation._TYPES_APPLIED = []
+        Compensation._NFFT_USED = None
+        Compensation._IS_PLOT = False
+
+    @staticmethod
+    def _to_type(value):
+        if value is None or isinstance(value, Compensation.Type):
+            return value
+        name = str(value).strip("'\" ").upper()
+        if name in ("", "NONE"):
+            return None
+        try:
+            return Compensation.Type[name]
+        except KeyError:
+            raise ValueError(f'unknown parameter "{value}", see `Compensation.Type` for reference!')
+
+    @staticmethod
+    def _split_types(types):
+        if isinstance(types, list):
+            return [Compensation._split_types(t) for t in types]
+        if isinstance(types, str):
+            if any(sep in types for sep in Compensation._TYPES_STR_SEP):
+                parts = re.split(f"[{Compensation._TYPES_STR_SEP}]+", types)
+                return [Compensation._split_types(t) for t in parts]
+            return Compensation._to_type(types)
+        if isinstance(types, Compensation.Type) or types is None:
+            return types
+        raise ValueError(f"unknown parameter type `{type(types)}`, see `Compensation.Type` for reference! ")
+
+    @staticmethod
+    def generate_by_type(compensation_types, filter_set, arir_config=None, amp_limit_db=None,
+                         fc=None, nfft=None, nfft_padded=None, logger=None):
+        """Product of all requested compensation spectra (``_compensation.py:182-374``)."""
+        C = Compensation
+        if C._NFFT_USED is None:
+            C._NFFT_USED = filter_set._irs_orig_shape[-1]
+        is_nfft_given = nfft is not None and nfft > 0
+        if not nfft_padded:
+            nfft_padded = nfft if is_nfft_given else filter_set._dirac_td.shape[-1]
+        comps_nm = np.ones(nfft_padded // 2 + 1, dtype=filter_set._dirac_blocks_fd.dtype)
+
+        if not C._TYPES_REQUESTED:
+            compensation_types = C._split_types(compensation_types)
+            if not isinstance(compensation_types, list):
+                compensation_types = [compensation_types]
+            for t in compensation_types:
+                if t not in C._TYPES_REQUESTED:
+                    C._TYPES_REQUESTED.append(t)
+
+        if isinstance(compensation_types, list):
+            for t in compensation_types:
+                comps_nm = comps_nm * C.generate_by_type(
+                    t, filter_set=filter_set, arir_config=arir_config, amp_limit_db=amp_limit_db,
+                    fc=fc, nfft=nfft, nfft_padded=nfft_padded, logger=logger)
+            return comps_nm
+
+        _type = C._to_type(compensation_types)
+        if _type is None:
+            return comps_nm
+        if filter_set._irs_blocks_nm is None:
+            raise RuntimeError("filter blocks in spherical harmonics domain have not been calculated yet.")
+        if _type in C._TYPES_APPLIED:
+            msg = f'skipping compensation type "{_type.value}" since it was already applied.'
+            logger.warning(msg) if logger else print(f"[WARNING]  {msg}", file=sys.stderr)
+            return comps_nm
+
+        def adjust(given, lower, upper):
+            adjusted = (upper if upper > 0 else given) if given / 2 >= upper else lower
+            if adjusted < 1 or adjusted < lower:
+                raise ValueError(f"Compensation filter target length of {adjusted} samples is too "
+                                 f'low for type "{_type.value}".')
+            return adjusted
+
+        if _type in (C.Type.SHT, C.Type.SDS, C.Type.EDS):
+            nfft = 1
+        else:
+            if not is_nfft_given:
+                nfft = filter_set._dirac_td.shape[-1] - C._NFFT_USED + 1
+                if _type is C.Type.SHF:
+                    nfft = adjust(nfft, *C._SHF_NFFT)
+                elif _type is C.Type.MRF:
+                    nfft = adjust(nfft, *C._MRF_NFFT)
+            if nfft % 2:
+                nfft -= 1
+        C._TYPES_APPLIED.append(_type)
+        C._NFFT_USED += nfft - 1
+
+        order = filter_set._sh_max_order
+        dtype = filter_set._irs_blocks_nm.dtype
+        fs = filter_set._fs
+        msg = f'applying "{_type.value}" compensation ...'
+        logger.info(msg) if logger else print(msg)
+        if _type == C.Type.MRF:
+            comp_nm = C._generate_fd_mrf(order, nfft, fs, arir_config, amp_limit_db, dtype)
+        elif _type == C.Type.SHF:
+            comp_nm = C._generate_fd_shf(order, nfft, fs, arir_config.array_radius,
+                                         C.Type.SHT in C._TYPES_REQUESTED, dtype)
+        elif _type == C.Type.SHT:
+            comp_nm = C._generate_fd_sht(order, dtype)
+        elif _type == C.Type.SDS:
+            comp_nm = C._generate_fd_sds(order, dtype)
+        elif _type == C.Type.EDS:
+            comp_nm = C._generate_fd_eds(order, dtype)
+        else:
+            raise NotImplementedError(f'chosen compensation type "{_type}" is not implemented yet.')
+        if comp_nm.shape[-1] == 1:
+            comp_nm = np.repeat(comp_nm, 2, axis=-1)
+        return zero_pad_fd(comp_nm, nfft_padded).astype(dtype)
+
+    # -- individual generators ----------------------------------------------------------------
+    @staticmethod
+    def _per_coefficient(values_per_degree, order):
+        """[order + 1; ...] -> [K; 1; ...]: every degree n repeated for its 2n + 1 orders."""
+        return np.repeat(values_per_degree[:, np.newaxis], range(1, order * 2 + 2, 2), axis=0)
+
+    @staticmethod
+    def _generate_fd_mrf(sh_max_order, nfft, fs, arir_config, amp_limit_db, dtype):
+        """Modal radial filters incl. the (-1)^m of the SH convention (``_compensation.py:556-627``)."""
+        comp = radial_filter_fullspec(sh_max_order, nfft, fs, arir_config, amp_limit_db)
+        comp, _, _ = rfi(comp, kernel_size=nfft)
+        comp_nm = Compensation._per_coefficient(comp.astype(dtype), sh_max_order)
+        sh_m = sph.mn_arrays(sh_max_order)[0]
+        return comp_nm * ((-1.0) ** sh_m)[:, np.newaxis, np.newaxis].astype(dtype)
+
+    @staticmethod
+    def _generate_fd_shf(sh_max_order, nfft, fs, radius, is_tapering, dtype):
+        """Spherical head filter, made causal by nfft/2 samples (``_compensation.py:630-690``)."""
+        comp = spherical_head_filter_spec(sh_max_order, nfft, fs, radius, is_tapering).astype(dtype)
+        return comp * delay_fd(comp.shape[-1], nfft // 2).astype(dtype)
+
+    @staticmethod
+    def _generate_fd_sht(sh_max_order, dtype):
+        """``_compensation.py:693-731``"""
+        w = tapering_window(sh_max_order).astype(dtype)
+        return Compensation._per_coefficient(w[:, np.newaxis], sh_max_order)
+
+    @staticmethod
+    def _generate_fd_sds(sh_max_order, dtype):
+        """Keep sectorial modes |m| = n only (``_compensation.py:734-783``)."""
+        w = np.ones(((sh_max_order + 1) ** 2, 1, 1), dtype=dtype)
+        for n in range(1, sh_max_order + 1):
+            w[n * n + 1: (n + 1) ** 2 - 1] = 0
+        return w
+
+    @staticmethod
+    def _generate_fd_eds(sh_max_order, dtype):
+        """Keep equatorial modes, n + m even (``_compensation.py:786-833``)."""
+        w = np.ones(((sh_max_order + 1) ** 2, 1, 1), dtype=dtype)
+        for n in range(1, sh_max_order + 1):
+            w[n * n + 1: (n + 1) ** 2: 2] = 0
+        return w

@@ -132,12 +132,16 @@ class OverlapSaveConvolver(Convolver):
         self._filter.calculate_filter_blocks_fd(self._block_length)
         self._plan = None
         if type(self) is OverlapSaveConvolver:
-            hfd = self._filter.get_filter_blocks_fd()  # [P, 1, Cout, F]
-            n_out = hfd.shape[-2]
-            self._n_in = n_out  # rows of `_input_block_td` (`_convolver.py:477-480`)
-            self._plan = OlsPlan(self._n_streams, block_length, n_out, n_out, hfd.shape[0],
-                                 device=self._device)
-            self._plan.set_filter(hfd[:, 0])
+            # rows of `_input_block_td` = filter channels (`_convolver.py:477-480`); a mono input
+            # is broadcast into all of them (`:588-591`), for which the plan has a cheaper form
+            self._make_plan(self._filter.get_filter_blocks_fd().shape[-2])
+
+    def _make_plan(self, n_in):
+        hfd = self._filter.get_filter_blocks_fd()  # [P, 1, Cout, F]
+        self._plan = OlsPlan(self._n_streams, self._block_length, n_in, hfd.shape[-2], hfd.shape[0],
+                             device=self._device)
+        self._plan.set_filter(hfd[:, 0])
+        self._plan.set_passthrough(self._is_passthrough)
 
     def __copy__(self):
         """Independent clone for ``JackRendererBenchmark.add_convolver`` (``_convolver.py:482-491``);
@@ -168,22 +172,22 @@ class OverlapSaveConvolver(Convolver):
         """
         if input_block_td is None:
             return Convolver.filter_block(self, None)
+        n_rows = input_block_td.shape[-2]
+        if n_rows != self._plan.n_in:
+            if n_rows != 1:
+                raise ValueError(f"expected {self._plan.n_out} (or 1) input channels, got {n_rows}")
+            self._make_plan(1)  # first mono block: switch to the mono-input delay line
         plan = self._plan
         if _is_torch_tensor(input_block_td):
             import torch
 
             x = input_block_td.reshape(plan.S, -1, plan.B)
-            if x.shape[1] == 1 and plan.n_in > 1:
-                x = x.expand(plan.S, plan.n_in, plan.B).contiguous()
             out = torch.empty((plan.S, plan.n_out, plan.B), dtype=torch.float32, device=x.device)
             plan.process_device(x.contiguous(), out, torch.cuda.current_stream(x.device))
             return out if input_block_td.dim() == 3 else out[0]
         x = np.asarray(input_block_td, dtype=np.float32)
         batched = x.ndim == 3
-        x = x.reshape(plan.S, -1, plan.B)
-        if x.shape[1] == 1 and plan.n_in > 1:
-            x = np.broadcast_to(x, (plan.S, plan.n_in, plan.B))
-        out = plan.process_host(x)
+        out = plan.process_host(x.reshape(plan.S, -1, plan.B))
         return out if batched else out[0]
 
 
@@ -330,6 +334,7 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         (``_convolver.py:1171-1220``) and hand it to the device plan."""
         from ._compensation import Compensation
 
+        Compensation.reset_config(is_plot=is_plot)
         self._filter.calculate_filter_blocks_nm()
         if self._comp_nm_override is not None:
             comp_nm = self._comp_nm_override
@@ -337,8 +342,7 @@ class AdjustableShConvolver(AdjustableFdConvolver):
             comp_nm = Compensation.generate_by_type(
                 compensation_types=self._comp, filter_set=self._filter,
                 arir_config=self._comp_arir_config, amp_limit_db=self._comp_mrf_limit,
-                nfft=None, nfft_padded=2 * self._block_length,
-                sh_cur_order=self._sh_cur_order, logger=logger)
+                nfft=None, nfft_padded=2 * self._block_length, logger=logger)
         self._filter._irs_blocks_nm *= comp_nm
         if upload and self._plan is not None:
             self._plan.update_filter(self._filter._irs_blocks_nm)

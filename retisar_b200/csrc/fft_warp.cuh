@@ -28,10 +28,13 @@ struct FftCfg {
 // Conflict-free placement for every access pattern of the passes below; found by brute force,
 // see tools/swizzle_search.py (2 wavefronts per 64-bit warp access = the minimum).
 template <int N2>
-__device__ __forceinline__ int fft_swz(int i) {
-    if (N2 == 64) return i ^ ((i >> 3) & 7);
-    return i ^ ((i >> 3) & 1) ^ (((i >> 4) & 7) << 1);
+__host__ __device__ __forceinline__ constexpr int fft_swz(int i) {
+    return (N2 == 64) ? (i ^ ((i >> 3) & 7)) : (i ^ ((i >> 3) & 1) ^ (((i >> 4) & 7) << 1));
 }
+// The swizzle is linear over GF(2), and every index used below is a sum of a lane-dependent part
+// and a compile-time part that occupy disjoint bit fields, so
+//   fft_swz(lane_part + const_part) == fft_swz(lane_part) ^ fft_swz(const_part)
+// : one XOR with an immediate per access instead of recomputing the swizzle.
 
 // multiply by -i (forward) / +i (inverse)
 template <bool INV>
@@ -117,9 +120,12 @@ __device__ __forceinline__ void fft_pass(float2 (&X)[FftCfg<N2>::EPL], float2 *b
         }
         dft_r<R, INV>(v);
         if constexpr (TO_SMEM) {
-            const int j0 = (j / NS) * NS * R + k;
+            // j0 = (j / NS) * NS * R + k with j = l + G*b; G*b is a multiple of NS
+            static_assert((Cfg::G % NS) == 0, "lane and butterfly fields must not overlap");
+            const int lbase = fft_swz<N2>((l / NS) * NS * R + (l & (NS - 1)));
+            const int cb = (Cfg::G * b / NS) * NS * R;
 #pragma unroll
-            for (int t = 0; t < R; ++t) buf[fft_swz<N2>(j0 + t * NS)] = v[t];
+            for (int t = 0; t < R; ++t) buf[lbase ^ fft_swz<N2>(cb + t * NS)] = v[t];
         } else {
 #pragma unroll
             for (int t = 0; t < R; ++t) X[b + t * NB] = v[t];
@@ -131,8 +137,9 @@ template <int N2>
 __device__ __forceinline__ void fft_exchange(float2 (&X)[FftCfg<N2>::EPL], const float2 *buf, int l) {
     using Cfg = FftCfg<N2>;
     __syncwarp();
+    const int lbase = fft_swz<N2>(l);
 #pragma unroll
-    for (int u = 0; u < Cfg::EPL; ++u) X[u] = buf[fft_swz<N2>(l + Cfg::G * u)];
+    for (int u = 0; u < Cfg::EPL; ++u) X[u] = buf[lbase ^ fft_swz<N2>(Cfg::G * u)];
     __syncwarp();
 }
 

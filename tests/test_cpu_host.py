@@ -205,3 +205,50 @@ def test_two_rank_gather_and_timing_over_gloo():
     mp.spawn(_gloo_worker, args=(2, port, results), nprocs=2, join=True)
     assert results["gathered"] == [0.0, 1.0, 2.0, 3.0, 4.0]
     assert results["max"] == 2.0
+
+
+def test_compensation_tables():
+    """Compensation bookkeeping (reference `_compensation.py:182-374`) and design sanity; the
+    design values themselves are parity-unpinned (third-party `sound_field_analysis`)."""
+    from retisar_b200 import workloads as wl
+    from retisar_b200._compensation import (Compensation, mode_strength, radial_filter_fullspec,
+                                            tapering_window)
+
+    tb = wl.sh_tables("c2", hrir_dirs=80)
+    h, cfg = tb["hrir_set"], tb["sh_config"]
+    h.calculate_filter_blocks_fd(256)
+    with pytest.raises(RuntimeError):  # SH blocks not calculated yet
+        Compensation.reset_config()
+        Compensation.generate_by_type("MRF", h, cfg.arir_config, 18, nfft_padded=512)
+    h.calculate_filter_blocks_nm()
+    Compensation.reset_config()
+    comp = Compensation.generate_by_type(
+        ["SPHERICAL_HARMONICS_TAPERING+SPHERICAL_HEAD_FILTER", Compensation.Type.MRF], h,
+        cfg.arir_config, 18, nfft=None, nfft_padded=512)
+    assert comp.shape == (25, 1, 257) and comp.dtype == np.complex64 and np.isfinite(comp).all()
+    assert Compensation._TYPES_APPLIED == [Compensation.Type.SHT, Compensation.Type.SHF,
+                                           Compensation.Type.MRF]
+    # filter-length budget: 128 HRIR taps + (40 - 1) SHF + (90 - 1) MRF = 256 = one block
+    assert Compensation._NFFT_USED == 256
+    # a second application is skipped (returns ones)
+    again = Compensation.generate_by_type("MRF", h, cfg.arir_config, 18, nfft_padded=512)
+    assert np.allclose(again, 1)
+    # radial filters: soft limit at +18 dB, inverse of the mode strength where it is large
+    rf = radial_filter_fullspec(4, 256, 48000, cfg.arir_config, 18)
+    assert np.abs(rf).max() <= 10 ** (18 / 20) * (1 + 1e-6)
+    kr = 2 * np.pi * np.linspace(0, 24000, 129) * 0.042 / 343
+    assert abs(abs(rf[0, 20] * mode_strength(0, kr[20])) - 1) < 0.15
+    # weights: taper is 1 for low degrees and falls to 0 at the top degree
+    w = tapering_window(8)
+    assert w[0] == 1 and w[-1] == 0 and np.all(np.diff(w) <= 0)
+    Compensation.reset_config()
+    sds = Compensation.generate_by_type("SDS", h, cfg.arir_config, 18, nfft_padded=512)
+    m, n = __import__("retisar_b200.sph", fromlist=["x"]).mn_arrays(4)
+    assert np.allclose(np.abs(sds[:, 0, 0]), (np.abs(m) == n).astype(float))
+    Compensation.reset_config()
+    eds = Compensation.generate_by_type("EQUATORIAL_DEGREE_SELECTION", h, cfg.arir_config, 18,
+                                        nfft_padded=512)
+    assert np.allclose(np.abs(eds[:, 0, 100]), ((n + m) % 2 == 0).astype(float))
+    Compensation.reset_config()
+    with pytest.raises(ValueError):
+        Compensation.generate_by_type("NOT_A_TYPE", h, cfg.arir_config, 18, nfft_padded=512)

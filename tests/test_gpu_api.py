@@ -1,0 +1,150 @@
+"""GPU tests of the reference-shaped class API: factory dispatch, tracker
+contract, controls, error behaviour, compensation path, copies, torch tensors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def tables():
+    from retisar_b200 import workloads as wl
+
+    return wl.sh_tables("c2", hrir_dirs=150)
+
+
+def _oracle(tables, hnm):
+    from oracle import sh_chain as oc
+
+    cfg = tables["sh_config"]
+    return oc.ShOracle(cfg.sh_m, cfg.sh_bases_weighted, hnm, tables["B"], tables["order"])
+
+
+def test_renderer_with_designed_compensation_and_tracker(tables):
+    """prepare_sh_processing with SHT+SHF+MRF, yaw read from the shared tracker array, output is
+    a fresh writable float32 [2; B] array; order update keeps signal state."""
+    from retisar_b200 import Convolver, HeadTracker, config
+    from retisar_b200._convolver import AdjustableShConvolver
+    from retisar_b200 import synthetic as syn
+
+    tracker = HeadTracker.create_shared_array()
+    conv = Convolver.create_instance_by_filter_set(tables["hrir_set"], tables["B"], [(0, 0)], tracker)
+    assert type(conv) is AdjustableShConvolver
+    with pytest.raises(RuntimeError):
+        conv.filter_block(np.zeros((32, 256), np.float32))  # not prepared yet
+    conv.prepare_sh_processing(tables["sh_config"], 18,
+                               "SPHERICAL_HARMONICS_TAPERING+SPHERICAL_HEAD_FILTER")
+    conv.init_fft_optimize()
+    assert conv.get_input_channel_count() == 32 and conv.get_output_channel_count() == 2
+    hnm = conv._filter.get_filter_blocks_nm().copy()
+    assert not np.allclose(hnm, 0)
+    o = _oracle(tables, hnm)
+    x = syn.noise_blocks(10, 32, 256, 5)
+    yaw = syn.yaw_walk(10, 6)
+    for t in range(10):
+        if t == 4:
+            assert conv.update_sh_processing(2) == 2
+            o.set_order(2)
+        if t == 7:
+            assert conv.update_sh_processing(None) == 4
+            o.set_order(4)
+        if t == 8:
+            assert conv.update_sh_processing(9) is None  # out of bounds: ignored
+        tracker[HeadTracker.DataIndex.AZIM] = float(yaw[t])
+        y = conv.filter_block(x[t])
+        assert y.shape == (2, 256) and y.dtype == np.float32 and y.flags.writeable
+        y *= 0.5  # the caller scales in place (`_jack_client.py:795`)
+        ref = o.filter_block(x[t], yaw[t])
+        assert np.abs(2 * y - ref).max() <= TOL, t
+    # pause protocol
+    config.IS_RUNNING.clear()
+    assert conv.filter_block(None) is None  # clears buffers
+    config.IS_RUNNING.set()
+    o.clear()
+    tracker[HeadTracker.DataIndex.AZIM] = 10.0
+    assert np.abs(conv.filter_block(x[0]) - o.filter_block(x[0], 10.0)).max() <= TOL
+
+
+def test_controls_and_copy(tables):
+    from retisar_b200 import workloads as wl
+    from copy import copy
+    from retisar_b200 import synthetic as syn
+
+    conv = wl.make_renderer(tables, 1)
+    o = _oracle(tables, conv._filter.get_filter_blocks_nm())
+    x = syn.noise_blocks(8, 32, 256, 9)
+    assert conv.set_crossfade(False) is False
+    o.set_crossfade(False)
+    assert conv.set_passthrough() is True  # toggle
+    o.is_passthrough = True
+    y = conv.filter_block(x[0], [30.0])
+    assert np.abs(y - o.filter_block(x[0], 30.0)).max() <= TOL
+    assert np.abs(y - x[0][:2]).max() <= TOL  # passthrough = first two microphones
+    assert conv.set_passthrough(False) is False
+    o.is_passthrough = False
+    assert conv.set_crossfade(None) is True
+    o.set_crossfade(True)
+    for t in range(1, 4):
+        assert np.abs(conv.filter_block(x[t], [40.0 * t]) - o.filter_block(x[t], 40.0 * t)).max() <= TOL
+    clone = copy(conv)  # independent state, same tables
+    assert clone is not conv and clone._plan is not conv._plan
+    o2 = _oracle(tables, conv._filter.get_filter_blocks_nm())
+    assert np.abs(clone.filter_block(x[5], [12.0]) - o2.filter_block(x[5], 12.0)).max() <= TOL
+    assert np.abs(conv.filter_block(x[4], [160.0]) - o.filter_block(x[4], 160.0)).max() <= TOL
+
+
+def test_errors_match_reference(tables):
+    from retisar_b200 import Convolver
+    from retisar_b200._filter_set import FilterSetMiro
+    from retisar_b200.plans import ShPlan
+
+    with pytest.raises(ValueError):  # no source positions (`_convolver.py:724-727`)
+        Convolver.create_instance_by_filter_set(tables["hrir_set"], 256, None, None)
+    with pytest.raises(NotImplementedError):  # more than one source (`:1036-1039`)
+        Convolver.create_instance_by_filter_set(tables["hrir_set"], 256, [(0, 0), (90, 0)], None)
+    with pytest.raises(NotImplementedError):  # partitions in the SH domain (`_filter_set.py:1136`)
+        ShPlan(1, 256, 32, 4, n_partitions=2)
+    with pytest.raises(NotImplementedError):
+        ShPlan(1, 100, 32, 4)  # unsupported block length
+    with pytest.raises(ValueError):
+        ShPlan(1, 256, 32, -1)
+    plan = ShPlan(1, 256, 32, 4)
+    with pytest.raises(RuntimeError):  # tables missing (`_filter_set.py:1232-1233`)
+        plan.process_host(np.zeros((1, 32, 256), np.float32), np.zeros(1, np.float32))
+    with pytest.raises(ValueError):
+        plan.set_order(7)
+
+
+def test_torch_device_path_and_batched_ols(tables):
+    import torch
+
+    from oracle import sh_chain as oc
+    from retisar_b200 import Convolver, FilterSet
+    from retisar_b200 import workloads as wl
+
+    S = 6
+    conv = wl.make_renderer(tables, S)
+    hnm = conv._filter.get_filter_blocks_nm()
+    oracles = [_oracle(tables, hnm) for _ in range(S)]
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    for t in range(3):
+        x = torch.randn((S, 32, 256), device="cuda", generator=g) * 0.1
+        yaw = torch.rand((S,), device="cuda", generator=g) * 720 - 360
+        y = conv.filter_block(x, yaw)
+        assert y.is_cuda and y.shape == (S, 2, 256)
+        ref = np.stack([o.filter_block(x[s].cpu().numpy(), float(yaw[s])) for s, o in enumerate(oracles)])
+        assert np.abs(y.cpu().numpy() - ref).max() <= TOL
+    # batched OLS convolver on the device, mono input broadcast
+    irs = (np.random.default_rng(0).standard_normal((4, 300)) * 0.05).astype(np.float32)
+    fs = FilterSet.create_instance_by_type(irs, "FIR_MULTICHANNEL")
+    fs.load(block_length=64, is_single_precision=True, is_prevent_logging=True)
+    ols = Convolver.create_instance_by_filter_set(fs, 64, n_streams=3)
+    H = oc.filter_blocks_fd(oc.zero_pad(irs[None], 64), 64)
+    refs = [oc.OlsOracle(H, 64) for _ in range(3)]
+    for t in range(8):
+        x = torch.randn((3, 1, 64), device="cuda", generator=g) * 0.1
+        y = ols.filter_block(x)
+        ref = np.stack([r.filter_block(x[s].cpu().numpy()) for s, r in enumerate(refs)])
+        assert np.abs(y.cpu().numpy() - ref).max() <= TOL
