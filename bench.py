@@ -53,8 +53,9 @@ def _cpu_worker(args):
     cfg = tb["sh_config"]
     tb["hrir_set"].calculate_filter_blocks_fd(tb["B"])
     tb["hrir_set"].calculate_filter_blocks_nm()
-    o = oc.ShOracle(cfg.sh_m, cfg.sh_bases_weighted, tb["hrir_set"].get_filter_blocks_nm(), tb["B"],
-                    tb["order"])
+    hnm = tb["hrir_set"].get_filter_blocks_nm()
+    cls = oc.ShOracle if hnm.shape[0] == 1 else oc.ShPartitionedOracle
+    o = cls(cfg.sh_m, cfg.sh_bases_weighted, hnm, tb["B"], tb["order"])
     x = syn.noise_blocks(8, tb["C"], tb["B"], seed)
     yaw = syn.yaw_walk(warm + n_blocks, seed + 1)
     for i in range(warm):
@@ -338,7 +339,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5", "c4"])
     ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -43,7 +43,9 @@ int rtb_device_count(void);
 /* SH-domain renderer ------------------------------------------------------------------------- */
 /* AdjustableShConvolver.__init__ (_convolver.py:1010-1049) for S batched streams.
  * block_length B in {32, 64, 128, 256}; n_ears must be 2; n_partitions = number of B-sample
- * partitions of the HRIR (1 = the reference's only supported case, _filter_set.py:1136-1140). */
+ * partitions of the HRIR.  1 is the reference's only supported case (_filter_set.py:1136-1140);
+ * > 1 is an EXTENSION defined by composition with the reference's partition-queue semantics
+ * (_convolver.py:802-836, :645-665), see DESIGN.md row a-X. */
 int rtb_sh_plan_create(rtb_sh_plan **plan, int device, int n_streams, int block_length,
                        int n_channels, int sh_max_order, int n_ears, int n_partitions);
 

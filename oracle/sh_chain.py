@@ -300,6 +300,11 @@ class ShPartitionedOracle(ShOracle):
         self.input_block_td[:, :B] = self.input_block_td[:, B:]
         self.input_block_td[:, B:] = x
         x_fd = np.fft.rfft(self.input_block_td)
+        if self.is_passthrough:  # `_convolver.py:558-562` then the queue roll `:645-665`
+            x_fd = x_fd[: self.blocks_fd.shape[-2]]
+            self.blocks_fd[0, 0, : x_fd.shape[-2]] = x_fd
+            self.blocks_fd, y = self._roll(self.blocks_fd)
+            return y
         nm = np.dot(self.Yw, x_fd)[self.rev][:, np.newaxis, :]
         azim = individual_azimuth_deg(yaw_deg, self.sources_deg, self.is_hrir)
         sh_azim = sh_rotation_phases(azim, self.sh_m, self.blocks_fd.dtype.type)

@@ -1,0 +1,253 @@
+// Row a-X (EXTENSION, not in the reference): SH-domain rendering with a P-partition HRIR.
+//
+// Semantics by composition of the reference's own partition-queue convention
+// (AdjustableFdConvolver.filter_block, ReTiSAR/_convolver.py:802-836, queue roll :645-665): the
+// current rotation is applied at input time into an OUTPUT-side queue of P ear spectra, a second
+// queue receives the previous rotation, both heads are inverse-transformed and cross-faded, then
+// the queues advance.  (An input-side delay line is not possible here: the rotation is time
+// varying and the rotated SH spectra are K/E times larger than the ear spectra.)
+//
+// Three kernels per block, after the analysis GEMM:
+//   sh_spectra_kernel        one warp per stream: FFT of every complex SH signal -> zspec (HBM)
+//   sh_partition_mac_kernel  per (32 bins, 8 streams): for all partitions q and signal terms j
+//                            queue[q][ear][f] += H[q][j][ear][f] * phase_j * Z_j(f)
+//                            -- per bin a [P*E x 2NP] x [2NP x streams] complex GEMM whose matrix is
+//                            shared by all streams; register tile 4 partitions x 2 ears x cur/last
+//                            x 2 streams per lane, H rows reused from L1 by the CTA's warps
+//   sh_partition_tail_kernel one warp per stream: queue heads -> inverse FFTs -> cross-fade
+#pragma once
+
+namespace rtb {
+
+struct ShPartParams {
+    const float *zprev, *zcur;   // [S][J][B] analysis rows, previous / current block
+    float2 *zspec;               // [S][NPT][N2] spectra of the complex signals (scratch)
+    const float4 *htab;          // [P][NPT][2][Fp] (ear0.re, ear0.im, ear1.re, ear1.im)
+    const ShSignal *signals;     // [NPT]
+    const float2 *tw;
+    const float *win_in, *win_out, *yaw_deg, *rad_last_in;
+    float *rad_last_out;
+    float2 *qcur, *qlast;        // [S][P][2][Fp] output-side queues (rings over P)
+    float *out;                  // [S][2][B]
+    int S, J, P, Fp, NPT;
+    int np_cur, np_last, order_max, crossfade, head_cur, head_last;
+    float tracker_dir, src_azim16;
+};
+
+template <int N2>
+__global__ void __launch_bounds__(128)
+sh_spectra_kernel(const ShPartParams prm) {
+    using Cfg = FftCfg<N2>;
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, GROUPS = Cfg::GROUPS, B = N2 / 2;
+    __shared__ float2 s_tw[N2];
+    __shared__ __align__(16) float2 s_buf[4][GROUPS * Cfg::REGION];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, l = lane % G;
+    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+    __syncthreads();
+    const int s = blockIdx.x * 4 + warp;
+    if (s >= prm.S) return;
+    float2 *buf = s_buf[warp] + grp * Cfg::REGION;
+    float *zrow = reinterpret_cast<float *>(buf);
+    const int np = max(prm.np_cur, prm.np_last);
+    const size_t zoff = (size_t)s * prm.J * B;
+
+    auto prefetch_z = [&](int p0) {
+        const int p = p0 + grp;
+        if (p >= np) return;
+        const ShSignal sg = prm.signals[p];
+        constexpr int CH = B / 4;
+        for (int i = l; i < 4 * CH; i += G) {
+            const int part = i / CH, off = (i % CH) * 4;
+            const int row = (part < 2) ? sg.row_re : sg.row_im;
+            float *dst = zrow + (part >> 1) * N2 + (part & 1) * B + off;
+            if (row >= 0)
+                cp_async16_cg(dst, ((part & 1) ? prm.zcur : prm.zprev) + zoff + (size_t)row * B + off);
+            else
+                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if (np > 0) prefetch_z(0);
+    cp_async_commit();
+    for (int p0 = 0; p0 < np; p0 += GROUPS) {
+        cp_async_wait_all();
+        __syncwarp();
+        const int p = p0 + grp;
+        const bool valid = p < np;
+        float2 X[EPL];
+#pragma unroll
+        for (int u = 0; u < EPL; ++u) {
+            X[u].x = valid ? zrow[l + G * u] : 0.f;
+            X[u].y = valid ? zrow[N2 + l + G * u] : 0.f;
+        }
+        __syncwarp();
+        fft_pass<N2, 8, 1, false, true>(X, buf, s_tw, l);
+        fft_exchange<N2>(X, buf, l);
+        if constexpr (Cfg::R_LAST != 0) {
+            fft_pass<N2, 8, 8, false, true>(X, buf, s_tw, l);
+            fft_exchange<N2>(X, buf, l);
+        }
+        if (p0 + GROUPS < np) prefetch_z(p0 + GROUPS);
+        cp_async_commit();
+        if constexpr (Cfg::R_LAST == 0) fft_pass<N2, 8, 8, false, false>(X, buf, s_tw, l);
+        else fft_pass<N2, Cfg::R_LAST, 64, false, false>(X, buf, s_tw, l);
+        if (valid) {
+            float2 *dst = prm.zspec + ((size_t)s * prm.NPT + p) * N2 + l;
+#pragma unroll
+            for (int u = 0; u < EPL; ++u) dst[G * u] = X[u];
+        }
+    }
+    cp_async_wait_all();
+}
+
+#define RTB_QC 4  // partitions per register tile
+
+template <int N2>
+__global__ void __launch_bounds__(128)
+sh_partition_mac_kernel(const ShPartParams prm) {
+    constexpr int B = N2 / 2;
+    __shared__ float2 s_cs[4][2][2][RTB_MAX_ORDER + 1];  // [warp][stream][cur/last][m] = (cos, sin)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * 32 + lane;
+    const bool fvalid = f <= B;
+    const int fm = (N2 - f) & (N2 - 1);  // mirrored bin
+    const int sbase = (blockIdx.y * 4 + warp) * 2;
+    if (sbase >= prm.S) return;
+    const bool has_s1 = sbase + 1 < prm.S;
+    // rotation phases of both streams, current and previous yaw (a4)
+    for (int i = lane; i < 4 * (prm.order_max + 1); i += 32) {
+        const int m = i % (prm.order_max + 1), which = i / (prm.order_max + 1);
+        const int st = which >> 1, cl = which & 1;
+        const int s = min(sbase + st, prm.S - 1);
+        const float rad = cl ? prm.rad_last_in[s]
+                             : yaw_deg_to_rad16(prm.yaw_deg[s], prm.tracker_dir, prm.src_azim16);
+        float sn, cs;
+        sincosf((float)m * rad, &sn, &cs);
+        s_cs[warp][st][cl][m] = make_float2(cs, sn);
+    }
+    __syncwarp();
+    const int np = max(prm.np_cur, prm.np_last);
+    const float2 *z0 = prm.zspec + (size_t)sbase * prm.NPT * N2;
+    const float2 *z1 = prm.zspec + (size_t)(has_s1 ? sbase + 1 : sbase) * prm.NPT * N2;
+    const size_t hq = (size_t)prm.NPT * 2 * prm.Fp;  // H stride between partitions
+
+    for (int q0 = 0; q0 < prm.P; q0 += RTB_QC) {
+        float2 acc[RTB_QC][2][2][2];  // [partition][ear][cur/last][stream]
+#pragma unroll
+        for (int a = 0; a < RTB_QC; ++a)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) acc[a][e][c][0] = acc[a][e][c][1] = make_float2(0.f, 0.f);
+        for (int p = 0; p < np; ++p) {
+            const ShSignal sg = prm.signals[p];
+            const bool in_cur = p < prm.np_cur, in_last = p < prm.np_last;
+            const int nterms = (sg.m2 != RTB_NO_TERM) ? 2 : 1;
+            for (int term = 0; term < nterms; ++term) {
+                const int m = term ? sg.m2 : sg.m1;
+                float2 A[2][2];  // [cur/last][stream]
+#pragma unroll
+                for (int st = 0; st < 2; ++st) {
+                    const float2 *zs = (st ? z1 : z0) + (size_t)p * N2;
+                    float2 z = fvalid ? __ldg(zs + (term ? fm : f)) : make_float2(0.f, 0.f);
+                    if (term) z.y = -z.y;
+                    const float2 pc = in_cur ? phase_of(s_cs[warp][st][0], m) : make_float2(0.f, 0.f);
+                    const float2 pl = in_last ? phase_of(s_cs[warp][st][1], m) : make_float2(0.f, 0.f);
+                    A[0][st] = cmul(pc, z);
+                    A[1][st] = cmul(pl, z);
+                }
+                const float4 *hp = prm.htab + (size_t)q0 * hq + ((size_t)p * 2 + term) * prm.Fp + f;
+#pragma unroll
+                for (int a = 0; a < RTB_QC; ++a) {
+                    if (q0 + a < prm.P && fvalid) {
+                        const float4 h = __ldg(hp + (size_t)a * hq);
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+#pragma unroll
+                            for (int st = 0; st < 2; ++st) {
+                                cfma(acc[a][0][c][st], make_float2(h.x, h.y), A[c][st]);
+                                cfma(acc[a][1][c][st], make_float2(h.z, h.w), A[c][st]);
+                            }
+                    }
+                }
+            }
+        }
+        if (fvalid) {
+#pragma unroll
+            for (int a = 0; a < RTB_QC; ++a) {
+                if (q0 + a >= prm.P) break;
+                const int sc = (prm.head_cur + q0 + a) % prm.P, sl = (prm.head_last + q0 + a) % prm.P;
+#pragma unroll
+                for (int st = 0; st < 2; ++st) {
+                    if (st && !has_s1) break;
+                    const size_t sq = (size_t)(sbase + st) * prm.P;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        float2 *qc = prm.qcur + ((sq + sc) * 2 + e) * prm.Fp + f;
+                        float2 v = *qc;
+                        v.x += acc[a][e][0][st].x; v.y += acc[a][e][0][st].y;
+                        *qc = v;
+                        if (prm.crossfade) {
+                            float2 *ql = prm.qlast + ((sq + sl) * 2 + e) * prm.Fp + f;
+                            float2 w = *ql;
+                            w.x += acc[a][e][1][st].x; w.y += acc[a][e][1][st].y;
+                            *ql = w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int N2>
+__global__ void __launch_bounds__(128)
+sh_partition_tail_kernel(const ShPartParams prm) {
+    using Cfg = FftCfg<N2>;
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS, B = N2 / 2;
+    __shared__ float2 s_tw[N2];
+    __shared__ __align__(16) float2 s_buf[4][GROUPS * Cfg::REGION];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, l = lane % G;
+    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+    __syncthreads();
+    const int s = blockIdx.x * 4 + warp;
+    if (s >= prm.S) return;
+    float2 acc[HB + 1][4];
+    float2 *qc = prm.qcur + ((size_t)s * prm.P + prm.head_cur) * 2 * prm.Fp;
+    float2 *ql = prm.qlast + ((size_t)s * prm.P + prm.head_last) * 2 * prm.Fp;
+    const float2 zero = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u <= HB; ++u) {
+        const int f = (u < HB) ? (l + G * u) : B;
+        acc[u][0] = qc[f];
+        acc[u][1] = qc[prm.Fp + f];
+        acc[u][2] = prm.crossfade ? ql[f] : zero;
+        acc[u][3] = prm.crossfade ? ql[prm.Fp + f] : zero;
+    }
+    __syncwarp();  // every group has read the heads before anyone clears them
+#pragma unroll
+    for (int u = 0; u <= HB; ++u) {  // queue slot 0 leaves the queue: blocks[-1] = 0 after the roll
+        const int f = (u < HB) ? (l + G * u) : B;
+        if (grp == 0 && (u < HB || l == 0)) {
+            qc[f] = zero;
+            qc[prm.Fp + f] = zero;
+            if (prm.crossfade) { ql[f] = zero; ql[prm.Fp + f] = zero; }
+        }
+    }
+    if (prm.crossfade && lane == 0)
+        prm.rad_last_out[s] = yaw_deg_to_rad16(prm.yaw_deg[s], prm.tracker_dir, prm.src_azim16);
+    render_tail<N2>(acc, s_buf[warp] + grp * Cfg::REGION, s_tw, lane, prm.win_in, prm.win_out,
+                    prm.crossfade, prm.out + (size_t)s * 2 * B);
+}
+
+// passthrough with partitions: the head of the current queue is dropped and the queue advances
+__global__ void sh_queue_clear_head_kernel(float2 *q, int S, int P, int Fp, int head) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = 2LL * Fp;
+    if (i >= (long long)S * per) return;
+    const long long s = i / per, r = i % per;
+    q[((size_t)s * P + head) * per + r] = make_float2(0.f, 0.f);
+}
+
+}  // namespace rtb

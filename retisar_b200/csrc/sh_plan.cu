@@ -33,6 +33,11 @@ struct rtb_sh_plan {
     float2 *d_tw = nullptr;       // [N2]
     float *d_win_in = nullptr, *d_win_out = nullptr;
     float *d_radlast = nullptr;   // [2][S]
+    // partitioned HRIR (P > 1): spectra scratch and the two output-side queues
+    int Fp = 0;
+    float2 *d_zspec = nullptr;    // [S][NP][N2]
+    float2 *d_qcur = nullptr, *d_qlast = nullptr;  // [S][P][2][Fp]
+    int head_cur = 0, head_last = 0;
     // staging for the host-buffer entry point
     float *d_in = nullptr, *d_yaw = nullptr, *d_out = nullptr;
     cudaStream_t own_stream = nullptr, d2h_stream = nullptr, k_stream = nullptr;
@@ -109,30 +114,42 @@ void launch_render(const rtb_sh_plan *p, const ShRenderParams &prm, cudaStream_t
     }
 }
 
-// H table: [NP][2][F] x (ear0.re, ear0.im, ear1.re, ear1.im); hnm is [P=1][K][E=2][F] complex
+// H table: [P][NP][2][Fs] x (ear0.re, ear0.im, ear1.re, ear1.im); hnm is [P][K][E=2][F] complex.
+// Row stride Fs = F for the single-partition kernel (staged by cp.async), Fp (sector aligned) for
+// the partitioned one.
 std::vector<float4> build_htab(const rtb_sh_plan *p, const float *hnm) {
-    const int F = p->F, NP = (int)p->sig_k1.size();
-    std::vector<float4> htab((size_t)NP * 2 * F, make_float4(0.f, 0.f, 0.f, 0.f));
-    auto HNM = [&](int k, int e, int f, int ri) { return hnm[2 * (((size_t)k * 2 + e) * F + f) + ri]; };
-    for (int q = 0; q < NP; ++q) {
-        const int k1 = p->sig_k1[q], k2 = p->sig_k2[q];
-        const float sg = p->sig_sign2[q];
-        for (int f = 0; f < F; ++f) {
-            htab[((size_t)q * 2) * F + f] = make_float4(HNM(k1, 0, f, 0), HNM(k1, 0, f, 1),
-                                                        HNM(k1, 1, f, 0), HNM(k1, 1, f, 1));
-            if (k2 >= 0)
-                htab[((size_t)q * 2 + 1) * F + f] = make_float4(sg * HNM(k2, 0, f, 0), sg * HNM(k2, 0, f, 1),
-                                                                sg * HNM(k2, 1, f, 0), sg * HNM(k2, 1, f, 1));
+    const int F = p->F, NP = (int)p->sig_k1.size(), K = p->K;
+    const int Fs = p->P > 1 ? p->Fp : F;
+    std::vector<float4> htab((size_t)p->P * NP * 2 * Fs, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int part = 0; part < p->P; ++part) {
+        auto HNM = [&](int k, int e, int f, int ri) {
+            return hnm[2 * ((((size_t)part * K + k) * 2 + e) * F + f) + ri];
+        };
+        for (int q = 0; q < NP; ++q) {
+            const int k1 = p->sig_k1[q], k2 = p->sig_k2[q];
+            const float sg = p->sig_sign2[q];
+            float4 *row = htab.data() + (((size_t)part * NP + q) * 2) * Fs;
+            for (int f = 0; f < F; ++f) {
+                row[f] = make_float4(HNM(k1, 0, f, 0), HNM(k1, 0, f, 1), HNM(k1, 1, f, 0), HNM(k1, 1, f, 1));
+                if (k2 >= 0)
+                    row[Fs + f] = make_float4(sg * HNM(k2, 0, f, 0), sg * HNM(k2, 0, f, 1),
+                                              sg * HNM(k2, 1, f, 0), sg * HNM(k2, 1, f, 1));
+            }
         }
     }
     return htab;
 }
+
+size_t queue_elems(const rtb_sh_plan *p) { return (size_t)p->S * p->P * 2 * p->Fp; }
 
 void free_tables(rtb_sh_plan *p) {
     cudaFree(p->d_rmT); p->d_rmT = nullptr;
     cudaFree(p->d_zring); p->d_zring = nullptr;
     cudaFree(p->d_htab); p->d_htab = nullptr;
     cudaFree(p->d_signals); p->d_signals = nullptr;
+    cudaFree(p->d_zspec); p->d_zspec = nullptr;
+    cudaFree(p->d_qcur); p->d_qcur = nullptr;
+    cudaFree(p->d_qlast); p->d_qlast = nullptr;
     p->tables_set = false;
 }
 
@@ -154,10 +171,6 @@ int rtb_sh_plan_create(rtb_sh_plan **out, int device, int n_streams, int block_l
         return fail(RTB_ERR_UNSUPPORTED, "block length %d not supported by the SH renderer "
                     "(supported: 32, 64, 128, 256)", block_length);
     if (n_partitions < 1) return fail(RTB_ERR_INVALID, "n_partitions must be >= 1");
-    if (n_partitions > 1)
-        return fail(RTB_ERR_UNSUPPORTED,
-                    "More than one (%d) blocks would be necessary for loaded filter and partitioned "
-                    "convolution in SH domain is not implemented yet.", n_partitions);
     int ndev = 0;
     RTB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(RTB_ERR_INVALID, "no CUDA device %d", device);
@@ -169,6 +182,7 @@ int rtb_sh_plan_create(rtb_sh_plan **out, int device, int n_streams, int block_l
     p->K = (sh_max_order + 1) * (sh_max_order + 1);
     p->E = n_ears; p->P = n_partitions;
     p->F = block_length + 1; p->N2 = 2 * block_length;
+    p->Fp = (p->F + 3) / 4 * 4;
     p->cur_order = p->last_order = sh_max_order;
 
     DeviceGuard guard(device);
@@ -308,6 +322,13 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     if (err == cudaSuccess) err = cudaMalloc(&p->d_zring, zbytes);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_htab, sizeof(float4) * htab.size());
     if (err == cudaSuccess) err = cudaMalloc(&p->d_signals, sizeof(ShSignal) * NP);
+    if (p->P > 1) {
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_zspec, sizeof(float2) * (size_t)p->S * NP * p->N2);
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_qcur, sizeof(float2) * queue_elems(p));
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_qlast, sizeof(float2) * queue_elems(p));
+        if (err == cudaSuccess) err = cudaMemset(p->d_qcur, 0, sizeof(float2) * queue_elems(p));
+        if (err == cudaSuccess) err = cudaMemset(p->d_qlast, 0, sizeof(float2) * queue_elems(p));
+    }
     if (err != cudaSuccess) {
         free_tables(p);
         return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
@@ -347,6 +368,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
         p->an_grid = n_sm * ctas_per_sm;  // persistent CTAs; capped by the tile count at launch
     }
     p->slot = 0; p->rad_idx = 0;
+    p->head_cur = p->head_last = 0;
     p->cur_order = p->last_order = p->order;
     p->last_valid = false;
     p->tables_set = true;
@@ -391,7 +413,14 @@ int rtb_sh_plan_set_passthrough(rtb_sh_plan *p, int on) {
 int rtb_sh_plan_set_crossfade(rtb_sh_plan *p, int on) {
     if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
     p->crossfade = on != 0;
-    if (!p->crossfade) p->last_valid = false;  // _last_sh_azim_nm.fill(0), _convolver.py:1338-1339
+    if (!p->crossfade) {
+        p->last_valid = false;  // _last_sh_azim_nm.fill(0), _convolver.py:1338-1339
+        if (p->d_qlast) {       // _last_blocks_fd.fill(0), _convolver.py:887-889
+            DeviceGuard guard(p->device);
+            RTB_CUDA(cudaDeviceSynchronize());
+            RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * queue_elems(p)));
+        }
+    }
     return RTB_OK;
 }
 
@@ -411,6 +440,10 @@ int rtb_sh_plan_reset(rtb_sh_plan *p) {
     DeviceGuard guard(p->device);
     // _input_block_td.fill(0); the P == 1 spectra buffers are rewritten every block anyway
     RTB_CUDA(cudaMemset(p->d_zring, 0, sizeof(float) * 2 * (size_t)p->S * p->J * p->B));
+    if (p->P > 1) {  // _blocks_fd.fill(0); _last_blocks_fd.fill(0)
+        RTB_CUDA(cudaMemset(p->d_qcur, 0, sizeof(float2) * queue_elems(p)));
+        RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * queue_elems(p)));
+    }
     return RTB_OK;
 }
 
@@ -428,6 +461,44 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
     if (p->passthrough) {
         const long long total = (long long)count * p->E * p->B;
         sh_passthrough_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_in, d_out, count, p->C, p->E, p->B);
+        if (p->P > 1) {  // queue slot 0 is overwritten and leaves the queue (_convolver.py:558-562, :653-659)
+            const long long n = (long long)count * 2 * p->Fp;
+            sh_queue_clear_head_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                p->d_qcur + (size_t)s0 * p->P * 2 * p->Fp, count, p->P, p->Fp, p->head_cur);
+            p->launches++;
+        }
+    } else if (p->P > 1) {
+        ShPartParams prm;
+        prm.zprev = zprev; prm.zcur = zcur;
+        prm.zspec = p->d_zspec + (size_t)s0 * p->NP * p->N2;
+        prm.htab = p->d_htab; prm.signals = p->d_signals; prm.tw = p->d_tw;
+        prm.win_in = p->d_win_in; prm.win_out = p->d_win_out;
+        prm.yaw_deg = d_yaw_deg;
+        prm.rad_last_in = p->d_radlast + (size_t)p->rad_idx * p->S + s0;
+        prm.rad_last_out = p->d_radlast + (size_t)(p->rad_idx ^ 1) * p->S + s0;
+        prm.qcur = p->d_qcur + (size_t)s0 * p->P * 2 * p->Fp;
+        prm.qlast = p->d_qlast + (size_t)s0 * p->P * 2 * p->Fp;
+        prm.out = d_out;
+        prm.S = count; prm.J = p->J; prm.P = p->P; prm.Fp = p->Fp; prm.NPT = p->NP;
+        prm.np_cur = signals_for_order(p, p->cur_order);
+        prm.np_last = (p->crossfade && p->last_valid) ? signals_for_order(p, p->last_order) : 0;
+        prm.order_max = p->order;
+        prm.crossfade = p->crossfade ? 1 : 0;
+        prm.head_cur = p->head_cur; prm.head_last = p->head_last;
+        prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
+        const unsigned gw = (unsigned)((count + 3) / 4);
+        const dim3 gmac((unsigned)((p->F + 31) / 32), (unsigned)((count + 7) / 8));
+        switch (p->N2) {
+            case 64: sh_spectra_kernel<64><<<gw, 128, 0, st>>>(prm); sh_partition_mac_kernel<64><<<gmac, 128, 0, st>>>(prm);
+                     sh_partition_tail_kernel<64><<<gw, 128, 0, st>>>(prm); break;
+            case 128: sh_spectra_kernel<128><<<gw, 128, 0, st>>>(prm); sh_partition_mac_kernel<128><<<gmac, 128, 0, st>>>(prm);
+                      sh_partition_tail_kernel<128><<<gw, 128, 0, st>>>(prm); break;
+            case 256: sh_spectra_kernel<256><<<gw, 128, 0, st>>>(prm); sh_partition_mac_kernel<256><<<gmac, 128, 0, st>>>(prm);
+                      sh_partition_tail_kernel<256><<<gw, 128, 0, st>>>(prm); break;
+            default: sh_spectra_kernel<512><<<gw, 128, 0, st>>>(prm); sh_partition_mac_kernel<512><<<gmac, 128, 0, st>>>(prm);
+                     sh_partition_tail_kernel<512><<<gw, 128, 0, st>>>(prm); break;
+        }
+        p->launches += 2;
     } else {
         ShRenderParams prm;
         prm.zprev = zprev; prm.zcur = zcur;
@@ -454,7 +525,9 @@ void advance_block(rtb_sh_plan *p) {
         p->rad_idx ^= 1;
         p->last_valid = true;
         p->last_order = p->cur_order;
+        if (p->P > 1) p->head_last = (p->head_last + 1) % p->P;  // the last-yaw queue rolled too
     }
+    if (p->P > 1) p->head_cur = (p->head_cur + 1) % p->P;
     p->slot ^= 1;
 }
 

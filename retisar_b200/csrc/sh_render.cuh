@@ -24,6 +24,79 @@ __device__ __forceinline__ void cp_async16_ca(void *smem_dst, const void *gsrc) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// a6, a7: ear spectra (cur/last x left/right on the bins the lane owns) -> Hermitian extension,
+// inverse FFT of (left + i right), overlap-save discard, cos^2 cross-fade, coalesced store.
+// With G < 32 the current-yaw pair is transformed by group 0 and the previous-yaw pair by group 1
+// at the same time; with G == 32 the warp does them one after the other.
+template <int N2>
+__device__ __forceinline__ void render_tail(float2 (&acc)[FftCfg<N2>::EPL / 2 + 1][4], float2 *buf,
+                                            const float2 *s_tw, int lane, const float *win_in,
+                                            const float *win_out, int crossfade, float *o) {
+    using Cfg = FftCfg<N2>;
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS;
+    constexpr int B = N2 / 2;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int grp = lane / G, l = lane % G;
+    const int partner = (G - l) & (G - 1);
+    __syncwarp();
+    float2 ycur[HB], ylast[HB];
+    constexpr int NITER = (GROUPS >= 2) ? 1 : 2;
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+        const bool use_last = (GROUPS >= 2) ? (grp == 1) : (it == 1);
+        float2 X[EPL], V[HB];
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            float2 eL = use_last ? acc[u][2] : acc[u][0];
+            float2 eR = use_last ? acc[u][3] : acc[u][1];
+            if (u == 0 && l == 0) { eL.y = 0.f; eR.y = 0.f; }  // irfft ignores Im of the DC bin
+            X[u] = make_float2(eL.x - eR.y, eL.y + eR.x);      // Z(f)    = L + i R
+            V[u] = make_float2(eL.x + eR.y, eR.x - eL.y);      // Z(N2-f) = conj(L) + i conj(R)
+        }
+        const float2 nyq = make_float2(use_last ? acc[HB][2].x : acc[HB][0].x,
+                                       use_last ? acc[HB][3].x : acc[HB][1].x);
+#pragma unroll
+        for (int u2 = HB; u2 < EPL; ++u2) {
+            float2 x;
+            x.x = __shfl_sync(FULL, V[EPL - 1 - u2].x, partner, G);
+            x.y = __shfl_sync(FULL, V[EPL - 1 - u2].y, partner, G);
+            if (l == 0) x = (u2 == HB) ? nyq : V[(EPL - u2) % HB];
+            X[u2] = x;
+        }
+        warp_fft<N2, true>(X, buf, s_tw, l);
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            if (GROUPS >= 2 || it == 0) ycur[u] = X[u + HB];
+            if (GROUPS >= 2 || it == 1) ylast[u] = X[u + HB];
+        }
+    }
+    if (GROUPS >= 2) {  // bring the previous-yaw block from group 1 to group 0
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            ylast[u].x = __shfl_sync(FULL, ylast[u].x, (lane + G) & 31);
+            ylast[u].y = __shfl_sync(FULL, ylast[u].y, (lane + G) & 31);
+        }
+    }
+    if (grp == 0) {
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            const int n = l + G * u;
+            float yl, yr;
+            if (crossfade) {
+                const float wi = __ldg(win_in + n), wo = __ldg(win_out + n);
+                yl = ycur[u].x * wi + ylast[u].x * wo;
+                yr = ycur[u].y * wi + ylast[u].y * wo;
+            } else {
+                const float sc = 1.0f / (float)N2;
+                yl = ycur[u].x * sc;
+                yr = ycur[u].y * sc;
+            }
+            o[n] = yl;
+            o[B + n] = yr;
+        }
+    }
+}
+
 template <int N2>
 __global__ void __launch_bounds__(128, RTB_RENDER_MIN_CTAS)
 sh_render_kernel(const ShRenderParams prm) {
@@ -193,68 +266,8 @@ sh_render_kernel(const ShRenderParams prm) {
                 acc[u][q].y += __shfl_xor_sync(FULL, acc[u][q].y, off);
             }
     }
-
-    // ---- a6, a7: Hermitian extension, inverse FFT of (left + i right), discard, cross-fade.
-    // With G < 32 the current-yaw pair is transformed by group 0 and the previous-yaw pair by
-    // group 1 at the same time; with G == 32 the warp does them one after the other.
-    __syncwarp();
-    float2 ycur[HB], ylast[HB];
-    constexpr int NITER = (GROUPS >= 2) ? 1 : 2;
-#pragma unroll
-    for (int it = 0; it < NITER; ++it) {
-        const bool use_last = (GROUPS >= 2) ? (grp == 1) : (it == 1);
-        float2 X[EPL], V[HB];
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-            float2 eL = use_last ? acc[u][2] : acc[u][0];
-            float2 eR = use_last ? acc[u][3] : acc[u][1];
-            if (u == 0 && l == 0) { eL.y = 0.f; eR.y = 0.f; }  // irfft ignores Im of the DC bin
-            X[u] = make_float2(eL.x - eR.y, eL.y + eR.x);      // Z(f)    = L + i R
-            V[u] = make_float2(eL.x + eR.y, eR.x - eL.y);      // Z(N2-f) = conj(L) + i conj(R)
-        }
-        const float2 nyq = make_float2(use_last ? acc[HB][2].x : acc[HB][0].x,
-                                       use_last ? acc[HB][3].x : acc[HB][1].x);
-#pragma unroll
-        for (int u2 = HB; u2 < EPL; ++u2) {
-            float2 x;
-            x.x = __shfl_sync(FULL, V[EPL - 1 - u2].x, partner, G);
-            x.y = __shfl_sync(FULL, V[EPL - 1 - u2].y, partner, G);
-            if (l == 0) x = (u2 == HB) ? nyq : V[(EPL - u2) % HB];
-            X[u2] = x;
-        }
-        warp_fft<N2, true>(X, buf, s_tw, l);
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-            if (GROUPS >= 2 || it == 0) ycur[u] = X[u + HB];
-            if (GROUPS >= 2 || it == 1) ylast[u] = X[u + HB];
-        }
-    }
-    if (GROUPS >= 2) {  // bring the previous-yaw block from group 1 to group 0
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-            ylast[u].x = __shfl_sync(FULL, ylast[u].x, (lane + G) & 31);
-            ylast[u].y = __shfl_sync(FULL, ylast[u].y, (lane + G) & 31);
-        }
-    }
-    if (grp == 0) {
-        float *o = prm.out + (size_t)s * 2 * B;
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-            const int n = l + G * u;
-            float yl, yr;
-            if (prm.crossfade) {
-                const float wi = __ldg(prm.win_in + n), wo = __ldg(prm.win_out + n);
-                yl = ycur[u].x * wi + ylast[u].x * wo;
-                yr = ycur[u].y * wi + ylast[u].y * wo;
-            } else {
-                const float sc = 1.0f / (float)N2;
-                yl = ycur[u].x * sc;
-                yr = ycur[u].y * sc;
-            }
-            o[n] = yl;
-            o[B + n] = yr;
-        }
-    }
+    render_tail<N2>(acc, s_buf[warp] + grp * Cfg::REGION, s_tw, lane, prm.win_in, prm.win_out,
+                    prm.crossfade, prm.out + (size_t)s * 2 * B);
 }
 
 }  // namespace rtb

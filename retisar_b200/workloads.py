@@ -11,6 +11,9 @@ FS = 48000
 CONFIGS = {
     "c2": dict(grid="em32", order=4, block=256, hrir_taps=128,
                desc="Eigenmike em32 (32 ch), SH order 4, 256-sample block, 128-tap KU100-shaped HRIR"),
+    "c3": dict(grid="le110", order=8, block=256, hrir_taps=4096,
+               desc="Lebedev 110-point array, SH order 8, 256-sample block, 4096-tap HRIR as 16 "
+                    "uniform partitions (extension a-X)"),
     "c5": dict(grid="le110", order=8, block=256, hrir_taps=128,
                desc="Lebedev 110-point array, SH order 8, 256-sample block, 128-tap HRIR"),
     "c4": dict(grid="rnd434", order=12, block=64, hrir_taps=64,
@@ -42,6 +45,7 @@ def sh_tables(name, hrir_dirs=2702, seed=7):
     hrir_set = FilterSetMiro.from_arrays(
         syn.decaying_noise_irs((hrir_dirs, 2, c["hrir_taps"]), seed + 1), haz, hco, None, order,
         is_hrir=True)
+    hrir_set.allow_partitions = c["hrir_taps"] > B  # extension a-X (the reference refuses P > 1)
     hrir_set.load(B, True, is_prevent_logging=True)
     K, F = (order + 1) ** 2, B + 1
     return dict(array_set=array_set, hrir_set=hrir_set, sh_config=array_set.get_sh_configuration(),
