@@ -19,11 +19,20 @@
 
 namespace rtb {
 
+// one (signal, term) step of the contraction: which spectrum, mirrored or not, which phase
+struct ShStep {
+    int p;      // signal index
+    int term;   // 0: bin f, 1: conj(bin N2-f)
+    int m;      // phase exp(-i*m*alpha)
+    int pad;
+};
+
 struct ShPartParams {
     const float *zprev, *zcur;   // [S][J][B] analysis rows, previous / current block
     float2 *zspec;               // [S][NPT][N2] spectra of the complex signals (scratch)
     const float4 *htab;          // [P][NPT][2][Fp] (ear0.re, ear0.im, ear1.re, ear1.im)
     const ShSignal *signals;     // [NPT]
+    const struct ShStep *steps;  // flattened (signal, term) list, ordered by signal
     const float2 *tw;
     const float *win_in, *win_out, *yaw_deg, *rad_last_in;
     float *rad_last_out;
@@ -31,6 +40,7 @@ struct ShPartParams {
     float *out;                  // [S][2][B]
     int S, J, P, Fp, NPT;
     int np_cur, np_last, order_max, crossfade, head_cur, head_last;
+    int nsteps_cur, nsteps_last;  // steps (prefix) taking part in the current / previous yaw sum
     float tracker_dir, src_azim16;
 };
 
@@ -110,7 +120,8 @@ sh_partition_mac_kernel(const ShPartParams prm) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * 32 + lane;
     const bool fvalid = f <= B;
-    const int fm = (N2 - f) & (N2 - 1);  // mirrored bin
+    const int fc = fvalid ? f : 0;                 // clamped: out-of-range lanes read bin 0
+    const int fm = (N2 - fc) & (N2 - 1);           // mirrored bin
     const int sbase = (blockIdx.y * 4 + warp) * 2;
     if (sbase >= prm.S) return;
     const bool has_s1 = sbase + 1 < prm.S;
@@ -126,7 +137,7 @@ sh_partition_mac_kernel(const ShPartParams prm) {
         s_cs[warp][st][cl][m] = make_float2(cs, sn);
     }
     __syncwarp();
-    const int np = max(prm.np_cur, prm.np_last);
+    const int nsteps = max(prm.nsteps_cur, prm.nsteps_last);
     const float2 *z0 = prm.zspec + (size_t)sbase * prm.NPT * N2;
     const float2 *z1 = prm.zspec + (size_t)(has_s1 ? sbase + 1 : sbase) * prm.NPT * N2;
     const size_t hq = (size_t)prm.NPT * 2 * prm.Fp;  // H stride between partitions
@@ -139,59 +150,77 @@ sh_partition_mac_kernel(const ShPartParams prm) {
             for (int e = 0; e < 2; ++e)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) acc[a][e][c][0] = acc[a][e][c][1] = make_float2(0.f, 0.f);
-        for (int p = 0; p < np; ++p) {
-            const ShSignal sg = prm.signals[p];
-            const bool in_cur = p < prm.np_cur, in_last = p < prm.np_last;
-            const int nterms = (sg.m2 != RTB_NO_TERM) ? 2 : 1;
-            for (int term = 0; term < nterms; ++term) {
-                const int m = term ? sg.m2 : sg.m1;
-                float2 A[2][2];  // [cur/last][stream]
+        const float4 *hbase = prm.htab + (size_t)q0 * hq + fc;
+        // software pipeline: the loads of step j+1 are in flight while step j is computed
+        ShStep stp = nsteps > 0 ? prm.steps[0] : ShStep{0, 0, 0, 0};
+        float4 h[RTB_QC];
+        float2 zz[2];
+        auto load = [&](const ShStep &st_, float4 (&hh)[RTB_QC], float2 (&z)[2]) {
+            const size_t zo = (size_t)st_.p * N2 + (st_.term ? fm : fc);
+            z[0] = __ldg(z0 + zo);
+            z[1] = __ldg(z1 + zo);
+            const float4 *hp = hbase + ((size_t)st_.p * 2 + st_.term) * prm.Fp;
 #pragma unroll
-                for (int st = 0; st < 2; ++st) {
-                    const float2 *zs = (st ? z1 : z0) + (size_t)p * N2;
-                    float2 z = fvalid ? __ldg(zs + (term ? fm : f)) : make_float2(0.f, 0.f);
-                    if (term) z.y = -z.y;
-                    const float2 pc = in_cur ? phase_of(s_cs[warp][st][0], m) : make_float2(0.f, 0.f);
-                    const float2 pl = in_last ? phase_of(s_cs[warp][st][1], m) : make_float2(0.f, 0.f);
-                    A[0][st] = cmul(pc, z);
-                    A[1][st] = cmul(pl, z);
-                }
-                const float4 *hp = prm.htab + (size_t)q0 * hq + ((size_t)p * 2 + term) * prm.Fp + f;
-#pragma unroll
-                for (int a = 0; a < RTB_QC; ++a) {
-                    if (q0 + a < prm.P && fvalid) {
-                        const float4 h = __ldg(hp + (size_t)a * hq);
-#pragma unroll
-                        for (int c = 0; c < 2; ++c)
-#pragma unroll
-                            for (int st = 0; st < 2; ++st) {
-                                cfma(acc[a][0][c][st], make_float2(h.x, h.y), A[c][st]);
-                                cfma(acc[a][1][c][st], make_float2(h.z, h.w), A[c][st]);
-                            }
-                    }
-                }
+            for (int a = 0; a < RTB_QC; ++a)
+                hh[a] = (q0 + a < prm.P) ? __ldg(hp + (size_t)a * hq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if (nsteps > 0) load(stp, h, zz);
+        for (int j = 0; j < nsteps; ++j) {
+            ShStep nxt = stp;
+            float4 hn[RTB_QC];
+            float2 zn[2];
+            if (j + 1 < nsteps) {
+                nxt = prm.steps[j + 1];
+                load(nxt, hn, zn);
             }
+            const bool in_cur = j < prm.nsteps_cur, in_last = j < prm.nsteps_last;
+            float2 A[2][2];  // [cur/last][stream]
+#pragma unroll
+            for (int st = 0; st < 2; ++st) {
+                float2 z = zz[st];
+                if (stp.term) z.y = -z.y;
+                const float2 pc = in_cur ? phase_of(s_cs[warp][st][0], stp.m) : make_float2(0.f, 0.f);
+                const float2 pl = in_last ? phase_of(s_cs[warp][st][1], stp.m) : make_float2(0.f, 0.f);
+                A[0][st] = cmul(pc, z);
+                A[1][st] = cmul(pl, z);
+            }
+#pragma unroll
+            for (int a = 0; a < RTB_QC; ++a)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int st = 0; st < 2; ++st) {
+                        cfma(acc[a][0][c][st], make_float2(h[a].x, h[a].y), A[c][st]);
+                        cfma(acc[a][1][c][st], make_float2(h[a].z, h[a].w), A[c][st]);
+                    }
+            stp = nxt;
+#pragma unroll
+            for (int a = 0; a < RTB_QC; ++a) h[a] = hn[a];
+            zz[0] = zn[0];
+            zz[1] = zn[1];
         }
         if (fvalid) {
 #pragma unroll
             for (int a = 0; a < RTB_QC; ++a) {
-                if (q0 + a >= prm.P) break;
-                const int sc = (prm.head_cur + q0 + a) % prm.P, sl = (prm.head_last + q0 + a) % prm.P;
+                if (q0 + a < prm.P) {
+                    const int sc = (prm.head_cur + q0 + a) % prm.P, sl = (prm.head_last + q0 + a) % prm.P;
 #pragma unroll
-                for (int st = 0; st < 2; ++st) {
-                    if (st && !has_s1) break;
-                    const size_t sq = (size_t)(sbase + st) * prm.P;
+                    for (int st = 0; st < 2; ++st) {
+                        if (st == 0 || has_s1) {
+                            const size_t sq = (size_t)(sbase + st) * prm.P;
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        float2 *qc = prm.qcur + ((sq + sc) * 2 + e) * prm.Fp + f;
-                        float2 v = *qc;
-                        v.x += acc[a][e][0][st].x; v.y += acc[a][e][0][st].y;
-                        *qc = v;
-                        if (prm.crossfade) {
-                            float2 *ql = prm.qlast + ((sq + sl) * 2 + e) * prm.Fp + f;
-                            float2 w = *ql;
-                            w.x += acc[a][e][1][st].x; w.y += acc[a][e][1][st].y;
-                            *ql = w;
+                            for (int e = 0; e < 2; ++e) {
+                                float2 *qc = prm.qcur + ((sq + sc) * 2 + e) * prm.Fp + f;
+                                float2 v = *qc;
+                                v.x += acc[a][e][0][st].x; v.y += acc[a][e][0][st].y;
+                                *qc = v;
+                                if (prm.crossfade) {
+                                    float2 *ql = prm.qlast + ((sq + sl) * 2 + e) * prm.Fp + f;
+                                    float2 w = *ql;
+                                    w.x += acc[a][e][1][st].x; w.y += acc[a][e][1][st].y;
+                                    *ql = w;
+                                }
+                            }
                         }
                     }
                 }

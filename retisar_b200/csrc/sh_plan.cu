@@ -30,6 +30,8 @@ struct rtb_sh_plan {
     float *d_zring = nullptr;     // [2][S][J][B]
     float4 *d_htab = nullptr;     // [NP][2][F]
     ShSignal *d_signals = nullptr;
+    ShStep *d_steps = nullptr;    // flattened (signal, term) list for the partitioned kernels
+    std::vector<int> steps_prefix;  // steps_prefix[np] = number of steps of the first np signals
     float2 *d_tw = nullptr;       // [N2]
     float *d_win_in = nullptr, *d_win_out = nullptr;
     float *d_radlast = nullptr;   // [2][S]
@@ -147,6 +149,7 @@ void free_tables(rtb_sh_plan *p) {
     cudaFree(p->d_zring); p->d_zring = nullptr;
     cudaFree(p->d_htab); p->d_htab = nullptr;
     cudaFree(p->d_signals); p->d_signals = nullptr;
+    cudaFree(p->d_steps); p->d_steps = nullptr;
     cudaFree(p->d_zspec); p->d_zspec = nullptr;
     cudaFree(p->d_qcur); p->d_qcur = nullptr;
     cudaFree(p->d_qlast); p->d_qlast = nullptr;
@@ -337,6 +340,17 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     RTB_CUDA(cudaMemcpy(p->d_rmT, rmT.data(), sizeof(float) * rmT.size(), cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_htab, htab.data(), sizeof(float4) * htab.size(), cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_signals, sig.data(), sizeof(ShSignal) * NP, cudaMemcpyHostToDevice));
+    {
+        std::vector<ShStep> steps;
+        p->steps_prefix.assign(NP + 1, 0);
+        for (int q = 0; q < NP; ++q) {
+            steps.push_back(ShStep{q, 0, sig[q].m1, 0});
+            if (sig[q].m2 != RTB_NO_TERM) steps.push_back(ShStep{q, 1, sig[q].m2, 0});
+            p->steps_prefix[q + 1] = (int)steps.size();
+        }
+        RTB_CUDA(cudaMalloc(&p->d_steps, sizeof(ShStep) * steps.size()));
+        RTB_CUDA(cudaMemcpy(p->d_steps, steps.data(), sizeof(ShStep) * steps.size(), cudaMemcpyHostToDevice));
+    }
     RTB_CUDA(cudaMemcpy(p->d_win_in, wi.data(), sizeof(float) * B, cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_win_out, wo.data(), sizeof(float) * B, cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemset(p->d_zring, 0, zbytes));
@@ -485,6 +499,9 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         prm.order_max = p->order;
         prm.crossfade = p->crossfade ? 1 : 0;
         prm.head_cur = p->head_cur; prm.head_last = p->head_last;
+        prm.steps = p->d_steps;
+        prm.nsteps_cur = p->steps_prefix[prm.np_cur];
+        prm.nsteps_last = p->steps_prefix[prm.np_last];
         prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
         const unsigned gw = (unsigned)((count + 3) / 4);
         const dim3 gmac((unsigned)((p->F + 31) / 32), (unsigned)((count + 7) / 8));
