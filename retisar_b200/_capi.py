@@ -11,7 +11,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 
 RTB_OK, RTB_ERR_INVALID, RTB_ERR_STATE, RTB_ERR_UNSUPPORTED, RTB_ERR_CUDA, RTB_ERR_NOMEM = range(6)
 RTB_Q_SYMMETRIC, RTB_Q_ROWS, RTB_Q_SIGNALS, RTB_Q_LAUNCHES, RTB_Q_STATE_BYTES = 1, 2, 3, 4, 5
-RTB_Q_ANALYSIS_NS, RTB_Q_RENDER_NS = 6, 7
+RTB_Q_ANALYSIS_NS, RTB_Q_RENDER_NS, RTB_Q_TENSOR_CORE = 6, 7, 8
 
 # every symbol include/retisar_b200.h declares: name -> (restype, argtypes)
 _c_float_p = ctypes.POINTER(ctypes.c_float)

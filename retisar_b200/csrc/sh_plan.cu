@@ -25,6 +25,10 @@ struct rtb_sh_plan {
     // bulk-copy analysis kernel: tile width, pipeline depth, grid, dynamic smem (0 = not usable)
     int an_TW = 0, an_stages = 0, an_grid = 0, an_smem = 0, an_nrun = 2;
     bool an_rsmem = true;
+    // tensor-core analysis kernel (wide arrays): padded sizes, operand table, launch config
+    bool tc_enabled = false;
+    int tc_Kpad = 0, tc_Npad = 0, tc_smem = 0, tc_cols = 0, tc_grid = 0;
+    float *d_tc_b = nullptr;      // [2][Kpad/4][Npad/8][8][4] analysis matrix split into TF32 hi / lo
     // device memory
     float *d_rmT = nullptr;       // [C][Jpad]
     float *d_zring = nullptr;     // [2][S][J][B]
@@ -97,6 +101,18 @@ void launch_analysis_j(const rtb_sh_plan *p, const float *d_in, float *zcur, int
 }
 
 void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int count, cudaStream_t st) {
+    if (p->tc_enabled) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(sh_analysis_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            attr_set = true;
+        }
+        const long long tiles = (long long)count * (p->B / RTB_TC_M);
+        const int grid = (int)std::min<long long>(tiles, (long long)p->tc_grid);
+        sh_analysis_tc_kernel<<<grid, 256, p->tc_smem, st>>>(d_in, p->d_tc_b, zcur, count, p->C, p->J, p->B,
+                                                            p->tc_Kpad, p->tc_Npad, p->tc_cols);
+        return;
+    }
     switch (p->JT) {
         case 4: launch_analysis_j<4>(p, d_in, zcur, count, st); break;
         case 5: launch_analysis_j<5>(p, d_in, zcur, count, st); break;
@@ -150,6 +166,7 @@ void free_tables(rtb_sh_plan *p) {
     cudaFree(p->d_htab); p->d_htab = nullptr;
     cudaFree(p->d_signals); p->d_signals = nullptr;
     cudaFree(p->d_steps); p->d_steps = nullptr;
+    cudaFree(p->d_tc_b); p->d_tc_b = nullptr;
     cudaFree(p->d_zspec); p->d_zspec = nullptr;
     cudaFree(p->d_qcur); p->d_qcur = nullptr;
     cudaFree(p->d_qlast); p->d_qlast = nullptr;
@@ -380,6 +397,35 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device);
         const int ctas_per_sm = std::max(1, std::min(4, (int)((224 * 1024) / (p->an_smem + 2048))));
         p->an_grid = n_sm * ctas_per_sm;  // persistent CTAs; capped by the tile count at launch
+        // tensor-core variant: wide arrays (FP32-bound on SIMT), whole analysis matrix resident in smem
+        p->tc_enabled = false;
+        const char *env = getenv("RTB_ANALYSIS_TC");
+        const bool want = env ? (env[0] != '0') : (C >= 64);
+        const int Kpad = (C + 7) / 8 * 8, Npad = (J + 15) / 16 * 16;
+        const size_t tc_smem = sizeof(float) * 2 * (size_t)Kpad * (RTB_TC_M + Npad);
+        if (want && B % RTB_TC_M == 0 && Npad <= 256 && Kpad <= RTB_TC_MAX_K && tc_smem <= 216 * 1024) {
+            std::vector<float> bsrc(2 * (size_t)Kpad * Npad, 0.f);
+            for (int j = 0; j < J; ++j)
+                for (int c = 0; c < C; ++c) {
+                    const float v = rows[j][c];
+                    uint32_t u;
+                    memcpy(&u, &v, 4);
+                    u = (u + 0x1000u) & 0xffffe000u;  // round to nearest TF32
+                    float hi;
+                    memcpy(&hi, &u, 4);
+                    const size_t off = (((size_t)(c / 4) * (Npad / 8) + j / 8) * 8 + j % 8) * 4 + c % 4;
+                    bsrc[off] = hi;
+                    bsrc[(size_t)Kpad * Npad + off] = v - hi;
+                }
+            cudaError_t e2 = cudaMalloc(&p->d_tc_b, sizeof(float) * bsrc.size());
+            if (e2 == cudaSuccess)
+                e2 = cudaMemcpy(p->d_tc_b, bsrc.data(), sizeof(float) * bsrc.size(), cudaMemcpyHostToDevice);
+            if (e2 != cudaSuccess) return fail(RTB_ERR_CUDA, "tensor-core table upload failed: %s", cudaGetErrorString(e2));
+            p->tc_enabled = true;
+            p->tc_Kpad = Kpad; p->tc_Npad = Npad; p->tc_smem = (int)tc_smem;
+            p->tc_cols = Npad <= 32 ? 32 : (Npad <= 64 ? 64 : (Npad <= 128 ? 128 : 256));
+            p->tc_grid = n_sm;
+        }
     }
     p->slot = 0; p->rad_idx = 0;
     p->head_cur = p->head_last = 0;
@@ -621,6 +667,7 @@ int rtb_sh_plan_query(rtb_sh_plan *p, int what, int64_t *value) {
         case RTB_Q_ROWS: *value = p->J; break;
         case RTB_Q_SIGNALS: *value = p->NP; break;
         case RTB_Q_LAUNCHES: *value = p->launches; break;
+        case RTB_Q_TENSOR_CORE: *value = p->tc_enabled ? 1 : 0; break;
         case RTB_Q_STATE_BYTES: *value = (int64_t)sizeof(float) * (2 * (int64_t)p->J * p->B + 2); break;
         case RTB_Q_ANALYSIS_NS:
         case RTB_Q_RENDER_NS: {

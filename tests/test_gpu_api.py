@@ -104,7 +104,11 @@ def test_errors_match_reference(tables):
     with pytest.raises(NotImplementedError):  # more than one source (`:1036-1039`)
         Convolver.create_instance_by_filter_set(tables["hrir_set"], 256, [(0, 0), (90, 0)], None)
     with pytest.raises(NotImplementedError):  # partitions in the SH domain (`_filter_set.py:1136`)
-        ShPlan(1, 256, 32, 4, n_partitions=2)
+        h = FilterSetMiro.from_arrays(np.zeros((10, 2, 600), np.float32), np.linspace(0, 6, 10),
+                                      np.linspace(0.1, 3, 10), None, 1, True)
+        h.load(256, True, is_prevent_logging=True)
+        h.calculate_filter_blocks_fd(256)
+        h.calculate_filter_blocks_nm()  # 3 blocks: refused unless `allow_partitions` is set
     with pytest.raises(NotImplementedError):
         ShPlan(1, 100, 32, 4)  # unsupported block length
     with pytest.raises(ValueError):
