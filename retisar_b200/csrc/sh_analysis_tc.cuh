@@ -3,7 +3,7 @@
 // (order 8, 110 channels: 23 flop/B).  Included by sh_kernels.cuh.
 //
 //   D[t][j] (TMEM, fp32)  =  A[t][c] (smem, K-major)  x  B[j][c]^T (smem, K-major)
-//   M = 128 samples of one stream, N = rows padded to 16, K = channels padded to 8, kind::tf32.
+//   M = 128 samples of one stream, N = rows padded to 16, K = channels in chunks of KC, kind::tf32.
 //
 // Plain TF32 (10-bit mantissa) would break the 1e-5 parity bar, so both operands are split
 // a = a_hi + a_lo (hi = a rounded to TF32, lo = a - hi, exact in fp32) and three MMAs accumulate
@@ -12,10 +12,16 @@
 // split on the fly while it is scattered from coalesced global loads into the un-swizzled
 // core-matrix layout [c/4][t/8][t%8][c%4] (a thread's four channels form one 16-byte run, a warp
 // writes 512 contiguous bytes).  MN-major operands would avoid that transposition but produced
-// zeros with un-swizzled TF32 descriptors on this part (probe variant 0), so K-major it is.
+// zeros with un-swizzled TF32 descriptors on this part (tools/tc_probe.cu, variant 0), so both
+// operands are K-major.
 //
-// First version: the three phases of a tile (load+split, MMA, epilogue) are not overlapped; the
-// TMA-staged, warp-specialised pipeline is the follow-up.
+// Warp-specialised, persistent (one CTA per SM, 13 warps):
+//   warps 0-3 / 4-7  two loader groups alternating over the K-chunks, each filling its own
+//                    operand stage: row reads (the group's next chunk is requested before the
+//                    current one is processed), TF32 split, scatter, fence.proxy.async
+//   warp 12          one thread issues the MMAs of a chunk and commits the stage back
+//   warps 8-11       epilogue: TMEM lane quarter -> registers -> analysis rows (coalesced 128 B)
+// Two operand stages and two TMEM accumulators let the three roles overlap.
 #pragma once
 
 namespace rtb {
@@ -34,134 +40,192 @@ __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
     lo = v - hi;
 }
 
-#define RTB_TC_M 128
-#define RTB_TC_MAX_K 128  // channels (padded) the register prefetch is sized for
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
 
-__global__ void __launch_bounds__(256, 1)
+#define RTB_TC_M 128
+#define RTB_TC_MAX_KC 64   // channels per pipeline chunk (register staging of the loaders)
+#define RTB_TC_THREADS 416
+
+template <int KC>
+__global__ void __launch_bounds__(RTB_TC_THREADS, 1)
 sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                       const float *__restrict__ bsrc,  // [2][Kpad/4][Npad/8][8][4]: hi then lo
                       float *__restrict__ zcur,        // [S][J][B]
-                      int S, int C, int J, int B, int Kpad, int Npad, int tmem_cols) {
+                      int S, int C, int J, int B, int Kpad, int Npad, int acc_cols) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *a_hi = reinterpret_cast<float *>(smem_raw);   // [Kpad/4][16][8][4]
-    float *a_lo = a_hi + (size_t)Kpad * RTB_TC_M;
-    float *b_hi = a_lo + (size_t)Kpad * RTB_TC_M;        // [Kpad/4][Npad/8][8][4]
+    float *a_stage = reinterpret_cast<float *>(smem_raw);   // [2 stages][hi, lo][KC/4][16][8][4]
+    float *b_hi = a_stage + (size_t)4 * KC * RTB_TC_M;      // [Kpad/4][Npad/8][8][4]
     float *b_lo = b_hi + (size_t)Kpad * Npad;
-    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < Kpad * Npad / 2; i += 256)  // both halves (hi, lo) are contiguous
+    for (int i = tid; i < Kpad * Npad / 2; i += RTB_TC_THREADS)  // hi and lo halves are contiguous
         reinterpret_cast<float4 *>(b_hi)[i] = __ldg(reinterpret_cast<const float4 *>(bsrc) + i);
     if (tid == 0) {
-        mbar_init(&mma_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full_bar[i], 4);    // one arrival per loader warp of the stage's group
+            mbar_init(&empty_bar[i], 1);   // tcgen05.commit
+            mbar_init(&tfull_bar[i], 1);   // tcgen05.commit
+            mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * acc_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // B operand written by generic stores
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Npad >> 3) << 17) |
-                           ((uint32_t)(RTB_TC_M >> 4) << 24);
-    const uint32_t lbo_a = (RTB_TC_M / 8) * 128, lbo_b = (Npad / 8) * 128, sbo = 128;
     const int tiles_per_stream = B / RTB_TC_M;
     const long long n_tiles = (long long)S * tiles_per_stream;
-    const int t_in = tid & 127, khalf = tid >> 7;  // loader: sample, and which half of the k-chunks
-    unsigned parity = 0;
+    const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int n_chunks = Kpad / KC;
+    const long long my_chunks = my_tiles * n_chunks;
+    const size_t stage_floats = (size_t)2 * KC * RTB_TC_M;
 
-    // The tile of the NEXT iteration is fetched into registers right after the MMAs of the current
-    // one are issued, so its HBM latency hides behind the tensor-core work and the epilogue.
-    constexpr int NKC = RTB_TC_MAX_K / 8;  // k-chunks (of 4 channels) per loader thread, at most
-    float xr[NKC][4];
-    auto load_tile = [&](long long tile) {
-        const long long s = tile / tiles_per_stream;
-        const int t0 = (int)(tile % tiles_per_stream) * RTB_TC_M;
-        const float *xs = x + ((size_t)s * C) * B + t0 + t_in;
+    if (warp < 8) {
+        // ===== loaders: thread = sample t of the tile.  Group g = warp / 4 takes the chunks with
+        // n % 2 == g, i.e. always fills stage g.
+        const int t_in = tid & 127, grp_l = warp >> 2;
+        auto issue_loads = [&](long long n, float (&xr)[KC]) {
+            const long long tile = blockIdx.x + (n / n_chunks) * gridDim.x;
+            const int h = (int)(n % n_chunks);
+            const long long s = tile / tiles_per_stream;
+            const int t0 = (int)(tile % tiles_per_stream) * RTB_TC_M;
+            const float *xp = x + ((size_t)s * C + (size_t)h * KC) * B + t0 + t_in;
+            const int cmax = C - h * KC;
 #pragma unroll
-        for (int u = 0; u < NKC; ++u) {
-            const int kc = khalf + 2 * u;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = kc * 4 + i;
-                xr[u][i] = (kc < Kpad / 4 && c < C) ? __ldg(xs + (size_t)c * B) : 0.f;
+            for (int i = 0; i < KC; ++i) {  // predicated: channels beyond C read as zero
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\tmov.f32 %0, 0f00000000;\n\t"
+                    "@p ld.global.nc.f32 %0, [%1];\n\t}"
+                    : "=f"(xr[i]) : "l"(xp), "r"(i), "r"(cmax));
+                xp += B;
             }
-        }
-    };
-    if (blockIdx.x < n_tiles) load_tile(blockIdx.x);
-
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long s = tile / tiles_per_stream;
-        const int t0 = (int)(tile % tiles_per_stream) * RTB_TC_M;
-        // ---- phase 1: split the prefetched samples, scatter into the core-matrix layout
+        };
+        auto process = [&](long long n, float (&xr)[KC]) {
+            const int st = (int)(n & 1);
+            mbar_wait(&empty_bar[st], (unsigned)(((n >> 1) & 1) ^ 1));
+            float *ahi = a_stage + st * stage_floats, *alo = ahi + (size_t)KC * RTB_TC_M;
 #pragma unroll
-        for (int u = 0; u < NKC; ++u) {
-            const int kc = khalf + 2 * u;
-            if (kc < Kpad / 4) {
+            for (int u = 0; u < KC / 4; ++u) {
                 float hi[4], lo[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) split_tf32(xr[u][i], hi[i], lo[i]);
-                const size_t off = (((size_t)kc * (RTB_TC_M / 8) + (t_in >> 3)) * 8 + (t_in & 7)) * 4;
-                *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                for (int i = 0; i < 4; ++i) split_tf32(xr[4 * u + i], hi[i], lo[i]);
+                const size_t off = (((size_t)u * (RTB_TC_M / 8) + (t_in >> 3)) * 8 + (t_in & 7)) * 4;
+                *reinterpret_cast<float4 *>(ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[st]);
+        };
+        float xa[KC], xb[KC];
+        long long n = grp_l;  // this group's chunks: grp_l, grp_l + 2, ...
+        if (n < my_chunks) issue_loads(n, xa);
+        for (; n < my_chunks; n += 4) {
+            if (n + 2 < my_chunks) issue_loads(n + 2, xb);
+            process(n, xa);
+            if (n + 2 < my_chunks) {
+                if (n + 4 < my_chunks) issue_loads(n + 4, xa);
+                process(n + 2, xb);
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor core reads
-        __syncthreads();
-        // ---- phase 2: one thread issues hi*hi + lo*hi + hi*lo over all k-steps
-        if (tid == 0) {
+    } else if (warp == 12) {
+        // ===== MMA issuer (one thread): hi*hi + lo*hi + hi*lo per chunk, accumulating in TMEM
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Npad >> 3) << 17) |
+                                   ((uint32_t)(RTB_TC_M >> 4) << 24);  // D f32, A/B tf32, K-major, N, M
+            const uint32_t lbo_a = (RTB_TC_M / 8) * 128, lbo_b = (Npad / 8) * 128, sbo = 128;
+            const uint64_t step_a = (2 * lbo_a) >> 4, step_b = (2 * lbo_b) >> 4;
+            long long n = 0;
+            for (long long it = 0; it < my_tiles; ++it) {
+                const int acc = (int)(it & 1);
+                mbar_wait(&tempty_bar[acc], (unsigned)(((it >> 1) & 1) ^ 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + acc * acc_cols;
+                for (int h = 0; h < n_chunks; ++h, ++n) {
+                    const int st = (int)(n & 1);
+                    mbar_wait(&full_bar[st], (unsigned)((n >> 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // descriptors differ only in the 14-bit start-address field: build them once per
+                    // chunk and step the field by a constant (no carry: shared memory is < 256 KB)
+                    const uint32_t ahi = smem_u32(a_stage + st * stage_floats);
+                    const uint32_t alo = ahi + (uint32_t)(KC * RTB_TC_M * sizeof(float));
+                    const uint32_t boff = (uint32_t)h * (KC / 4) * lbo_b;  // this chunk's k-range of B
+                    const uint64_t da_hi = umma_desc(ahi, lbo_a, sbo), da_lo = umma_desc(alo, lbo_a, sbo);
+                    const uint64_t db_hi = umma_desc(smem_u32(b_hi) + boff, lbo_b, sbo);
+                    const uint64_t db_lo = umma_desc(smem_u32(b_lo) + boff, lbo_b, sbo);
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint64_t da0 = pass == 1 ? da_lo : da_hi;
+                        const uint64_t db0 = pass == 2 ? db_lo : db_hi;
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ++ks)
+                            umma_tf32(d_tmem, da0 + ks * step_a, db0 + ks * step_b, idesc,
+                                      (h | pass | ks) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[st]);  // the stage is free once these MMAs have read it
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: warp w drains TMEM lanes 32*(w%4).. (rows t) to the analysis rows z[j][t]
+        const int q = warp & 3;
+        for (long long it = 0; it < my_tiles; ++it) {
+            const long long tile = blockIdx.x + it * gridDim.x;
+            const long long s = tile / tiles_per_stream;
+            const int t0 = (int)(tile % tiles_per_stream) * RTB_TC_M;
+            const int acc = (int)(it & 1);
+            mbar_wait(&tfull_bar[acc], (unsigned)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t accumulate = 0;
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t pa = smem_u32(pass == 1 ? a_lo : a_hi);
-                const uint32_t pb = smem_u32(pass == 2 ? b_lo : b_hi);
-                for (int ks = 0; ks < Kpad / 8; ++ks) {
-                    const uint64_t da = umma_desc(pa + ks * 2 * lbo_a, lbo_a, sbo);
-                    const uint64_t db = umma_desc(pb + ks * 2 * lbo_b, lbo_b, sbo);
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-                    accumulate = 1;
+            float *zp = zcur + ((size_t)s * J) * B + t0 + q * 32 + lane;
+            for (int cb = 0; cb < Npad; cb += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * acc_cols + cb, v);
+                const int nrow = J - cb;  // rows of this chunk that exist (uniform)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {  // predicated stores, pointer stepped by one row
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p st.global.b32 [%0], %1;\n\t}"
+                                 ::"l"(zp), "r"(v[j]), "r"(j), "r"(nrow) : "memory");
+                    zp += B;
                 }
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                         ::"r"(smem_u32(&mma_bar)) : "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x);
-        // ---- phase 3: TMEM -> registers -> z rows.  Warp w reads the lane quarter w % 4 (rows t);
-        // the two warps of a quarter alternate over 32-column chunks
-        mbar_wait(&mma_bar, parity);
-        parity ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;
-        float *zt = zcur + ((size_t)s * J) * B + t0 + q * 32 + lane;
-        for (int cb = (warp >> 2) * 32; cb < Npad; cb += 64) {
-            uint32_t v[32];
-            const uint32_t addr = tmem + ((uint32_t)(q * 32) << 16) + cb;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(addr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (cb + j < J) zt[(size_t)(cb + j) * B] = __uint_as_float(v[j]);
-        }
-        // the accumulator and the A buffers are reused by the next tile
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
     }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * acc_cols));
 }
 
 }  // namespace rtb
