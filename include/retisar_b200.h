@@ -118,6 +118,30 @@ int rtb_ols_plan_query(rtb_ols_plan *plan, int what, int64_t *value); /* RTB_Q_L
 int rtb_ols_plan_set_profiling(rtb_ols_plan *plan, int on);
 int rtb_ols_plan_destroy(rtb_ols_plan *plan);
 
+/* HRIR / BRIR switching renderer ----------------------------------------------------------------- */
+/* AdjustableFdConvolver.__init__ (_convolver.py:702-751) for S batched streams: n_sources input
+ * channels per stream, a filter set of n_dirs horizontal directions (FilterSetSsr: 360,
+ * _filter_set.py:843-899) with n_partitions blocks, 2 ears. */
+typedef struct rtb_fd_plan rtb_fd_plan;
+int rtb_fd_plan_create(rtb_fd_plan **plan, int device, int n_streams, int block_length, int n_sources,
+                       int n_dirs, int n_partitions);
+/* _irs_blocks_fd [P][n_dirs][2][F] complex (_filter_set.py:625-664) and the cross-fade windows
+ * (_convolver.py:741-747; NULL = cos^2 default) */
+int rtb_fd_plan_set_filter(rtb_fd_plan *plan, const float *hfd, const float *win_in, const float *win_out);
+/* _sources_deg[:, 0] (_convolver.py:729) and tracker_dir = +1 HRIR / -1 BRIR (_convolver.py:958) */
+int rtb_fd_plan_set_sources(rtb_fd_plan *plan, const float *source_azim_deg, int tracker_dir);
+int rtb_fd_plan_set_passthrough(rtb_fd_plan *plan, int on);
+/* set_crossfade (_convolver.py:868-892): off clears the previous-filter queue */
+int rtb_fd_plan_set_crossfade(rtb_fd_plan *plan, int on);
+int rtb_fd_plan_reset(rtb_fd_plan *plan);
+/* AdjustableFdConvolver.filter_block (_convolver.py:780-836): d_in [S][n_sources][B], d_yaw_deg [S]
+ * -> d_out [S][2][B] */
+int rtb_fd_process_block(rtb_fd_plan *plan, const float *d_in, const float *d_yaw_deg, float *d_out,
+                         void *cuda_stream);
+int rtb_fd_process_block_host(rtb_fd_plan *plan, const float *h_in, const float *h_yaw_deg, float *h_out);
+int rtb_fd_plan_query(rtb_fd_plan *plan, int what, int64_t *value);
+int rtb_fd_plan_destroy(rtb_fd_plan *plan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,6 +136,41 @@ def golden_ols(name, irs, B, T, seed, mono_in=False, events=None, is_hpcf=False)
     print(name, "max|y|", np.abs(outs).max())
 
 
+def golden_fd(name, n_dirs, taps, B, T, seed, sources, is_hrir=True, events=None):
+    """AdjustableFdConvolver.filter_block (`_convolver.py:780-866`) over T blocks."""
+    events = events or {}
+    ref = rh.import_reference()
+    irs = syn.decaying_noise_irs((n_dirs, 2, taps), seed)
+    fset = rh.make_ssr_filter_set(irs, B, is_hrir=is_hrir)
+    tracker = rh.make_tracker()
+    conv = ref._convolver.AdjustableFdConvolver(fset, B, list(sources), tracker)
+    x = syn.noise_blocks(T, len(sources), B, seed + 1)
+    yaws = syn.yaw_walk(T, seed + 2, step=40.0)
+    outs = np.zeros((T, 2, B), dtype=np.float32)
+    ev_codes = np.zeros((T, 2), dtype=np.int32)
+    EV = {"crossfade": 2, "passthrough": 3, "clear": 4}
+    for t in range(T):
+        if t in events:
+            kind, val = events[t]
+            ev_codes[t] = (EV[kind], int(val))
+            if kind == "crossfade":
+                conv.set_crossfade(bool(val))
+            elif kind == "passthrough":
+                conv.set_passthrough(bool(val))
+            else:
+                conv._clear_buffers()
+        tracker[ref.HeadTracker.DataIndex.AZIM] = float(yaws[t])
+        outs[t] = conv.filter_block(x[t].copy())
+    np.savez_compressed(
+        os.path.join(GOLD, f"{name}.npz"), kind="fd", B=B, x=x, yaw=yaws, y=outs,
+        # the 360-direction filter set is regenerated from its seed (syn.decaying_noise_irs);
+        # the checksum guards against a drifting random stream
+        irs_shape=np.asarray(irs.shape), irs_seed=seed, irs_sum=np.float64(np.abs(irs.astype(np.float64)).sum()),
+        sources=np.asarray(sources, dtype=np.float32), is_hrir=is_hrir, events=ev_codes,
+    )
+    print(name, "max|y|", np.abs(outs).max())
+
+
 def golden_tables(name, grid, order, B, seed, enforce_pinv=False):
     """get_sh_configuration / calculate_filter_blocks_fd / _nm (`_filter_set.py:625-664,1093-1280`)."""
     arr, hrir = _array_and_hrir(grid, order, B, 24, min(B, 100), seed, enforce_pinv)
@@ -216,6 +251,13 @@ def main():
     # order 12 on a 434-point pseudo-random grid (c4 geometry), 64-sample block
     rnd434 = syn.random_sphere_grid(434, 434) + (None,)
     golden_sh_chain("sh_rnd434_n12_b64", rnd434, 12, 64, 3, 106, hrir_dirs=400)
+
+    # HRIR / BRIR switching renderer (SSR-style sets)
+    golden_fd("fd_hrir_1src_b64", 360, 150, 64, 20, 301, [(0, 0)],
+              events={7: ("crossfade", 0), 10: ("crossfade", 1), 13: ("passthrough", 1),
+                      15: ("passthrough", 0), 17: ("clear", 0)})
+    golden_fd("fd_brir_2src_b128", 360, 300, 128, 10, 302, [(30, 0), (-45.5, 0)], is_hrir=False)
+    golden_fd("fd_hrir_3src_b32", 360, 40, 32, 12, 303, [(0, 0), (90, 0), (200.25, 0)])
 
     # OLS: benchmark-like 2-ch, partitioned
     golden_ols("ols_2ch_1024_b256", syn.decaying_noise_irs((2, 1024), 201), 256, 8, 202)

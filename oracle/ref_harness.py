@@ -204,3 +204,19 @@ def make_sh_convolver(hrir_set, array_set, block_length, tracker, comp_nm=None,
     conv._input_block_td = np.zeros((conv._sh_bases_weighted.shape[-1], block_length * 2),
                                     dtype=hrir_set.get_dirac_td().dtype)
     return conv
+
+
+def make_ssr_filter_set(irs_td, block_length, is_hrir=True, fs=48000):
+    """Reference `FilterSetSsr` filled from an array [directions; 2; taps] instead of the 720-channel
+    WAV that `FilterSetSsr._load` reads (`_filter_set.py:852-881`)."""
+    ref = import_reference()
+    fset = ref._filter_set.FilterSetSsr(file_name="SYNTHETIC", is_hrir=is_hrir)
+    fset._irs_td = np.ascontiguousarray(irs_td)
+    fset._fs = fs
+    fset._points_azim_deg = np.linspace(0, 360, irs_td.shape[0], endpoint=False, dtype=np.int16)
+    fset._points_elev_deg = np.zeros_like(fset._points_azim_deg)
+    fset._irs_orig_shape = fset._irs_td.shape
+    fset._zero_pad(block_length=block_length)
+    fset._dirac_td = np.zeros(fset._irs_td.shape[-2:], dtype=fset._irs_td.dtype)
+    fset._dirac_td[:, 0] = 1.0
+    return fset

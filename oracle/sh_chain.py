@@ -323,3 +323,83 @@ class ShPartitionedOracle(ShOracle):
         self.last_blocks_fd, y_out = self._roll(self.last_blocks_fd)
         self.last_sh_azim_nm = sh_azim
         return (y_in * self.w_in) + (y_out * self.w_out)
+
+
+# --------------------------------------------------------------------------------------------
+# f3: HRIR / BRIR switching renderer
+# --------------------------------------------------------------------------------------------
+class FdOracle:
+    """`AdjustableFdConvolver` (`_convolver.py:672-975`) with a `FilterSetSsr`
+    (`_filter_set.py:843-899`): per source the filter of the direction `int(-azimuth)` is applied
+    at input time into a P-partition output queue, a second queue receives the previous block's
+    filters, heads are cross-faded.
+
+    irs_blocks_fd: [P, directions, 2, F] complex.
+    """
+
+    def __init__(self, irs_blocks_fd, block_length, sources_deg, is_hrir=True):
+        self.B = block_length
+        self.H = irs_blocks_fd
+        P, _, E, F = irs_blocks_fd.shape
+        cdtype = irs_blocks_fd.dtype
+        rdtype = np.float32 if cdtype == np.complex64 else np.float64
+        self.sources_deg = np.array(sources_deg, dtype=np.float16)  # `:729`
+        n_src = self.sources_deg.shape[0]
+        self.blocks_fd = np.zeros((P, 1, E, F), dtype=cdtype)  # `:732`
+        self.last_blocks_fd = np.zeros_like(self.blocks_fd)  # `:750`
+        self.last_filters_fd = np.zeros((1, P, E, F), dtype=cdtype)  # `:751` (dirac-shaped)
+        self.input_block_td = np.zeros((n_src, 2 * self.B), dtype=rdtype)  # `:735-738`
+        self.is_hrir = is_hrir
+        self.is_crossfade = True
+        self.is_passthrough = False
+        self.w_in, self.w_out = crossfade_windows(self.B, rdtype)
+
+    def set_crossfade(self, state):  # `:868-892`
+        self.is_crossfade = state
+        if not state:
+            self.last_blocks_fd.fill(0)
+            self.last_filters_fd.fill(0)
+
+    def clear(self):  # `:774-778`
+        self.input_block_td.fill(0)
+        self.blocks_fd.fill(0)
+        self.last_blocks_fd.fill(0)
+
+    def _current_filters(self, yaw_deg):  # `:913-945`
+        tracker_dir = 1 if self.is_hrir else -1
+        azims = (tracker_dir * float(yaw_deg) + self.sources_deg[:, 0] + 360.0) % 360.0
+        return np.stack([self.H[:, int(-a)] for a in azims])  # `_filter_set.py:898-899`
+
+    @staticmethod
+    def _multiply(blocks_fd, filters_fd, x_fd):  # `:838-866`
+        for s in range(filters_fd.shape[0]):
+            for block_fd, filter_fd in zip(blocks_fd, filters_fd[s]):
+                block_fd[0] += filter_fd * x_fd[s] / filters_fd.shape[0]
+
+    @staticmethod
+    def _roll(blocks_fd):  # `:624-669`
+        first_td = np.fft.irfft(blocks_fd[0])
+        if blocks_fd.shape[0] > 1:
+            blocks_fd = np.roll(blocks_fd, -1, axis=0)
+        blocks_fd[-1] = 0.0
+        return blocks_fd, first_td[0, :, first_td.shape[-1] // 2:]
+
+    def filter_block(self, x, yaw_deg):  # `:780-836`
+        B = self.B
+        self.input_block_td[:, :B] = self.input_block_td[:, B:]
+        self.input_block_td[:, B:] = x
+        x_fd = np.fft.rfft(self.input_block_td)
+        if self.is_passthrough:  # `:799-800` -> `:558-562`
+            x_fd = x_fd[: self.blocks_fd.shape[-2]]
+            self.blocks_fd[0, 0, : x_fd.shape[-2]] = x_fd
+            self.blocks_fd, y = self._roll(self.blocks_fd)
+            return y
+        filters_fd = self._current_filters(yaw_deg)
+        self._multiply(self.blocks_fd, filters_fd, x_fd)
+        self.blocks_fd, y_in = self._roll(self.blocks_fd)
+        if not self.is_crossfade:
+            return y_in
+        self._multiply(self.last_blocks_fd, self.last_filters_fd, x_fd)
+        self.last_blocks_fd, y_out = self._roll(self.last_blocks_fd)
+        self.last_filters_fd = filters_fd
+        return (y_in * self.w_in) + (y_out * self.w_out)

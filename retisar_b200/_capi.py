@@ -43,6 +43,16 @@ SIGNATURES = {
     "rtb_ols_plan_query": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
     "rtb_ols_plan_set_profiling": (_i, [_vp, _i]),
     "rtb_ols_plan_destroy": (_i, [_vp]),
+    "rtb_fd_plan_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
+    "rtb_fd_plan_set_filter": (_i, [_vp, _vp, _vp, _vp]),
+    "rtb_fd_plan_set_sources": (_i, [_vp, _vp, _i]),
+    "rtb_fd_plan_set_passthrough": (_i, [_vp, _i]),
+    "rtb_fd_plan_set_crossfade": (_i, [_vp, _i]),
+    "rtb_fd_plan_reset": (_i, [_vp]),
+    "rtb_fd_process_block": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "rtb_fd_process_block_host": (_i, [_vp, _vp, _vp, _vp]),
+    "rtb_fd_plan_query": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
+    "rtb_fd_plan_destroy": (_i, [_vp]),
 }
 
 

@@ -15,7 +15,7 @@ import numpy as np
 from . import config
 from ._filter_set import FilterSetMiro, FilterSetMultiChannel, FilterSetSofa, FilterSetSsr  # noqa: F401
 from ._tracker import HeadTracker
-from .plans import OlsPlan, ShPlan
+from .plans import FdPlan, OlsPlan, ShPlan
 from . import sph
 
 
@@ -37,7 +37,8 @@ class Convolver(object):
                                              device=device)
         elif type(filter_set) == FilterSetSsr:
             convolver = AdjustableFdConvolver(filter_set, block_length, source_positions,
-                                              shared_tracker_data)
+                                              shared_tracker_data, n_streams=n_streams,
+                                              device=device)
         elif filter_set.get_sh_configuration().arir_config:
             convolver = OverlapSaveConvolver(filter_set, block_length, n_streams=n_streams,
                                              device=device)
@@ -192,12 +193,8 @@ class OverlapSaveConvolver(Convolver):
 
 
 class AdjustableFdConvolver(OverlapSaveConvolver):
-    """HRIR/BRIR-switching renderer (``_convolver.py:672-975``).
-
-    Only the parts the SH renderer inherits are implemented (source positions, tracker access,
-    cross-fade windows and switches); direction-switched partitioned rendering itself is listed
-    as a later row in SURVEY.md section 8f.
-    """
+    """HRIR / BRIR switching renderer (``_convolver.py:672-975``): per source the filter pair of the
+    direction given by the head yaw is applied, previous and current filters are cross-faded."""
 
     def __init__(self, filter_set, block_length, source_positions, shared_tracker_data,
                  n_streams=1, device=None):
@@ -214,15 +211,49 @@ class AdjustableFdConvolver(OverlapSaveConvolver):
         w = np.arange(self._block_length, dtype=rdtype)
         self._window_out_td = np.square(np.cos(w * np.pi / (2 * (self._block_length - 1))))
         self._window_in_td = np.flip(self._window_out_td).copy()
+        if type(self) is AdjustableFdConvolver:
+            hfd = self._filter._irs_blocks_fd  # [P, directions, 2, F]
+            self._plan = FdPlan(self._n_streams, block_length, self._sources_deg.shape[0],
+                                hfd.shape[1], hfd.shape[0], device=self._device)
+            self._plan.set_filter(hfd, self._window_in_td, self._window_out_td)
+            self._plan.set_sources(self._sources_deg[:, 0].astype(np.float32),
+                                   1 if self._filter._is_hrir else -1)
 
-    def filter_block(self, input_block_td):
+    def __copy__(self):
+        new = type(self)(copy(self._filter), self._block_length,
+                         [tuple(float(v) for v in row) for row in self._sources_deg],
+                         self._tracker_deg, n_streams=self._n_streams, device=self._device)
+        new.set_crossfade(self._is_crossfade)
+        new.set_passthrough(self._is_passthrough)
+        return new
+
+    def filter_block(self, input_block_td, yaw_deg=None):
+        """One block through the direction-switched renderer (``_convolver.py:780-836``):
+        input [sources; B] -> [2; B]; batched and torch-tensor forms as for the SH renderer."""
         if input_block_td is None:
             return Convolver.filter_block(self, None)
-        raise NotImplementedError("direction-switched HRIR/BRIR rendering is not built yet")
+        plan = self._plan
+        if yaw_deg is None:
+            azim = self._tracker_deg[HeadTracker.DataIndex.AZIM] if self._tracker_deg is not None else 0.0
+            yaw_deg = np.full(plan.S, azim, dtype=np.float32)
+        if _is_torch_tensor(input_block_td):
+            import torch
+
+            x = input_block_td.reshape(plan.S, plan.NS, plan.B).contiguous()
+            if not _is_torch_tensor(yaw_deg):
+                yaw_deg = torch.as_tensor(np.asarray(yaw_deg, dtype=np.float32), device=x.device)
+            out = torch.empty((plan.S, 2, plan.B), dtype=torch.float32, device=x.device)
+            plan.process_device(x, yaw_deg.contiguous(), out, torch.cuda.current_stream(x.device))
+            return out if input_block_td.dim() == 3 else out[0]
+        x = np.asarray(input_block_td, dtype=np.float32)
+        out = plan.process_host(x.reshape(plan.S, plan.NS, plan.B), yaw_deg)
+        return out if x.ndim == 3 else out[0]
 
     def set_crossfade(self, new_state=None):
-        """``_convolver.py:868-892``"""
+        """``_convolver.py:868-892``: switching off also clears the previous-filter state."""
         self._is_crossfade = (not self._is_crossfade) if new_state is None else bool(new_state)
+        if type(self) is AdjustableFdConvolver and self._plan is not None:
+            self._plan.set_crossfade(self._is_crossfade)
         return self._is_crossfade
 
     def get_input_channel_count(self):

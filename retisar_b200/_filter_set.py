@@ -300,12 +300,27 @@ class FilterSetMultiChannel(FilterSet):
 class FilterSetSsr(FilterSet):
     """360 horizontal HRIR / BRIR pairs, SoundScapeRenderer layout (``_filter_set.py:843-899``)."""
 
+    @classmethod
+    def from_arrays(cls, irs_td, is_hrir=True, fs=48000):
+        """Extension: a set from an in-memory array [directions; 2; samples] (the reference only
+        reads the 720-channel WAV layout).  Call ``load()`` afterwards."""
+        obj = cls("GENERATED", is_hrir)
+        obj._arrays = dict(irs_td=np.asarray(irs_td), fs=fs)
+        return obj
+
+    def _describe_source(self):
+        return "GENERATED" if hasattr(self, "_arrays") else super()._describe_source()
+
     def _load(self, dtype):
-        if not isinstance(self._file_name, str):
-            raise TypeError(f'unknown parameter type "{type(self._file_name)}".')
-        data, self._fs = _read_audio(self._file_name, dtype)
-        left, right = data[:, 0:-1:2].T, data[:, 1::2].T
-        self._irs_td = np.ascontiguousarray(np.stack((left, right), axis=1))
+        if hasattr(self, "_arrays"):
+            self._irs_td = np.ascontiguousarray(self._arrays["irs_td"], dtype=dtype)
+            self._fs = int(self._arrays["fs"])
+        else:
+            if not isinstance(self._file_name, str):
+                raise TypeError(f'unknown parameter type "{type(self._file_name)}".')
+            data, self._fs = _read_audio(self._file_name, dtype)
+            left, right = data[:, 0:-1:2].T, data[:, 1::2].T
+            self._irs_td = np.ascontiguousarray(np.stack((left, right), axis=1))
         self._points_azim_deg = np.linspace(0, 360, self._irs_td.shape[0], endpoint=False,
                                             dtype=np.int16)
         self._points_elev_deg = np.zeros_like(self._points_azim_deg)

@@ -1,0 +1,423 @@
+// HRIR / BRIR switching renderer for S batched streams (reference: AdjustableFdConvolver,
+// ReTiSAR/_convolver.py:672-975, with a FilterSetSsr, _filter_set.py:843-899).
+//
+// Per block and stream: every source signal is transformed (overlap-save), the filter pair of the
+// direction int(-azimuth) is picked per source from the head yaw (float16 chain, :947-975), and
+// H[dir][p] * X / n_sources is added into slot p of an OUTPUT-side queue of P ear spectra
+// (:838-866); a second queue receives the previous block's directions; the heads are inverse
+// transformed, cross-faded (:833-836) and leave the queue (:645-665).  The filter changes from
+// block to block, so unlike the time-invariant OLS convolver the partition sum has to stay on the
+// output side.  One warp per stream, spectra and the queue head in registers.
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "sh_kernels.cuh"
+
+using namespace rtb;
+
+namespace {
+
+struct FdParams {
+    const float *x;            // [S][NS][B]
+    const float *xprev;        // [S][NS][B] state (read)
+    float *xnext;              // [S][NS][B] state (write)
+    const float2 *hfd;         // [n_dirs][P][2][Fp]
+    float2 *qcur, *qlast;      // [S][P][2][Fp] output-side queues (rings)
+    const float *yaw_deg;      // [S]
+    const float *src_azim16;   // [NS] source azimuths, already rounded to float16
+    const int *dir_last_in;    // [S][NS] direction index of the previous block
+    int *dir_last_out;         // [S][NS]
+    const float2 *tw;
+    const float *win_in, *win_out;
+    float *out;                // [S][2][B]
+    int S, NS, P, Fp, n_dirs, head_cur, head_last, crossfade, last_valid, passthrough;
+    float tracker_dir, inv_ns;
+};
+
+// float16 azimuth chain of _calculate_individual_directions -> direction index int(-az)
+__device__ __forceinline__ int direction_index(float yaw_deg, float tracker_dir, float src16, int n_dirs) {
+    float a = rn16(tracker_dir * yaw_deg);
+    a = rn16(a + src16);
+    a = rn16(a + 360.0f);
+    float r = fmodf(a, 360.0f);
+    if (r != 0.0f && r < 0.0f) r += 360.0f;
+    if (!(r >= 0.0f)) return 0;  // NaN yaw (|yaw| beyond float16): the reference fails here
+    const int k = (int)r;  // int(-az) == -trunc(az); python negative indexing wraps once
+    return k == 0 ? 0 : n_dirs - k;
+}
+
+template <int N2>
+__global__ void __launch_bounds__(128)
+fd_render_kernel(const FdParams prm) {
+    using Cfg = FftCfg<N2>;
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS, B = N2 / 2;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ float2 s_tw[N2];
+    __shared__ __align__(16) float2 s_buf[4][GROUPS * Cfg::REGION];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, l = lane % G;
+    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+    __syncthreads();
+    const int s = blockIdx.x * 4 + warp;
+    if (s >= prm.S) return;
+    // with G < 32 every group redundantly processes the same stream (sources are few); group 0 writes
+    float2 *buf = s_buf[warp] + grp * Cfg::REGION;
+    const int partner = (G - l) & (G - 1);
+    const int Fp = prm.Fp, NS = prm.NS;
+    const float yaw = prm.passthrough ? 0.f : prm.yaw_deg[s];
+
+    float2 acc[HB + 1][4];  // queue heads: [bin slot][cur L, cur R, last L, last R]
+    float2 *qc = prm.qcur + (size_t)s * prm.P * 2 * Fp, *ql = prm.qlast + (size_t)s * prm.P * 2 * Fp;
+    const bool do_last = prm.crossfade && !prm.passthrough;
+#pragma unroll
+    for (int u = 0; u <= HB; ++u) {
+        const int f = (u < HB) ? (l + G * u) : B;
+        acc[u][0] = qc[((size_t)prm.head_cur * 2 + 0) * Fp + f];
+        acc[u][1] = qc[((size_t)prm.head_cur * 2 + 1) * Fp + f];
+        acc[u][2] = do_last ? ql[((size_t)prm.head_last * 2 + 0) * Fp + f] : make_float2(0.f, 0.f);
+        acc[u][3] = do_last ? ql[((size_t)prm.head_last * 2 + 1) * Fp + f] : make_float2(0.f, 0.f);
+    }
+
+    for (int s0 = 0; s0 < NS; s0 += 2) {  // two sources per complex FFT
+        const bool has1 = s0 + 1 < NS;
+        float2 X[EPL];
+        const size_t r0 = ((size_t)s * NS + s0) * B + l, r1 = r0 + B;
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            X[u].x = prm.xprev[r0 + G * u];
+            X[u + HB].x = prm.x[r0 + G * u];
+            X[u].y = has1 ? prm.xprev[r1 + G * u] : 0.f;
+            X[u + HB].y = has1 ? prm.x[r1 + G * u] : 0.f;
+        }
+        if (grp == 0) {
+#pragma unroll
+            for (int u = 0; u < HB; ++u) {
+                prm.xnext[r0 + G * u] = X[u + HB].x;
+                if (has1) prm.xnext[r1 + G * u] = X[u + HB].y;
+            }
+        }
+        __syncwarp();
+        warp_fft<N2, false>(X, buf, s_tw, l);
+        float2 X0[HB + 1], X1[HB + 1];
+#pragma unroll
+        for (int u = 0; u <= HB; ++u) {
+            const float2 zf = X[u];
+            float2 zp;
+            if (u < HB) {
+                zp.x = __shfl_sync(FULL, X[EPL - 1 - u].x, partner, G);
+                zp.y = __shfl_sync(FULL, X[EPL - 1 - u].y, partner, G);
+                if (l == 0) zp = (u == 0) ? X[0] : X[(EPL - u) % EPL];
+            } else {
+                zp = X[HB];
+            }
+            X0[u] = make_float2(0.5f * (zf.x + zp.x), 0.5f * (zf.y - zp.y));
+            X1[u] = make_float2(0.5f * (zf.y + zp.y), 0.5f * (zp.x - zf.x));
+        }
+        if (prm.passthrough) {  // queue slot 0 := spectra of the first two sources (_convolver.py:558-562)
+            if (s0 == 0) {
+#pragma unroll
+                for (int u = 0; u <= HB; ++u) { acc[u][0] = X0[u]; if (has1) acc[u][1] = X1[u]; }
+            }
+            continue;
+        }
+        // directions of the two sources for the current and the previous block
+        const int dc0 = direction_index(yaw, prm.tracker_dir, prm.src_azim16[s0], prm.n_dirs);
+        const int dc1 = has1 ? direction_index(yaw, prm.tracker_dir, prm.src_azim16[s0 + 1], prm.n_dirs) : 0;
+        const int dl0 = prm.dir_last_in[(size_t)s * NS + s0];
+        const int dl1 = has1 ? prm.dir_last_in[(size_t)s * NS + s0 + 1] : 0;
+        if (prm.crossfade && lane == 0) {
+            prm.dir_last_out[(size_t)s * NS + s0] = dc0;
+            if (has1) prm.dir_last_out[(size_t)s * NS + s0 + 1] = dc1;
+        }
+        const bool use_last = do_last && prm.last_valid;
+        const size_t dstride = (size_t)prm.P * 2 * Fp;
+        for (int p = 0; p < prm.P; ++p) {
+            const float2 *hc0 = prm.hfd + dc0 * dstride + (size_t)p * 2 * Fp;
+            const float2 *hc1 = prm.hfd + dc1 * dstride + (size_t)p * 2 * Fp;
+            const float2 *hl0 = prm.hfd + dl0 * dstride + (size_t)p * 2 * Fp;
+            const float2 *hl1 = prm.hfd + dl1 * dstride + (size_t)p * 2 * Fp;
+            float2 *qcp = qc + (size_t)((prm.head_cur + p) % prm.P) * 2 * Fp;
+            float2 *qlp = ql + (size_t)((prm.head_last + p) % prm.P) * 2 * Fp;
+#pragma unroll
+            for (int u = 0; u <= HB; ++u) {
+                const int f = (u < HB) ? (l + G * u) : B;
+                const bool own = (u < HB) || (l == 0);
+                const float2 a0 = make_float2(X0[u].x * prm.inv_ns, X0[u].y * prm.inv_ns);
+                const float2 a1 = make_float2(X1[u].x * prm.inv_ns, X1[u].y * prm.inv_ns);
+                float2 c[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    cfma(c[e], __ldg(hc0 + (size_t)e * Fp + f), a0);
+                    if (has1) cfma(c[e], __ldg(hc1 + (size_t)e * Fp + f), a1);
+                    if (use_last) {
+                        cfma(c[2 + e], __ldg(hl0 + (size_t)e * Fp + f), a0);
+                        if (has1) cfma(c[2 + e], __ldg(hl1 + (size_t)e * Fp + f), a1);
+                    }
+                }
+                if (p == 0) {  // the head stays in registers
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { acc[u][q].x += c[q].x; acc[u][q].y += c[q].y; }
+                } else if (own && grp == 0) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        float2 v = qcp[(size_t)e * Fp + f];
+                        v.x += c[e].x; v.y += c[e].y;
+                        qcp[(size_t)e * Fp + f] = v;
+                        if (use_last) {
+                            float2 w = qlp[(size_t)e * Fp + f];
+                            w.x += c[2 + e].x; w.y += c[2 + e].y;
+                            qlp[(size_t)e * Fp + f] = w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // the heads leave the queues
+    __syncwarp();
+    if (grp == 0) {
+#pragma unroll
+        for (int u = 0; u <= HB; ++u) {
+            const int f = (u < HB) ? (l + G * u) : B;
+            if (u < HB || l == 0) {
+                qc[((size_t)prm.head_cur * 2 + 0) * Fp + f] = make_float2(0.f, 0.f);
+                qc[((size_t)prm.head_cur * 2 + 1) * Fp + f] = make_float2(0.f, 0.f);
+                if (do_last) {
+                    ql[((size_t)prm.head_last * 2 + 0) * Fp + f] = make_float2(0.f, 0.f);
+                    ql[((size_t)prm.head_last * 2 + 1) * Fp + f] = make_float2(0.f, 0.f);
+                }
+            }
+        }
+    }
+    render_tail<N2>(acc, buf, s_tw, lane, prm.win_in, prm.win_out, do_last ? 1 : 0,
+                    prm.out + (size_t)s * 2 * B);
+}
+
+}  // namespace
+
+struct rtb_fd_plan {
+    int device = 0;
+    int S = 0, B = 0, NS = 0, n_dirs = 0, P = 0, F = 0, Fp = 0, N2 = 0;
+    bool filter_set = false;
+    float *d_xstate = nullptr;            // [2][S][NS][B]
+    float2 *d_hfd = nullptr;              // [n_dirs][P][2][Fp]
+    float2 *d_qcur = nullptr, *d_qlast = nullptr;
+    int *d_dirlast = nullptr;             // [2][S][NS]
+    float *d_src = nullptr;               // [NS]
+    float2 *d_tw = nullptr;
+    float *d_win_in = nullptr, *d_win_out = nullptr;
+    float *d_in = nullptr, *d_yaw = nullptr, *d_out = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int par = 0, dir_idx = 0, head_cur = 0, head_last = 0;
+    bool crossfade = true, passthrough = false, last_valid = false;
+    float tracker_dir = 1.f;
+    long long launches = 0;
+};
+
+namespace {
+size_t fd_queue_elems(const rtb_fd_plan *p) { return (size_t)p->S * p->P * 2 * p->Fp; }
+size_t fd_state_elems(const rtb_fd_plan *p) { return (size_t)p->S * p->NS * p->B; }
+}  // namespace
+
+extern "C" {
+
+int rtb_fd_plan_create(rtb_fd_plan **out, int device, int n_streams, int block_length, int n_sources,
+                       int n_dirs, int n_partitions) {
+    if (!out) return fail(RTB_ERR_INVALID, "plan output pointer is NULL");
+    *out = nullptr;
+    if (n_streams < 1 || n_dirs < 1 || n_partitions < 1) return fail(RTB_ERR_INVALID, "sizes must be >= 1");
+    if (n_sources < 1)
+        return fail(RTB_ERR_INVALID, "no virtual source positions (according to playback file channel count) given.");
+    if (block_length != 32 && block_length != 64 && block_length != 128 && block_length != 256)
+        return fail(RTB_ERR_UNSUPPORTED, "block length %d not supported (supported: 32, 64, 128, 256)", block_length);
+    int ndev = 0;
+    RTB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(RTB_ERR_INVALID, "no CUDA device %d", device);
+    rtb_fd_plan *p = new (std::nothrow) rtb_fd_plan();
+    if (!p) return fail(RTB_ERR_NOMEM, "out of host memory");
+    p->device = device; p->S = n_streams; p->B = block_length; p->NS = n_sources; p->n_dirs = n_dirs;
+    p->P = n_partitions; p->F = block_length + 1; p->Fp = (p->F + 3) / 4 * 4; p->N2 = 2 * block_length;
+    DeviceGuard guard(device);
+    cudaError_t err = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_xstate, sizeof(float) * 2 * fd_state_elems(p));
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_hfd, sizeof(float2) * (size_t)n_dirs * p->P * 2 * p->Fp);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_qcur, sizeof(float2) * fd_queue_elems(p));
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_qlast, sizeof(float2) * fd_queue_elems(p));
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_dirlast, sizeof(int) * 2 * (size_t)p->S * p->NS);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_src, sizeof(float) * p->NS);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_tw, sizeof(float2) * p->N2);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_win_in, sizeof(float) * p->B);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_win_out, sizeof(float) * p->B);
+    if (err == cudaSuccess) err = cudaMemset(p->d_src, 0, sizeof(float) * p->NS);
+    if (err == cudaSuccess) err = cudaMemset(p->d_dirlast, 0, sizeof(int) * 2 * (size_t)p->S * p->NS);
+    if (err != cudaSuccess) {
+        rtb_fd_plan_destroy(p);
+        return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
+                    "plan allocation failed: %s", cudaGetErrorString(err));
+    }
+    std::vector<float2> tw(p->N2);
+    for (int q = 0; q < p->N2; ++q) {
+        const double a = -2.0 * M_PI * q / p->N2;
+        tw[q] = make_float2((float)cos(a), (float)sin(a));
+    }
+    RTB_CUDA(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * p->N2, cudaMemcpyHostToDevice));
+    *out = p;
+    return rtb_fd_plan_reset(p);
+}
+
+int rtb_fd_plan_set_filter(rtb_fd_plan *p, const float *hfd, const float *win_in, const float *win_out) {
+    if (!p || !hfd) return fail(RTB_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(p->device);
+    // reference layout [P][dirs][2][F] -> device layout [dirs][P][2][Fp]
+    std::vector<float2> h((size_t)p->n_dirs * p->P * 2 * p->Fp, make_float2(0.f, 0.f));
+    for (int q = 0; q < p->P; ++q)
+        for (int d = 0; d < p->n_dirs; ++d)
+            for (int e = 0; e < 2; ++e)
+                for (int f = 0; f < p->F; ++f) {
+                    const size_t i = ((((size_t)q * p->n_dirs + d) * 2 + e) * p->F + f);
+                    h[(((size_t)d * p->P + q) * 2 + e) * p->Fp + f] = make_float2(hfd[2 * i], hfd[2 * i + 1]);
+                }
+    std::vector<float> wi(p->B), wo(p->B);
+    for (int n = 0; n < p->B; ++n) {
+        float o, i;
+        if (win_in && win_out) { i = win_in[n]; o = win_out[n]; }
+        else {
+            const double c0 = cos(n * M_PI / (2.0 * (p->B - 1))), c1 = cos((p->B - 1 - n) * M_PI / (2.0 * (p->B - 1)));
+            o = (float)(c0 * c0); i = (float)(c1 * c1);
+        }
+        wi[n] = i / (float)p->N2; wo[n] = o / (float)p->N2;
+    }
+    RTB_CUDA(cudaDeviceSynchronize());
+    RTB_CUDA(cudaMemcpy(p->d_hfd, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(p->d_win_in, wi.data(), sizeof(float) * p->B, cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(p->d_win_out, wo.data(), sizeof(float) * p->B, cudaMemcpyHostToDevice));
+    p->filter_set = true;
+    return RTB_OK;
+}
+
+int rtb_fd_plan_set_sources(rtb_fd_plan *p, const float *source_azim_deg, int tracker_dir) {
+    if (!p || !source_azim_deg) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (tracker_dir != 1 && tracker_dir != -1) return fail(RTB_ERR_INVALID, "tracker_dir must be +1 or -1");
+    DeviceGuard guard(p->device);
+    std::vector<float> src(p->NS);
+    for (int i = 0; i < p->NS; ++i) src[i] = __half2float(__float2half_rn(source_azim_deg[i]));
+    RTB_CUDA(cudaMemcpy(p->d_src, src.data(), sizeof(float) * p->NS, cudaMemcpyHostToDevice));
+    p->tracker_dir = (float)tracker_dir;
+    return RTB_OK;
+}
+
+int rtb_fd_plan_set_passthrough(rtb_fd_plan *p, int on) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    p->passthrough = on != 0;
+    return RTB_OK;
+}
+
+int rtb_fd_plan_set_crossfade(rtb_fd_plan *p, int on) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    p->crossfade = on != 0;
+    if (!p->crossfade) {  // _last_blocks_fd.fill(0); _last_filters_fd.fill(0)  (_convolver.py:887-890)
+        DeviceGuard guard(p->device);
+        RTB_CUDA(cudaDeviceSynchronize());
+        RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * fd_queue_elems(p)));
+        p->last_valid = false;
+    }
+    return RTB_OK;
+}
+
+int rtb_fd_plan_reset(rtb_fd_plan *p) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    DeviceGuard guard(p->device);
+    RTB_CUDA(cudaMemset(p->d_xstate, 0, sizeof(float) * 2 * fd_state_elems(p)));
+    RTB_CUDA(cudaMemset(p->d_qcur, 0, sizeof(float2) * fd_queue_elems(p)));
+    RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * fd_queue_elems(p)));
+    return RTB_OK;
+}
+
+int rtb_fd_process_block(rtb_fd_plan *p, const float *d_in, const float *d_yaw_deg, float *d_out, void *cuda_stream) {
+    if (!p || !d_in || !d_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (!p->filter_set) return fail(RTB_ERR_STATE, "blocks in frequency domain have not been calculated yet.");
+    if (!d_yaw_deg && !p->passthrough) return fail(RTB_ERR_INVALID, "NULL yaw pointer");
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    FdParams prm;
+    prm.x = d_in;
+    prm.xprev = p->d_xstate + (size_t)p->par * fd_state_elems(p);
+    prm.xnext = p->d_xstate + (size_t)(p->par ^ 1) * fd_state_elems(p);
+    prm.hfd = p->d_hfd; prm.qcur = p->d_qcur; prm.qlast = p->d_qlast;
+    prm.yaw_deg = d_yaw_deg ? d_yaw_deg : p->d_src;  // unused in passthrough
+    prm.src_azim16 = p->d_src;
+    prm.dir_last_in = p->d_dirlast + (size_t)p->dir_idx * p->S * p->NS;
+    prm.dir_last_out = p->d_dirlast + (size_t)(p->dir_idx ^ 1) * p->S * p->NS;
+    prm.tw = p->d_tw; prm.win_in = p->d_win_in; prm.win_out = p->d_win_out; prm.out = d_out;
+    prm.S = p->S; prm.NS = p->NS; prm.P = p->P; prm.Fp = p->Fp; prm.n_dirs = p->n_dirs;
+    prm.head_cur = p->head_cur; prm.head_last = p->head_last;
+    prm.crossfade = p->crossfade ? 1 : 0; prm.last_valid = p->last_valid ? 1 : 0;
+    prm.passthrough = p->passthrough ? 1 : 0;
+    prm.tracker_dir = p->tracker_dir; prm.inv_ns = 1.0f / (float)p->NS;
+    const unsigned grid = (unsigned)((p->S + 3) / 4);
+    switch (p->N2) {
+        case 64: fd_render_kernel<64><<<grid, 128, 0, st>>>(prm); break;
+        case 128: fd_render_kernel<128><<<grid, 128, 0, st>>>(prm); break;
+        case 256: fd_render_kernel<256><<<grid, 128, 0, st>>>(prm); break;
+        default: fd_render_kernel<512><<<grid, 128, 0, st>>>(prm); break;
+    }
+    p->launches++;
+    p->par ^= 1;
+    p->head_cur = (p->head_cur + 1) % p->P;
+    if (!p->passthrough && p->crossfade) {  // _last_filters_fd = filters (_convolver.py:829-831)
+        p->head_last = (p->head_last + 1) % p->P;
+        p->dir_idx ^= 1;
+        p->last_valid = true;
+    }
+    RTB_CUDA(cudaGetLastError());
+    return RTB_OK;
+}
+
+int rtb_fd_process_block_host(rtb_fd_plan *p, const float *h_in, const float *h_yaw_deg, float *h_out) {
+    if (!p || !h_in || !h_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(p->device);
+    const size_t n_in = fd_state_elems(p), n_out = (size_t)p->S * 2 * p->B;
+    if (!p->d_in) {
+        cudaError_t err = cudaMalloc(&p->d_in, sizeof(float) * n_in);
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_out, sizeof(float) * n_out);
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_yaw, sizeof(float) * p->S);
+        if (err == cudaSuccess) err = cudaMemset(p->d_yaw, 0, sizeof(float) * p->S);
+        if (err != cudaSuccess) return fail(RTB_ERR_NOMEM, "staging allocation failed: %s", cudaGetErrorString(err));
+    }
+    RTB_CUDA(cudaMemcpyAsync(p->d_in, h_in, sizeof(float) * n_in, cudaMemcpyHostToDevice, p->own_stream));
+    if (h_yaw_deg)
+        RTB_CUDA(cudaMemcpyAsync(p->d_yaw, h_yaw_deg, sizeof(float) * p->S, cudaMemcpyHostToDevice, p->own_stream));
+    int rc = rtb_fd_process_block(p, p->d_in, p->d_yaw, p->d_out, p->own_stream);
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaMemcpyAsync(h_out, p->d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost, p->own_stream));
+    RTB_CUDA(cudaStreamSynchronize(p->own_stream));
+    return RTB_OK;
+}
+
+int rtb_fd_plan_query(rtb_fd_plan *p, int what, int64_t *value) {
+    if (!p || !value) return fail(RTB_ERR_INVALID, "NULL argument");
+    switch (what) {
+        case RTB_Q_LAUNCHES: *value = p->launches; break;
+        case RTB_Q_STATE_BYTES:
+            *value = (int64_t)sizeof(float2) * 2 * p->P * 2 * p->Fp + (int64_t)sizeof(float) * 2 * p->NS * p->B;
+            break;
+        default: return fail(RTB_ERR_INVALID, "unknown query %d", what);
+    }
+    return RTB_OK;
+}
+
+int rtb_fd_plan_destroy(rtb_fd_plan *p) {
+    if (!p) return RTB_OK;
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_xstate); cudaFree(p->d_hfd); cudaFree(p->d_qcur); cudaFree(p->d_qlast);
+    cudaFree(p->d_dirlast); cudaFree(p->d_src); cudaFree(p->d_tw); cudaFree(p->d_win_in); cudaFree(p->d_win_out);
+    cudaFree(p->d_in); cudaFree(p->d_yaw); cudaFree(p->d_out);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+    return RTB_OK;
+}
+
+}  // extern "C"

@@ -233,7 +233,7 @@ namespace rtb {
 
 // a10: passthrough.  irfft(rfft(buffer))[B:] is the current block itself, so the first E input
 // channels are copied to the ears (_convolver.py:558-562); missing channels stay silent.
-__global__ void sh_passthrough_kernel(const float *__restrict__ x, float *__restrict__ out,
+static __global__ void sh_passthrough_kernel(const float *__restrict__ x, float *__restrict__ out,
                                       int S, int C, int E, int B) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)S * E * B;

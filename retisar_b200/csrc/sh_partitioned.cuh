@@ -271,7 +271,7 @@ sh_partition_tail_kernel(const ShPartParams prm) {
 }
 
 // passthrough with partitions: the head of the current queue is dropped and the queue advances
-__global__ void sh_queue_clear_head_kernel(float2 *q, int S, int P, int Fp, int head) {
+static __global__ void sh_queue_clear_head_kernel(float2 *q, int S, int P, int Fp, int head) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per = 2LL * Fp;
     if (i >= (long long)S * per) return;

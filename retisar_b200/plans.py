@@ -164,3 +164,62 @@ class OlsPlan:
 
     def process_device(self, d_x, d_out, stream=None):
         check(lib.rtb_ols_process_block(self._h, _dev_ptr(d_x), _dev_ptr(d_out), _stream_ptr(stream)))
+
+
+class FdPlan:
+    """S batched HRIR / BRIR switching renderers (C ABI ``rtb_fd_*``)."""
+
+    def __init__(self, n_streams, block_length, n_sources, n_dirs, n_partitions, device=0):
+        self._h = ctypes.c_void_p()
+        check(lib.rtb_fd_plan_create(ctypes.byref(self._h), device, n_streams, block_length,
+                                     n_sources, n_dirs, n_partitions))
+        self.S, self.B, self.NS, self.n_dirs, self.P = n_streams, block_length, n_sources, n_dirs, n_partitions
+        self.F, self.E, self.device = block_length + 1, 2, device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.rtb_fd_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def set_filter(self, hfd, win_in=None, win_out=None):
+        hfd = np.ascontiguousarray(hfd, dtype=np.complex64)
+        if hfd.shape != (self.P, self.n_dirs, 2, self.F):
+            raise ValueError(f"filter blocks shape {hfd.shape} != {(self.P, self.n_dirs, 2, self.F)}")
+        if win_in is not None:
+            win_in = np.ascontiguousarray(win_in, dtype=np.float32)
+            win_out = np.ascontiguousarray(win_out, dtype=np.float32)
+        check(lib.rtb_fd_plan_set_filter(self._h, np_ptr(hfd), np_ptr(win_in), np_ptr(win_out)))
+
+    def set_sources(self, source_azim_deg, tracker_dir=1):
+        src = np.ascontiguousarray(source_azim_deg, dtype=np.float32).reshape(self.NS)
+        check(lib.rtb_fd_plan_set_sources(self._h, np_ptr(src), int(tracker_dir)))
+
+    def set_passthrough(self, on):
+        check(lib.rtb_fd_plan_set_passthrough(self._h, int(bool(on))))
+
+    def set_crossfade(self, on):
+        check(lib.rtb_fd_plan_set_crossfade(self._h, int(bool(on))))
+
+    def reset(self):
+        check(lib.rtb_fd_plan_reset(self._h))
+
+    def query(self, what):
+        v = ctypes.c_int64()
+        check(lib.rtb_fd_plan_query(self._h, what, ctypes.byref(v)))
+        return v.value
+
+    def process_host(self, x, yaw_deg, out=None):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.shape != (self.S, self.NS, self.B):
+            raise ValueError(f"input shape {x.shape} != {(self.S, self.NS, self.B)}")
+        yaw = None if yaw_deg is None else np.ascontiguousarray(yaw_deg, dtype=np.float32).reshape(self.S)
+        if out is None:
+            out = np.empty((self.S, 2, self.B), dtype=np.float32)
+        check(lib.rtb_fd_process_block_host(self._h, np_ptr(x), np_ptr(yaw), np_ptr(out)))
+        return out
+
+    def process_device(self, d_x, d_yaw, d_out, stream=None):
+        check(lib.rtb_fd_process_block(self._h, _dev_ptr(d_x), _dev_ptr(d_yaw), _dev_ptr(d_out),
+                                       _stream_ptr(stream)))

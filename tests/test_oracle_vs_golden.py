@@ -112,3 +112,33 @@ def test_yaw_chain_matches_reference():
                 assert np.array_equal(az[0], g[f"az_{tag}"][i], equal_nan=True)
                 ph = oc.sh_rotation_phases(az, m)
                 assert np.array_equal(ph, g[f"ph_{tag}"][i], equal_nan=True)
+
+
+FD_CASES = ["fd_hrir_1src_b64", "fd_brir_2src_b128", "fd_hrir_3src_b32"]
+
+
+def fd_filter_set(g):
+    from retisar_b200 import synthetic as syn
+
+    irs = syn.decaying_noise_irs(tuple(g["irs_shape"]), int(g["irs_seed"]))
+    assert abs(np.abs(irs.astype(np.float64)).sum() - float(g["irs_sum"])) < 1e-6, "random stream drifted"
+    return irs
+
+
+@pytest.mark.parametrize("name", FD_CASES)
+def test_fd_oracle_matches_reference(name):
+    """AdjustableFdConvolver restatement vs the unmodified reference (bit exact)."""
+    g = load_golden(name)
+    B = int(g["B"])
+    H = oc.filter_blocks_fd(oc.zero_pad(fd_filter_set(g), B), B)
+    o = oc.FdOracle(H, B, g["sources"], bool(g["is_hrir"]))
+    for t in range(g["x"].shape[0]):
+        kind, val = g["events"][t]
+        if kind == 2:
+            o.set_crossfade(bool(val))
+        elif kind == 3:
+            o.is_passthrough = bool(val)
+        elif kind == 4:
+            o.clear()
+        y = o.filter_block(g["x"][t], g["yaw"][t])
+        assert np.array_equal(y, g["y"][t]), (t, np.abs(y - g["y"][t]).max())
