@@ -291,6 +291,12 @@ def run_gpu_arm(args):
         chain_bytes = S * wl.chain_bytes_per_stream_block(C, B, E)
         chain_flops = S * wl.chain_flops_per_stream_block(C, tb["K"], B, E)
         achieved = render_bytes / (re_us * 1e-6) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(f"{args.workload}:{S}", {}).get("bytes")
+        except (OSError, ValueError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -311,7 +317,7 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "sh_render_kernel", "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": render_bytes, "us_per_launch": re_us},
             "kernels": {"sh_analysis_kernel": {"us": an_us, "bytes": analysis_bytes,
                                                "GBps": analysis_bytes / (an_us * 1e-6) / 1e9},
