@@ -7,7 +7,9 @@ raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or
 import ctypes
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libretisar_b200.so")
+# RTB_LIB_PATH: load another build of the same library (A/B runs of kernel variants)
+_LIB_PATH = os.environ.get("RTB_LIB_PATH") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "lib", "libretisar_b200.so")
 
 RTB_OK, RTB_ERR_INVALID, RTB_ERR_STATE, RTB_ERR_UNSUPPORTED, RTB_ERR_CUDA, RTB_ERR_NOMEM = range(6)
 RTB_Q_SYMMETRIC, RTB_Q_ROWS, RTB_Q_SIGNALS, RTB_Q_LAUNCHES, RTB_Q_STATE_BYTES = 1, 2, 3, 4, 5

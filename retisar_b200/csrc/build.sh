@@ -2,7 +2,7 @@
 # Build libretisar_b200.so for sm_100a (B200) in-tree.  Usage: retisar_b200/csrc/build.sh [extra nvcc flags]
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-out="$here/../lib"
+out="${RTB_OUT_DIR:-$here/../lib}"
 mkdir -p "$out"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo \

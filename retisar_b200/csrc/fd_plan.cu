@@ -50,22 +50,27 @@ __device__ __forceinline__ int direction_index(float yaw_deg, float tracker_dir,
 }
 
 template <int N2>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FftCfg<N2>::THREADS)
 fd_render_kernel(const FdParams prm) {
     using Cfg = FftCfg<N2>;
     constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS, B = N2 / 2;
-    constexpr unsigned FULL = 0xffffffffu;
-    __shared__ float2 s_tw[N2];
-    __shared__ __align__(16) float2 s_buf[4][GROUPS * Cfg::REGION];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane / G, l = lane % G;
-    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
-    __syncthreads();
-    const int s = blockIdx.x * 4 + warp;
+    constexpr bool BIG = Cfg::BIG;  // one stream per CTA, exchange buffer in dynamic smem
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ float2 s_tw[BIG ? 1 : N2];
+    __shared__ __align__(16) float2 s_buf[BIG ? 1 : 4 * GROUPS * Cfg::REGION];
+    const int warp = BIG ? 0 : (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int grp = BIG ? 0 : lane / G, l = BIG ? (int)threadIdx.x : lane % G;
+    const float2 *tw = prm.tw;
+    float2 *buf = reinterpret_cast<float2 *>(dyn_smem);
+    if constexpr (!BIG) {
+        for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+        __syncthreads();
+        tw = s_tw;
+        buf = s_buf + (warp * GROUPS + grp) * Cfg::REGION;
+    }
+    const int s = BIG ? (int)blockIdx.x : (int)blockIdx.x * 4 + warp;
     if (s >= prm.S) return;
     // with G < 32 every group redundantly processes the same stream (sources are few); group 0 writes
-    float2 *buf = s_buf[warp] + grp * Cfg::REGION;
-    const int partner = (G - l) & (G - 1);
     const int Fp = prm.Fp, NS = prm.NS;
     const float yaw = prm.passthrough ? 0.f : prm.yaw_deg[s];
 
@@ -99,20 +104,14 @@ fd_render_kernel(const FdParams prm) {
                 if (has1) prm.xnext[r1 + G * u] = X[u + HB].y;
             }
         }
-        __syncwarp();
-        warp_fft<N2, false>(X, buf, s_tw, l);
+        fft_sync<N2>();
+        warp_fft<N2, false>(X, buf, tw, l);
         float2 X0[HB + 1], X1[HB + 1];
+        float2 M[HB + 1];
+        fft_mirror<N2>(X, M, buf, l);
 #pragma unroll
         for (int u = 0; u <= HB; ++u) {
-            const float2 zf = X[u];
-            float2 zp;
-            if (u < HB) {
-                zp.x = __shfl_sync(FULL, X[EPL - 1 - u].x, partner, G);
-                zp.y = __shfl_sync(FULL, X[EPL - 1 - u].y, partner, G);
-                if (l == 0) zp = (u == 0) ? X[0] : X[(EPL - u) % EPL];
-            } else {
-                zp = X[HB];
-            }
+            const float2 zf = X[u], zp = M[u];
             X0[u] = make_float2(0.5f * (zf.x + zp.x), 0.5f * (zf.y - zp.y));
             X1[u] = make_float2(0.5f * (zf.y + zp.y), 0.5f * (zp.x - zf.x));
         }
@@ -128,7 +127,7 @@ fd_render_kernel(const FdParams prm) {
         const int dc1 = has1 ? direction_index(yaw, prm.tracker_dir, prm.src_azim16[s0 + 1], prm.n_dirs) : 0;
         const int dl0 = prm.dir_last_in[(size_t)s * NS + s0];
         const int dl1 = has1 ? prm.dir_last_in[(size_t)s * NS + s0 + 1] : 0;
-        if (prm.crossfade && lane == 0) {
+        if (prm.crossfade && (BIG ? threadIdx.x == 0 : lane == 0)) {
             prm.dir_last_out[(size_t)s * NS + s0] = dc0;
             if (has1) prm.dir_last_out[(size_t)s * NS + s0 + 1] = dc1;
         }
@@ -177,7 +176,7 @@ fd_render_kernel(const FdParams prm) {
         }
     }
     // the heads leave the queues
-    __syncwarp();
+    fft_sync<N2>();
     if (grp == 0) {
 #pragma unroll
         for (int u = 0; u <= HB; ++u) {
@@ -192,7 +191,7 @@ fd_render_kernel(const FdParams prm) {
             }
         }
     }
-    render_tail<N2>(acc, buf, s_tw, lane, prm.win_in, prm.win_out, do_last ? 1 : 0,
+    render_tail<N2>(acc, buf, tw, grp, l, prm.win_in, prm.win_out, do_last ? 1 : 0,
                     prm.out + (size_t)s * 2 * B);
 }
 
@@ -231,8 +230,8 @@ int rtb_fd_plan_create(rtb_fd_plan **out, int device, int n_streams, int block_l
     if (n_streams < 1 || n_dirs < 1 || n_partitions < 1) return fail(RTB_ERR_INVALID, "sizes must be >= 1");
     if (n_sources < 1)
         return fail(RTB_ERR_INVALID, "no virtual source positions (according to playback file channel count) given.");
-    if (block_length != 32 && block_length != 64 && block_length != 128 && block_length != 256)
-        return fail(RTB_ERR_UNSUPPORTED, "block length %d not supported (supported: 32, 64, 128, 256)", block_length);
+    if (!block_length_supported(block_length))
+        return fail(RTB_ERR_UNSUPPORTED, "block length %d not supported (supported: " RTB_BLOCK_LENGTHS ")", block_length);
     int ndev = 0;
     RTB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(RTB_ERR_INVALID, "no CUDA device %d", device);
@@ -357,13 +356,9 @@ int rtb_fd_process_block(rtb_fd_plan *p, const float *d_in, const float *d_yaw_d
     prm.crossfade = p->crossfade ? 1 : 0; prm.last_valid = p->last_valid ? 1 : 0;
     prm.passthrough = p->passthrough ? 1 : 0;
     prm.tracker_dir = p->tracker_dir; prm.inv_ns = 1.0f / (float)p->NS;
-    const unsigned grid = (unsigned)((p->S + 3) / 4);
-    switch (p->N2) {
-        case 64: fd_render_kernel<64><<<grid, 128, 0, st>>>(prm); break;
-        case 128: fd_render_kernel<128><<<grid, 128, 0, st>>>(prm); break;
-        case 256: fd_render_kernel<256><<<grid, 128, 0, st>>>(prm); break;
-        default: fd_render_kernel<512><<<grid, 128, 0, st>>>(prm); break;
-    }
+#define RTB_FD_LAUNCH(N) fft_kernel_launch<N>(fd_render_kernel<N>, prm, p->S, st, 0, 4)
+    RTB_DISPATCH_N2(p->N2, RTB_FD_LAUNCH)
+#undef RTB_FD_LAUNCH
     p->launches++;
     p->par ^= 1;
     p->head_cur = (p->head_cur + 1) % p->P;

@@ -1,8 +1,9 @@
 // Warp-level complex FFT (Stockham autosort, radix 8/4/2) held in registers, with the inter-pass
 // exchange through a warp-private, XOR-swizzled shared-memory buffer.
 //
-// A transform of N2 points is owned by a "group" of G lanes (G = 32 for N2 >= 256, N2/8 below),
-// so small transforms run 2 or 4 per warp side by side.  Lane l of a group holds EPL = N2/G
+// A transform of N2 points is owned by a "group" of G lanes (G = 32 for N2 = 256 and 512, N2/8
+// below, so small transforms run 2 or 4 per warp side by side; N2/16 lanes = a whole CTA for
+// N2 >= 1024, with the same code and __syncthreads between the passes).  Lane l of a group holds EPL = N2/G
 // complex values X[u] <-> element index l + G*u, before the first and after the last pass.  That
 // layout is what the callers build directly from coalesced global loads and consume directly in
 // registers (no shared-memory round trip for the spectrum): elements u < EPL/2 of the result are
@@ -17,13 +18,27 @@ namespace rtb {
 
 template <int N2>
 struct FftCfg {
-    static_assert(N2 == 64 || N2 == 128 || N2 == 256 || N2 == 512, "unsupported FFT length");
-    static constexpr int G = (N2 >= 256) ? 32 : N2 / 8;  // lanes per transform
+    static_assert(N2 >= 64 && N2 <= 8192 && (N2 & (N2 - 1)) == 0, "unsupported FFT length");
+    // lanes per transform: a fraction of a warp (N2 < 256), one warp, or -- for N2 >= 1024 -- a
+    // whole CTA of N2/16 threads ("big" transforms: exchanges go through __syncthreads)
+    static constexpr int G = (N2 >= 512) ? N2 / 16 : ((N2 >= 256) ? 32 : N2 / 8);
+    static constexpr bool BIG = G > 32;
     static constexpr int EPL = N2 / G;                   // complex elements per lane (8 or 16)
-    static constexpr int GROUPS = 32 / G;                // transforms per warp
-    static constexpr int R_LAST = (N2 == 64) ? 0 : (N2 == 128 ? 2 : (N2 == 256 ? 4 : 8));
+    static constexpr int GROUPS = BIG ? 1 : 32 / G;      // transforms per warp
+    // radix-8 passes through shared memory, then one register pass of radix R_LAST (0 = none)
+    static constexpr int NPASS8 = (N2 >= 4096) ? 4 : ((N2 >= 512) ? 3 : 2);
+    static constexpr int R_LAST = N2 >> (3 * NPASS8) == 1 ? 0 : N2 >> (3 * NPASS8);
     static constexpr int REGION = N2 + (N2 == 64 ? 8 : 0);  // float2 slots per transform buffer
+    static constexpr int THREADS = BIG ? G : 128;        // CTA size of the kernels built on it
+    static constexpr int TASKS = BIG ? 1 : 4 * GROUPS;   // transforms side by side per CTA
 };
+
+// barrier over the lanes of one transform
+template <int N2>
+__device__ __forceinline__ void fft_sync() {
+    if constexpr (FftCfg<N2>::BIG) __syncthreads();
+    else __syncwarp();
+}
 
 // Conflict-free placement for every access pattern of the passes below; found by brute force,
 // see tools/swizzle_search.py (2 wavefronts per 64-bit warp access = the minimum).
@@ -41,8 +56,6 @@ template <bool INV>
 __device__ __forceinline__ float2 rot90(float2 a) {
     return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
 template <bool INV>
 __device__ __forceinline__ void dft2(float2 &b0, float2 &b1) {
@@ -65,14 +78,9 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
     const float h = 0.70710678118654752440f;
     float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
     float2 d0 = csub(v[0], v[4]), e1 = csub(v[1], v[5]), e2 = csub(v[2], v[6]), e3 = csub(v[3], v[7]);
-    float2 d1, d3;
-    if (INV) {
-        d1 = make_float2(h * (e1.x - e1.y), h * (e1.x + e1.y));
-        d3 = make_float2(h * (-e3.x - e3.y), h * (e3.x - e3.y));
-    } else {
-        d1 = make_float2(h * (e1.x + e1.y), h * (e1.y - e1.x));
-        d3 = make_float2(h * (e3.y - e3.x), h * (-e3.x - e3.y));
-    }
+    // d1 = e1 * exp(-+i pi/4) = h (e1 + rot90(e1)),  d3 = e3 * exp(-+3i pi/4) = h (rot90(e3) - e3)
+    float2 d1 = cscale(cadd(e1, rot90<INV>(e1)), h);
+    float2 d3 = cscale(csub(rot90<INV>(e3), e3), h);
     float2 d2 = rot90<INV>(e2);
     dft4<INV>(a0, a1, a2, a3);
     dft4<INV>(d0, d1, d2, d3);
@@ -136,29 +144,135 @@ __device__ __forceinline__ void fft_pass(float2 (&X)[FftCfg<N2>::EPL], float2 *b
 template <int N2>
 __device__ __forceinline__ void fft_exchange(float2 (&X)[FftCfg<N2>::EPL], const float2 *buf, int l) {
     using Cfg = FftCfg<N2>;
-    __syncwarp();
+    fft_sync<N2>();
     const int lbase = fft_swz<N2>(l);
 #pragma unroll
     for (int u = 0; u < Cfg::EPL; ++u) X[u] = buf[lbase ^ fft_swz<N2>(Cfg::G * u)];
-    __syncwarp();
+    fft_sync<N2>();
 }
 
 // In-register transform of the group's N2 points.  `buf` = this group's REGION of shared memory,
-// `tw` = exp(-2*pi*i*q/N2), q < N2 (shared memory), l = lane index inside the group.
-// All 32 lanes of the warp must call it together.
+// `tw` = exp(-2*pi*i*q/N2), q < N2 (shared or global memory), l = lane index inside the group.
+// All lanes of the group (and of the warp) must call it together.
+// `after_last_exchange()` runs once the exchange buffer is idle (before the final register pass):
+// the place to start prefetching the next input into it.
+template <int N2, bool INV, class Hook>
+__device__ __forceinline__ void warp_fft_hook(float2 (&X)[FftCfg<N2>::EPL], float2 *buf,
+                                              const float2 *tw, int l, Hook &&after_last_exchange) {
+    using Cfg = FftCfg<N2>;
+    constexpr int NP = Cfg::NPASS8;
+    constexpr bool TAIL = Cfg::R_LAST != 0;
+    fft_pass<N2, 8, 1, INV, true>(X, buf, tw, l);
+    fft_exchange<N2>(X, buf, l);
+    if constexpr (NP == 2 && !TAIL) after_last_exchange();
+    fft_pass<N2, 8, 8, INV, (NP > 2 || TAIL)>(X, buf, tw, l);
+    if constexpr (NP > 2 || TAIL) fft_exchange<N2>(X, buf, l);
+    if constexpr (NP >= 3) {
+        if constexpr (NP == 3 && !TAIL) after_last_exchange();
+        fft_pass<N2, 8, 64, INV, (NP > 3 || TAIL)>(X, buf, tw, l);
+        if constexpr (NP > 3 || TAIL) fft_exchange<N2>(X, buf, l);
+    }
+    if constexpr (NP >= 4) {
+        if constexpr (!TAIL) after_last_exchange();
+        fft_pass<N2, 8, 512, INV, TAIL>(X, buf, tw, l);
+        if constexpr (TAIL) fft_exchange<N2>(X, buf, l);
+    }
+    if constexpr (TAIL) {
+        after_last_exchange();
+        fft_pass<N2, Cfg::R_LAST, (1 << (3 * NP)), INV, false>(X, buf, tw, l);
+    }
+}
+
 template <int N2, bool INV>
 __device__ __forceinline__ void warp_fft(float2 (&X)[FftCfg<N2>::EPL], float2 *buf,
                                          const float2 *tw, int l) {
+    warp_fft_hook<N2, INV>(X, buf, tw, l, [] {});
+}
+
+// After a forward transform lane l holds element l + G*u in X[u].  Mirror access: the element at
+// index (N2 - f) mod N2 for the bins f = l + G*u, u < EPL/2, the lane owns, plus (slot EPL/2) the
+// Nyquist element itself.  Inside a warp that is slot EPL-1-u of lane G-l (lane 0: its own
+// slots); a CTA-wide transform goes through the exchange buffer (natural order).
+template <int N2>
+__device__ __forceinline__ void fft_mirror(const float2 (&X)[FftCfg<N2>::EPL],
+                                           float2 (&M)[FftCfg<N2>::EPL / 2 + 1], float2 *buf, int l) {
     using Cfg = FftCfg<N2>;
-    fft_pass<N2, 8, 1, INV, true>(X, buf, tw, l);
-    fft_exchange<N2>(X, buf, l);
-    if constexpr (Cfg::R_LAST == 0) {
-        fft_pass<N2, 8, 8, INV, false>(X, buf, tw, l);
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2;
+    if constexpr (Cfg::BIG) {
+#pragma unroll
+        for (int u = HB; u < EPL; ++u) buf[l + G * u] = X[u];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < HB; ++u) M[u] = (u == 0 && l == 0) ? X[0] : buf[N2 - (l + G * u)];
+        M[HB] = X[HB];
+        __syncthreads();
     } else {
-        fft_pass<N2, 8, 8, INV, true>(X, buf, tw, l);
-        fft_exchange<N2>(X, buf, l);
-        fft_pass<N2, Cfg::R_LAST, 64, INV, false>(X, buf, tw, l);
+        const int partner = (G - l) & (G - 1);
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            float2 zp;
+            zp.x = __shfl_sync(0xffffffffu, X[EPL - 1 - u].x, partner, G);
+            zp.y = __shfl_sync(0xffffffffu, X[EPL - 1 - u].y, partner, G);
+            if (l == 0) zp = (u == 0) ? X[0] : X[(EPL - u) % EPL];
+            M[u] = zp;
+        }
+        M[HB] = X[HB];
     }
 }
+
+// Hermitian extension before an inverse transform: V[u] is the value wanted at element index
+// N2 - f for the bins f = l + G*u (u < EPL/2) this lane owns; fills X[EPL/2 .. EPL-1] (element
+// l + G*u2), with `nyq` for element N2/2.
+template <int N2>
+__device__ __forceinline__ void fft_hermitian_fill(float2 (&X)[FftCfg<N2>::EPL],
+                                                   const float2 (&V)[FftCfg<N2>::EPL / 2], float2 nyq,
+                                                   float2 *buf, int l) {
+    using Cfg = FftCfg<N2>;
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2;
+    if constexpr (Cfg::BIG) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < HB; ++u) buf[l + G * u] = V[u];
+        __syncthreads();
+#pragma unroll
+        for (int u2 = HB; u2 < EPL; ++u2)
+            X[u2] = (u2 == HB && l == 0) ? nyq : buf[N2 - (l + G * u2)];
+        __syncthreads();
+    } else {
+        const int partner = (G - l) & (G - 1);
+#pragma unroll
+        for (int u2 = HB; u2 < EPL; ++u2) {
+            float2 x;
+            x.x = __shfl_sync(0xffffffffu, V[EPL - 1 - u2].x, partner, G);
+            x.y = __shfl_sync(0xffffffffu, V[EPL - 1 - u2].y, partner, G);
+            if (l == 0) x = (u2 == HB) ? nyq : V[(EPL - u2) % HB];
+            X[u2] = x;
+        }
+    }
+}
+
+// Launch of a kernel built on FftCfg<N2>: `tasks` transforms-in-flight (streams, channel pairs...),
+// TASKS per CTA; CTA-wide transforms get their exchange buffer as dynamic shared memory.
+template <int N2, class Kernel, class Params>
+inline void fft_kernel_launch(Kernel kernel, const Params &prm, long long tasks, cudaStream_t st,
+                              size_t extra_smem = 0, int small_tasks_per_cta = 0) {
+    using Cfg = FftCfg<N2>;
+    const size_t smem = (Cfg::BIG ? sizeof(float2) * Cfg::REGION : 0) + extra_smem;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int per_cta = Cfg::BIG ? 1 : (small_tasks_per_cta ? small_tasks_per_cta : Cfg::TASKS);
+    const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
+    kernel<<<grid, Cfg::THREADS, smem, st>>>(prm);
+}
+
+// N2 = 2 * block length dispatch over every supported size
+#define RTB_DISPATCH_N2(N2V, CALL)                                                                  \
+    switch (N2V) {                                                                                  \
+        case 64: CALL(64); break;     case 128: CALL(128); break;   case 256: CALL(256); break;     \
+        case 512: CALL(512); break;   case 1024: CALL(1024); break; case 2048: CALL(2048); break;   \
+        case 4096: CALL(4096); break; default: CALL(8192); break;                                   \
+    }
+
+inline bool block_length_supported(int b) { return b >= 32 && b <= 4096 && (b & (b - 1)) == 0; }
+#define RTB_BLOCK_LENGTHS "32, 64, 128, 256, 512, 1024, 2048, 4096"
 
 }  // namespace rtb

@@ -39,34 +39,40 @@ struct OlsParams {
 };
 
 template <int N2>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FftCfg<N2>::THREADS)
 ols_fdl_kernel(const OlsParams prm) {
     using Cfg = FftCfg<N2>;
     constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS;
     constexpr int B = N2 / 2;
-    constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool BIG = Cfg::BIG;  // one transform per CTA, exchange buffer in dynamic smem
 
-    __shared__ float2 s_tw[N2];
-    __shared__ __align__(16) float2 s_buf[4][GROUPS * Cfg::REGION];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ float2 s_tw[BIG ? 1 : N2];
+    __shared__ __align__(16) float2 s_buf[BIG ? 1 : 4 * GROUPS * Cfg::REGION];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane / G, l = lane % G;
-    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
-    __syncthreads();
+    const int warp = BIG ? 0 : (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int grp = BIG ? 0 : lane / G, l = BIG ? (int)threadIdx.x : lane % G;
+    const float2 *tw = prm.tw;
+    float2 *buf = reinterpret_cast<float2 *>(dyn_smem);
+    if constexpr (!BIG) {
+        for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+        __syncthreads();
+        tw = s_tw;
+        buf = s_buf + (warp * GROUPS + grp) * Cfg::REGION;
+    }
 
     const int npairs = (prm.Cout + 1) / 2;
-    const long long task = ((long long)blockIdx.x * 4 + warp) * GROUPS + grp;
+    const long long wtask = BIG ? (long long)blockIdx.x : ((long long)blockIdx.x * 4 + warp) * GROUPS;
+    const long long task = wtask + grp;
     const bool valid = task < (long long)prm.S * npairs;
     // a warp whose groups are all out of range has nothing to do (uniform exit)
-    if (((long long)blockIdx.x * 4 + warp) * GROUPS >= (long long)prm.S * npairs) return;
+    if (wtask >= (long long)prm.S * npairs) return;
     const int s = valid ? (int)(task / npairs) : 0;
     const int pair = valid ? (int)(task % npairs) : 0;
     const int co0 = 2 * pair, co1 = 2 * pair + 1;
     const bool has1 = co1 < prm.Cout;
     const bool mono = prm.Cin == 1 && prm.Cout > 1;
     const int ci0 = mono ? 0 : co0, ci1 = mono ? 0 : co1;
-    float2 *buf = s_buf[warp] + grp * Cfg::REGION;
-    const int partner = (G - l) & (G - 1);
 
     // ---- a1: overlap-save buffers (previous | current block) of both channels, one complex FFT
     float2 X[EPL];
@@ -90,22 +96,16 @@ ols_fdl_kernel(const OlsParams prm) {
             }
         }
     }
-    warp_fft<N2, false>(X, buf, s_tw, l);
+    warp_fft<N2, false>(X, buf, tw, l);
 
     // separate the two real signals on the bins this lane owns: slot u <-> bin l + G*u, slot HB
     // is the Nyquist bin (lane 0)
     float2 X0[HB + 1], X1[HB + 1];
+    float2 M[HB + 1];
+    fft_mirror<N2>(X, M, buf, l);
 #pragma unroll
     for (int u = 0; u <= HB; ++u) {
-        const float2 zf = X[u];
-        float2 zp;
-        if (u < HB) {
-            zp.x = __shfl_sync(FULL, X[EPL - 1 - u].x, partner, G);
-            zp.y = __shfl_sync(FULL, X[EPL - 1 - u].y, partner, G);
-            if (l == 0) zp = (u == 0) ? X[0] : X[(EPL - u) % EPL];
-        } else {
-            zp = X[HB];
-        }
+        const float2 zf = X[u], zp = M[u];
         // Z = A + iB with A, B Hermitian: A(f) = (Z(f) + conj Z(-f)) / 2, B(f) = (Z(f) - conj Z(-f)) / 2i
         X0[u] = make_float2(0.5f * (zf.x + zp.x), 0.5f * (zf.y - zp.y));
         X1[u] = mono ? X0[u] : make_float2(0.5f * (zf.y + zp.y), 0.5f * (zp.x - zf.x));
@@ -179,17 +179,10 @@ ols_fdl_kernel(const OlsParams prm) {
             V[u] = make_float2(eL.x + eR.y, eR.x - eL.y);
         }
         const float2 nyq = make_float2(Y0[HB].x, has1 ? Y1[HB].x : 0.f);
-#pragma unroll
-        for (int u2 = HB; u2 < EPL; ++u2) {
-            float2 x;
-            x.x = __shfl_sync(FULL, V[EPL - 1 - u2].x, partner, G);
-            x.y = __shfl_sync(FULL, V[EPL - 1 - u2].y, partner, G);
-            if (l == 0) x = (u2 == HB) ? nyq : V[(EPL - u2) % HB];
-            X[u2] = x;
-        }
+        fft_hermitian_fill<N2>(X, V, nyq, buf, l);
     }
-    __syncwarp();
-    warp_fft<N2, true>(X, buf, s_tw, l);
+    fft_sync<N2>();
+    warp_fft<N2, true>(X, buf, tw, l);
     if (valid) {
         const float sc = 1.0f / (float)N2;
         float *o0 = prm.out + ((size_t)s * prm.Cout + co0) * B + l;
@@ -239,8 +232,8 @@ int rtb_ols_plan_create(rtb_ols_plan **out, int device, int n_streams, int block
         return fail(RTB_ERR_INVALID, "n_streams, n_out and n_partitions must be >= 1");
     if (n_in != n_out && n_in != 1)
         return fail(RTB_ERR_INVALID, "channel-wise convolver: n_in must equal n_out or be 1 (got %d, %d)", n_in, n_out);
-    if (block_length != 32 && block_length != 64 && block_length != 128 && block_length != 256)
-        return fail(RTB_ERR_UNSUPPORTED, "block length %d not supported (supported: 32, 64, 128, 256)", block_length);
+    if (!block_length_supported(block_length))
+        return fail(RTB_ERR_UNSUPPORTED, "block length %d not supported (supported: " RTB_BLOCK_LENGTHS ")", block_length);
     int ndev = 0;
     RTB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(RTB_ERR_INVALID, "no CUDA device %d", device);
@@ -316,12 +309,9 @@ int rtb_ols_process_block(rtb_ols_plan *p, const float *d_in, float *d_out, void
     prm.slot = p->slot; prm.passthrough = p->passthrough ? 1 : 0;
     const long long pairs = (long long)p->S * ((p->Cout + 1) / 2);
     if (p->profiling) cudaEventRecord(p->ev[0], st);
-    switch (p->N2) {
-        case 64: ols_fdl_kernel<64><<<(unsigned)((pairs + 15) / 16), 128, 0, st>>>(prm); break;
-        case 128: ols_fdl_kernel<128><<<(unsigned)((pairs + 7) / 8), 128, 0, st>>>(prm); break;
-        case 256: ols_fdl_kernel<256><<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(prm); break;
-        default: ols_fdl_kernel<512><<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(prm); break;
-    }
+#define RTB_OLS_LAUNCH(N) fft_kernel_launch<N>(ols_fdl_kernel<N>, prm, pairs, st)
+    RTB_DISPATCH_N2(p->N2, RTB_OLS_LAUNCH)
+#undef RTB_OLS_LAUNCH
     if (p->profiling) { cudaEventRecord(p->ev[1], st); p->ev_valid = true; }
     p->launches++;
     p->slot = (p->slot + 1) % p->P;

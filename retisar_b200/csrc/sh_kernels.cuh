@@ -116,18 +116,21 @@ sh_analysis_kernel(const float *__restrict__ x,    // [S][C][B]
             const int jc = task / n_tsub, ts = task % n_tsub;
             const int tl = ts * WT + tc * 4;  // first run; the second starts 32 samples later
             const float *rp = (R_SMEM ? rsm : rmP) + (size_t)jc * C * 32 + jr * 8;
-            float acc[JTH][NX];
+            // accumulators as (sample, sample + 1) pairs: one FFMA2 with the matrix element
+            // broadcast does two MACs per issue slot
+            f32x2_t acc[JTH][NX / 2];
 #pragma unroll
             for (int j = 0; j < JTH; ++j)
 #pragma unroll
-                for (int i = 0; i < NX; ++i) acc[j][i] = 0.f;
+                for (int i = 0; i < NX / 2; ++i) acc[j][i] = pk2(0.f, 0.f);
 #pragma unroll 4
             for (int c = 0; c < C; ++c) {
-                float xv[NX];
+                f32x2_t xv[NX / 2];
 #pragma unroll
                 for (int q = 0; q < NRUN; ++q) {
                     const float4 xa = *reinterpret_cast<const float4 *>(xs + (size_t)c * TW + tl + 32 * q);
-                    xv[4 * q] = xa.x; xv[4 * q + 1] = xa.y; xv[4 * q + 2] = xa.z; xv[4 * q + 3] = xa.w;
+                    xv[2 * q] = pk2(xa.x, xa.y);
+                    xv[2 * q + 1] = pk2(xa.z, xa.w);
                 }
                 float r[8];
                 const float4 *rq = reinterpret_cast<const float4 *>(rp + (size_t)c * 32);
@@ -140,7 +143,7 @@ sh_analysis_kernel(const float *__restrict__ x,    // [S][C][B]
 #pragma unroll
                 for (int j = 0; j < JTH; ++j)
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) acc[j][i] = fmaf(r[j], xv[i], acc[j][i]);
+                    for (int i = 0; i < NX / 2; ++i) acc[j][i] = fma2(xv[i], pk2(r[j], r[j]), acc[j][i]);
             }
             const int jbase = jc * 4 * JTH + jr * JTH;
 #pragma unroll
@@ -148,9 +151,10 @@ sh_analysis_kernel(const float *__restrict__ x,    // [S][C][B]
                 if (jbase + j < J) {
                     float *zp = zcur + ((size_t)s * J + jbase + j) * B + tbase + tl;
 #pragma unroll
-                    for (int q = 0; q < NRUN; ++q)
-                        *reinterpret_cast<float4 *>(zp + 32 * q) =
-                            make_float4(acc[j][4 * q], acc[j][4 * q + 1], acc[j][4 * q + 2], acc[j][4 * q + 3]);
+                    for (int q = 0; q < NRUN; ++q) {
+                        const float2 lo = up2(acc[j][2 * q]), hi = up2(acc[j][2 * q + 1]);
+                        *reinterpret_cast<float4 *>(zp + 32 * q) = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    }
                 }
             }
         }
@@ -227,6 +231,7 @@ __device__ __forceinline__ float2 phase_of(const float2 *cs, int m) {
 
 #include "sh_analysis_tc.cuh"
 #include "sh_render.cuh"
+#include "sh_render_mg.cuh"
 #include "sh_partitioned.cuh"
 
 namespace rtb {

@@ -91,16 +91,10 @@ sh_spectra_kernel(const ShPartParams prm) {
             X[u].y = valid ? zrow[N2 + l + G * u] : 0.f;
         }
         __syncwarp();
-        fft_pass<N2, 8, 1, false, true>(X, buf, s_tw, l);
-        fft_exchange<N2>(X, buf, l);
-        if constexpr (Cfg::R_LAST != 0) {
-            fft_pass<N2, 8, 8, false, true>(X, buf, s_tw, l);
-            fft_exchange<N2>(X, buf, l);
-        }
-        if (p0 + GROUPS < np) prefetch_z(p0 + GROUPS);
-        cp_async_commit();
-        if constexpr (Cfg::R_LAST == 0) fft_pass<N2, 8, 8, false, false>(X, buf, s_tw, l);
-        else fft_pass<N2, Cfg::R_LAST, 64, false, false>(X, buf, s_tw, l);
+        warp_fft_hook<N2, false>(X, buf, s_tw, l, [&] {
+            if (p0 + GROUPS < np) prefetch_z(p0 + GROUPS);
+            cp_async_commit();
+        });
         if (valid) {
             float2 *dst = prm.zspec + ((size_t)s * prm.NPT + p) * N2 + l;
 #pragma unroll
@@ -266,7 +260,7 @@ sh_partition_tail_kernel(const ShPartParams prm) {
     }
     if (prm.crossfade && lane == 0)
         prm.rad_last_out[s] = yaw_deg_to_rad16(prm.yaw_deg[s], prm.tracker_dir, prm.src_azim16);
-    render_tail<N2>(acc, s_buf[warp] + grp * Cfg::REGION, s_tw, lane, prm.win_in, prm.win_out,
+    render_tail<N2>(acc, s_buf[warp] + grp * Cfg::REGION, s_tw, grp, l, prm.win_in, prm.win_out,
                     prm.crossfade, prm.out + (size_t)s * 2 * B);
 }
 

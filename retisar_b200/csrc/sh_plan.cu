@@ -34,6 +34,14 @@ struct rtb_sh_plan {
     float *d_zring = nullptr;     // [2][S][J][B]
     float4 *d_htab = nullptr;     // [NP][2][F]
     ShSignal *d_signals = nullptr;
+    // steady-state render kernel (signals grouped by m, sh_render_mg.cuh): tables for `mg_order`
+    bool mg_enabled = false;
+    int mg_order = -1, mg_np = 0;
+    float4 *d_mg_htab = nullptr;
+    ShMgSignal *d_mg_signals = nullptr;
+    std::vector<ShSignal> h_sig;       // host copy of the signal list
+    std::vector<float> h_hnm;          // host copy of H_nm [K][2][F] complex (P == 1)
+    std::vector<int16_t> h_shm;        // sh_m[K]
     ShStep *d_steps = nullptr;    // flattened (signal, term) list for the partitioned kernels
     std::vector<int> steps_prefix;  // steps_prefix[np] = number of steps of the first np signals
     float2 *d_tw = nullptr;       // [N2]
@@ -132,13 +140,96 @@ void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int c
 }
 
 void launch_render(const rtb_sh_plan *p, const ShRenderParams &prm, cudaStream_t st) {
+#define RTB_SH_LAUNCH(N) fft_kernel_launch<N>(sh_render_kernel<N>, prm, prm.S, st, 0, 4)
+    RTB_DISPATCH_N2(p->N2, RTB_SH_LAUNCH)
+#undef RTB_SH_LAUNCH
+}
+
+void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStream_t st) {
     const unsigned grid = (unsigned)((prm.S + 3) / 4);
-    switch (p->N2) {
-        case 64: sh_render_kernel<64><<<grid, 128, 0, st>>>(prm); break;
-        case 128: sh_render_kernel<128><<<grid, 128, 0, st>>>(prm); break;
-        case 256: sh_render_kernel<256><<<grid, 128, 0, st>>>(prm); break;
-        default: sh_render_kernel<512><<<grid, 128, 0, st>>>(prm); break;
+    if (p->N2 == 256) sh_render_mg_kernel<256><<<grid, 128, 0, st>>>(prm);
+    else sh_render_mg_kernel<512><<<grid, 128, 0, st>>>(prm);
+}
+
+// Tables of the steady-state render kernel for SH order `order`: signals sorted by m (one group
+// per phase pair), real m = 0 rows paired two per FFT, term-2 spectra stored mirrored.
+int build_mg_tables(rtb_sh_plan *p, int order) {
+    const int F = p->F, B = p->B, K = p->K;
+    auto H = [&](int k, int e, int f) {
+        const size_t o = 2 * (((size_t)k * 2 + e) * F + f);
+        return make_float2(p->h_hnm[o], p->h_hnm[o + 1]);
+    };
+    std::vector<ShMgSignal> sig;
+    std::vector<float4> htab;
+    auto add = [&](int row_re, int row_im, int m1, int m2, int has2) {
+        ShMgSignal g;
+        g.row_re = row_re; g.row_im = row_im; g.m1 = m1; g.m2 = m2; g.has2 = has2; g.flush = 0;
+        g.pad0 = g.pad1 = 0;
+        sig.push_back(g);
+        htab.resize(htab.size() + 2 * (size_t)F, make_float4(0.f, 0.f, 0.f, 0.f));
+        return htab.data() + htab.size() - 2 * (size_t)F;
+    };
+    if (p->symmetric) {
+        auto q_of = [](int n, int m) { return n * (n + 1) / 2 + m; };  // index into h_sig
+        // m = 0: real rows, two per transform
+        for (int n = 0; n <= order; n += 2) {
+            const int ka = n * n + n, kb = (n + 1) * (n + 1) + (n + 1);
+            const bool pair = n + 1 <= order;
+            float4 *t = add(p->h_sig[q_of(n, 0)].row_re, pair ? p->h_sig[q_of(n + 1, 0)].row_re : -1, 0,
+                            pair ? 0 : RTB_NO_TERM, pair ? 1 : 0);
+            for (int f = 0; f < F; ++f) {
+                float2 a[2], b[2];
+                for (int e = 0; e < 2; ++e) { a[e] = H(ka, e, f); b[e] = pair ? H(kb, e, f) : make_float2(0.f, 0.f); }
+                if (!pair) { t[f] = make_float4(a[0].x, a[0].y, a[1].x, a[1].y); continue; }
+                // H1 = (Ha - i Hb) / 2, H2 = (Ha + i Hb) / 2
+                t[f] = make_float4(0.5f * (a[0].x + b[0].y), 0.5f * (a[0].y - b[0].x),
+                                   0.5f * (a[1].x + b[1].y), 0.5f * (a[1].y - b[1].x));
+                t[F + (B - f)] = make_float4(0.5f * (a[0].x - b[0].y), 0.5f * (a[0].y + b[0].x),
+                                             0.5f * (a[1].x - b[1].y), 0.5f * (a[1].y + b[1].x));
+            }
+        }
+        sig.back().flush = 1;
+        if (order >= 1) sig.back().m2 = 0;  // the group has a V sum even when its last transform is unpaired
+        for (int m = 1; m <= order; ++m) {
+            for (int n = m; n <= order; ++n) {
+                const int kpos = n * n + n + m, kneg = n * n + n - m;
+                const ShSignal &s0 = p->h_sig[q_of(n, m)];
+                float4 *t = add(s0.row_re, s0.row_im, -m, m, 1);
+                const float sg = (m & 1) ? -1.f : 1.f;
+                for (int f = 0; f < F; ++f) {
+                    const float2 a0 = H(kneg, 0, f), a1 = H(kneg, 1, f), b0 = H(kpos, 0, f), b1 = H(kpos, 1, f);
+                    t[f] = make_float4(a0.x, a0.y, a1.x, a1.y);
+                    t[F + (B - f)] = make_float4(sg * b0.x, sg * b0.y, sg * b1.x, sg * b1.y);
+                }
+            }
+            sig.back().flush = 1;
+        }
+    } else {
+        const int Ko = (order + 1) * (order + 1);
+        std::vector<int> ks(Ko);
+        for (int k = 0; k < Ko; ++k) ks[k] = k;
+        std::stable_sort(ks.begin(), ks.end(), [&](int a, int b) { return p->h_shm[a] < p->h_shm[b]; });
+        for (int i = 0; i < Ko; ++i) {
+            const int k = ks[i];
+            float4 *t = add(p->h_sig[k].row_re, p->h_sig[k].row_im, p->h_shm[k], RTB_NO_TERM, 0);
+            for (int f = 0; f < F; ++f) {
+                const float2 a0 = H(k, 0, f), a1 = H(k, 1, f);
+                t[f] = make_float4(a0.x, a0.y, a1.x, a1.y);
+            }
+            if (i + 1 == Ko || p->h_shm[ks[i + 1]] != p->h_shm[k]) sig.back().flush = 1;
+        }
     }
+    (void)K;
+    cudaFree(p->d_mg_htab); p->d_mg_htab = nullptr;
+    cudaFree(p->d_mg_signals); p->d_mg_signals = nullptr;
+    p->mg_order = -1;
+    RTB_CUDA(cudaMalloc(&p->d_mg_htab, sizeof(float4) * htab.size()));
+    RTB_CUDA(cudaMalloc(&p->d_mg_signals, sizeof(ShMgSignal) * sig.size()));
+    RTB_CUDA(cudaMemcpy(p->d_mg_htab, htab.data(), sizeof(float4) * htab.size(), cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(p->d_mg_signals, sig.data(), sizeof(ShMgSignal) * sig.size(), cudaMemcpyHostToDevice));
+    p->mg_np = (int)sig.size();
+    p->mg_order = order;
+    return RTB_OK;
 }
 
 // H table: [P][NP][2][Fs] x (ear0.re, ear0.im, ear1.re, ear1.im); hnm is [P][K][E=2][F] complex.
@@ -174,6 +265,9 @@ void free_tables(rtb_sh_plan *p) {
     cudaFree(p->d_zring); p->d_zring = nullptr;
     cudaFree(p->d_htab); p->d_htab = nullptr;
     cudaFree(p->d_signals); p->d_signals = nullptr;
+    cudaFree(p->d_mg_htab); p->d_mg_htab = nullptr;
+    cudaFree(p->d_mg_signals); p->d_mg_signals = nullptr;
+    p->mg_order = -1;
     cudaFree(p->d_steps); p->d_steps = nullptr;
     cudaFree(p->d_tc_b); p->d_tc_b = nullptr;
     cudaFree(p->d_zspec); p->d_zspec = nullptr;
@@ -196,9 +290,12 @@ int rtb_sh_plan_create(rtb_sh_plan **out, int device, int n_streams, int block_l
         return fail(RTB_ERR_INVALID, "Invalid value \"%d\" for spherical harmonics order.", sh_max_order);
     if (n_ears != 2)
         return fail(RTB_ERR_UNSUPPORTED, "the SH renderer produces exactly 2 ear signals (got %d)", n_ears);
-    if (block_length != 32 && block_length != 64 && block_length != 128 && block_length != 256)
+    if (!block_length_supported(block_length))
         return fail(RTB_ERR_UNSUPPORTED, "block length %d not supported by the SH renderer "
-                    "(supported: 32, 64, 128, 256)", block_length);
+                    "(supported: " RTB_BLOCK_LENGTHS ")", block_length);
+    if (n_partitions > 1 && block_length > 256)
+        return fail(RTB_ERR_UNSUPPORTED, "the partitioned SH-domain HRIR extension supports block lengths up to 256 "
+                    "(got %d with %d partitions)", block_length, n_partitions);
     if (n_partitions < 1) return fail(RTB_ERR_INVALID, "n_partitions must be >= 1");
     int ndev = 0;
     RTB_CUDA(cudaGetDeviceCount(&ndev));
@@ -383,6 +480,15 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     RTB_CUDA(cudaMemset(p->d_radlast, 0, sizeof(float) * 2 * p->S));
 
     p->symmetric = symmetric;
+    p->h_sig = sig;
+    p->h_shm.assign(sh_m, sh_m + K);
+    p->mg_enabled = p->P == 1 && (p->N2 == 256 || p->N2 == 512);
+    if (const char *env = getenv("RTB_RENDER_MG")) p->mg_enabled = p->mg_enabled && env[0] != '0';
+    if (p->mg_enabled) {
+        p->h_hnm.assign(hnm, hnm + 2 * (size_t)K * 2 * F);
+        const int rc = build_mg_tables(p, p->order);
+        if (rc != RTB_OK) return rc;
+    }
     p->J = J; p->Jpad = Jpad; p->JT = bestJT; p->n_jchunks = n_jchunks; p->NP = NP;
     {   // bulk-copy pipeline of the analysis kernel: widest tile that leaves room for >= 2 stages
         const size_t rbytes = (size_t)n_jchunks * C * 32 * sizeof(float);
@@ -457,6 +563,10 @@ int rtb_sh_plan_update_filter(rtb_sh_plan *p, const float *hnm) {
     // reference's in-place `_irs_blocks_nm *= comp_nm` under a cleared IS_RUNNING
     RTB_CUDA(cudaDeviceSynchronize());
     RTB_CUDA(cudaMemcpy(p->d_htab, htab.data(), sizeof(float4) * htab.size(), cudaMemcpyHostToDevice));
+    if (p->mg_enabled) {
+        p->h_hnm.assign(hnm, hnm + 2 * (size_t)p->K * 2 * p->F);
+        return build_mg_tables(p, p->mg_order >= 0 ? p->mg_order : p->cur_order);
+    }
     return RTB_OK;
 }
 
@@ -575,21 +685,48 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         }
         p->launches += 2;
     } else {
-        ShRenderParams prm;
-        prm.zprev = zprev; prm.zcur = zcur;
-        prm.htab = p->d_htab; prm.signals = p->d_signals; prm.tw = p->d_tw;
-        prm.win_in = p->d_win_in; prm.win_out = p->d_win_out;
-        prm.yaw_deg = d_yaw_deg;
-        prm.rad_last_in = p->d_radlast + (size_t)p->rad_idx * p->S + s0;
-        prm.rad_last_out = p->d_radlast + (size_t)(p->rad_idx ^ 1) * p->S + s0;
-        prm.out = d_out;
-        prm.S = count; prm.J = p->J; prm.B = p->B;
-        prm.np_cur = signals_for_order(p, p->cur_order);
-        prm.np_last = (p->crossfade && p->last_valid) ? signals_for_order(p, p->last_order) : 0;
-        prm.order_max = p->order;
-        prm.crossfade = p->crossfade ? 1 : 0;
-        prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
-        launch_render(p, prm, st);
+        const int np_cur = signals_for_order(p, p->cur_order);
+        const int np_last = (p->crossfade && p->last_valid) ? signals_for_order(p, p->last_order) : 0;
+        // steady state (both yaws at the same order): the m-grouped kernel; its tables follow
+        // the current order (rebuilt on the first block after the order settled)
+        bool use_mg = p->mg_enabled && (np_last == 0 || np_last == np_cur);
+        if (use_mg && p->mg_order != p->cur_order) {
+            cudaStreamSynchronize(st);
+            use_mg = build_mg_tables(p, p->cur_order) == RTB_OK;
+        }
+        if (use_mg) {
+            ShRenderMgParams prm;
+            prm.zprev = zprev; prm.zcur = zcur;
+            prm.htab = p->d_mg_htab; prm.signals = p->d_mg_signals; prm.tw = p->d_tw;
+            prm.win_in = p->d_win_in; prm.win_out = p->d_win_out;
+            prm.yaw_deg = d_yaw_deg;
+            prm.rad_last_in = p->d_radlast + (size_t)p->rad_idx * p->S + s0;
+            prm.rad_last_out = p->d_radlast + (size_t)(p->rad_idx ^ 1) * p->S + s0;
+            prm.out = d_out;
+            prm.S = count; prm.J = p->J; prm.B = p->B;
+            prm.np = p->mg_np;
+            prm.last_on = np_last > 0 ? 1 : 0;
+            prm.order_max = p->order;
+            prm.crossfade = p->crossfade ? 1 : 0;
+            prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
+            launch_render_mg(p, prm, st);
+        } else {
+            ShRenderParams prm;
+            prm.zprev = zprev; prm.zcur = zcur;
+            prm.htab = p->d_htab; prm.signals = p->d_signals; prm.tw = p->d_tw;
+            prm.win_in = p->d_win_in; prm.win_out = p->d_win_out;
+            prm.yaw_deg = d_yaw_deg;
+            prm.rad_last_in = p->d_radlast + (size_t)p->rad_idx * p->S + s0;
+            prm.rad_last_out = p->d_radlast + (size_t)(p->rad_idx ^ 1) * p->S + s0;
+            prm.out = d_out;
+            prm.S = count; prm.J = p->J; prm.B = p->B;
+            prm.np_cur = np_cur;
+            prm.np_last = np_last;
+            prm.order_max = p->order;
+            prm.crossfade = p->crossfade ? 1 : 0;
+            prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
+            launch_render(p, prm, st);
+        }
     }
     p->launches++;
 }

@@ -30,15 +30,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // at the same time; with G == 32 the warp does them one after the other.
 template <int N2>
 __device__ __forceinline__ void render_tail(float2 (&acc)[FftCfg<N2>::EPL / 2 + 1][4], float2 *buf,
-                                            const float2 *s_tw, int lane, const float *win_in,
+                                            const float2 *s_tw, int grp, int l, const float *win_in,
                                             const float *win_out, int crossfade, float *o) {
     using Cfg = FftCfg<N2>;
     constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS;
     constexpr int B = N2 / 2;
     constexpr unsigned FULL = 0xffffffffu;
-    const int grp = lane / G, l = lane % G;
-    const int partner = (G - l) & (G - 1);
-    __syncwarp();
+    fft_sync<N2>();
     float2 ycur[HB], ylast[HB];
     constexpr int NITER = (GROUPS >= 2) ? 1 : 2;
 #pragma unroll
@@ -55,22 +53,17 @@ __device__ __forceinline__ void render_tail(float2 (&acc)[FftCfg<N2>::EPL / 2 + 
         }
         const float2 nyq = make_float2(use_last ? acc[HB][2].x : acc[HB][0].x,
                                        use_last ? acc[HB][3].x : acc[HB][1].x);
-#pragma unroll
-        for (int u2 = HB; u2 < EPL; ++u2) {
-            float2 x;
-            x.x = __shfl_sync(FULL, V[EPL - 1 - u2].x, partner, G);
-            x.y = __shfl_sync(FULL, V[EPL - 1 - u2].y, partner, G);
-            if (l == 0) x = (u2 == HB) ? nyq : V[(EPL - u2) % HB];
-            X[u2] = x;
-        }
+        fft_hermitian_fill<N2>(X, V, nyq, buf, l);
         warp_fft<N2, true>(X, buf, s_tw, l);
 #pragma unroll
         for (int u = 0; u < HB; ++u) {
             if (GROUPS >= 2 || it == 0) ycur[u] = X[u + HB];
             if (GROUPS >= 2 || it == 1) ylast[u] = X[u + HB];
         }
+        if (NITER == 2 && it == 0 && !crossfade) break;  // the previous-yaw block is not needed
     }
     if (GROUPS >= 2) {  // bring the previous-yaw block from group 1 to group 0
+        const int lane = grp * G + l;
 #pragma unroll
         for (int u = 0; u < HB; ++u) {
             ylast[u].x = __shfl_sync(FULL, ylast[u].x, (lane + G) & 31);
@@ -98,36 +91,45 @@ __device__ __forceinline__ void render_tail(float2 (&acc)[FftCfg<N2>::EPL / 2 + 
 }
 
 template <int N2>
-__global__ void __launch_bounds__(128, RTB_RENDER_MIN_CTAS)
+__global__ void __launch_bounds__(FftCfg<N2>::THREADS, FftCfg<N2>::BIG ? 1 : RTB_RENDER_MIN_CTAS)
 sh_render_kernel(const ShRenderParams prm) {
     using Cfg = FftCfg<N2>;
     constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS;
     constexpr int B = N2 / 2, F = B + 1;
     constexpr int HSIG = 2 * F;  // float4 entries of one signal's HRIR tile (two terms)
+    constexpr bool BIG = Cfg::BIG;  // one stream per CTA; HRIR tiles and twiddles straight from L2
+    constexpr int NW = BIG ? 1 : 4;  // streams per CTA
     constexpr unsigned FULL = 0xffffffffu;
 
-    __shared__ float2 s_tw[N2];
-    __shared__ __align__(16) float2 s_buf[4][GROUPS * Cfg::REGION];
-    __shared__ __align__(16) float4 s_h[2][GROUPS * HSIG];
-    __shared__ float2 s_cs[4][2][RTB_MAX_ORDER + 1];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ float2 s_tw[BIG ? 1 : N2];
+    __shared__ __align__(16) float2 s_buf[BIG ? 1 : 4 * GROUPS * Cfg::REGION];
+    __shared__ __align__(16) float4 s_h[2][BIG ? 1 : GROUPS * HSIG];
+    __shared__ float2 s_cs[NW][2][RTB_MAX_ORDER + 1];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane / G, l = lane % G;
-    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+    const int warp = BIG ? 0 : (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int grp = BIG ? 0 : lane / G, l = BIG ? (int)threadIdx.x : lane % G;
+    const float2 *tw = prm.tw;
+    float2 *buf = reinterpret_cast<float2 *>(dyn_smem);
+    if constexpr (!BIG) {
+        for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+        tw = s_tw;
+        buf = s_buf + (warp * GROUPS + grp) * Cfg::REGION;
+    }
 
-    const int s = blockIdx.x * 4 + warp;
+    const int s = BIG ? (int)blockIdx.x : (int)blockIdx.x * 4 + warp;
     const bool active = s < prm.S;
-    float2 *buf = s_buf[warp] + grp * Cfg::REGION;
     float *zrow = reinterpret_cast<float *>(buf);  // landing zone: re row [N2] | im row [N2]
-    const int partner = (G - l) & (G - 1);
     const int np = max(prm.np_cur, prm.np_last);
     const size_t zoff = (size_t)(active ? s : 0) * prm.J * B;
 
     // stage the HRIR tiles of signals p0 .. p0+GROUPS-1 (contiguous in the table)
     auto prefetch_h = [&](int p0, int stage) {
-        const int n = min(GROUPS, np - p0) * HSIG;
-        const float4 *src = prm.htab + (size_t)p0 * HSIG;
-        for (int i = threadIdx.x; i < n; i += 128) cp_async16_ca(&s_h[stage][i], src + i);
+        if constexpr (!BIG) {
+            const int n = min(GROUPS, np - p0) * HSIG;
+            const float4 *src = prm.htab + (size_t)p0 * HSIG;
+            for (int i = threadIdx.x; i < n; i += 128) cp_async16_ca(&s_h[stage][i], src + i);
+        }
     };
     // bring the (previous | current) block of the group's signal into its exchange buffer
     auto prefetch_z = [&](int p0) {
@@ -157,14 +159,14 @@ sh_render_kernel(const ShRenderParams prm) {
     if (active) {
         const float rad_cur = yaw_deg_to_rad16(prm.yaw_deg[s], prm.tracker_dir, prm.src_azim16);
         const float rad_last = prm.rad_last_in[s];
-        if (lane <= prm.order_max) {
+        if (threadIdx.x < 32 * NW && lane <= prm.order_max) {
             float sn, cs;
             sincosf((float)lane * rad_cur, &sn, &cs);
             s_cs[warp][0][lane] = make_float2(cs, sn);
             sincosf((float)lane * rad_last, &sn, &cs);
             s_cs[warp][1][lane] = make_float2(cs, sn);
         }
-        if (prm.crossfade && lane == 0) prm.rad_last_out[s] = rad_cur;
+        if (prm.crossfade && lane == 0 && (!BIG || threadIdx.x == 0)) prm.rad_last_out[s] = rad_cur;
     }
 
     // accumulators: [bin slot][cur ear0, cur ear1, last ear0, last ear1]
@@ -180,7 +182,7 @@ sh_render_kernel(const ShRenderParams prm) {
         __syncthreads();  // tile + rows of this round have landed; everyone left the last round
         if (p0 + GROUPS < np) prefetch_h(p0 + GROUPS, stage ^ 1);
         cp_async_commit();
-        if (!active) continue;
+        if (!BIG && !active) continue;
 
         const int p = p0 + grp;
         const bool valid = p < np;
@@ -192,18 +194,21 @@ sh_render_kernel(const ShRenderParams prm) {
             X[u].x = valid ? zrow[l + G * u] : 0.f;
             X[u].y = valid ? zrow[N2 + l + G * u] : 0.f;
         }
-        __syncwarp();
-        fft_pass<N2, 8, 1, false, true>(X, buf, s_tw, l);
-        fft_exchange<N2>(X, buf, l);
-        if constexpr (Cfg::R_LAST != 0) {
-            fft_pass<N2, 8, 8, false, true>(X, buf, s_tw, l);
-            fft_exchange<N2>(X, buf, l);
+        fft_sync<N2>();
+        // the exchange buffer is idle after the last exchange: prefetch the next signal's rows
+        // (a CTA-wide transform still needs it for the mirror exchange below)
+        warp_fft_hook<N2, false>(X, buf, tw, l, [&] {
+            if constexpr (!BIG) {
+                if (p0 + GROUPS < np) prefetch_z(p0 + GROUPS);
+                cp_async_commit();
+            }
+        });
+        float2 M[HB + 1];  // element N2-f for the bins this lane owns
+        fft_mirror<N2>(X, M, buf, l);
+        if constexpr (BIG) {
+            if (p0 + GROUPS < np) prefetch_z(p0 + GROUPS);
+            cp_async_commit();
         }
-        // the exchange buffer is idle from here on: prefetch the next signal's rows into it
-        if (p0 + GROUPS < np) prefetch_z(p0 + GROUPS);
-        cp_async_commit();
-        if constexpr (Cfg::R_LAST == 0) fft_pass<N2, 8, 8, false, false>(X, buf, s_tw, l);
-        else fft_pass<N2, Cfg::R_LAST, 64, false, false>(X, buf, s_tw, l);
 
         // ---- a3-a5: HRIR multiply, rotation, sum over SH coefficients
         const bool in_cur = valid && p < prm.np_cur, in_last = valid && p < prm.np_last;
@@ -217,32 +222,24 @@ sh_render_kernel(const ShRenderParams prm) {
             ph1l = phase_of(s_cs[warp][1], sg.m1);
             if (has2) ph2l = phase_of(s_cs[warp][1], sg.m2);
         }
-        const float4 *h1 = s_h[stage] + (valid ? grp : 0) * HSIG;
+        const float4 *h1 = BIG ? prm.htab + (size_t)(valid ? p : 0) * HSIG
+                               : s_h[stage] + (valid ? grp : 0) * HSIG;
         const float4 *h2 = h1 + F;
 #pragma unroll
         for (int u = 0; u <= HB; ++u) {
             const int f = (u < HB) ? (l + G * u) : B;  // slot HB is the Nyquist bin (lane 0 only)
             const float2 zf = X[u];
             {
-                const float4 h = h1[f];
+                const float4 h = BIG ? __ldg(h1 + f) : h1[f];
                 const float2 tc = cmul(ph1c, zf), tl = cmul(ph1l, zf);
                 cfma(acc[u][0], make_float2(h.x, h.y), tc);
                 cfma(acc[u][1], make_float2(h.z, h.w), tc);
                 cfma(acc[u][2], make_float2(h.x, h.y), tl);
                 cfma(acc[u][3], make_float2(h.z, h.w), tl);
             }
-            // element N2-f: slot EPL-1-u of the partner lane (lane 0: own slot EPL-u, bin 0: itself)
-            float2 zp;
-            if (u < HB) {
-                zp.x = __shfl_sync(FULL, X[EPL - 1 - u].x, partner, G);
-                zp.y = __shfl_sync(FULL, X[EPL - 1 - u].y, partner, G);
-                if (l == 0) zp = (u == 0) ? X[0] : X[(EPL - u) % EPL];
-            } else {
-                zp = X[HB];
-            }
-            if (has2) {  // uniform inside a group; groups diverge only on the shuffle-free part
-                const float4 h = h2[f];
-                const float2 zc = make_float2(zp.x, -zp.y);
+            if (has2) {  // uniform inside a group
+                const float4 h = BIG ? __ldg(h2 + f) : h2[f];
+                const float2 zc = make_float2(M[u].x, -M[u].y);
                 const float2 tc = cmul(ph2c, zc), tl = cmul(ph2l, zc);
                 cfma(acc[u][0], make_float2(h.x, h.y), tc);
                 cfma(acc[u][1], make_float2(h.z, h.w), tc);
@@ -256,18 +253,20 @@ sh_render_kernel(const ShRenderParams prm) {
     if (!active) return;
 
     // transforms that ran side by side in one warp each hold a partial sum
+    if constexpr (!BIG) {
 #pragma unroll
-    for (int off = G; off < 32; off <<= 1) {
+        for (int off = G; off < 32; off <<= 1) {
 #pragma unroll
-        for (int u = 0; u <= HB; ++u)
+            for (int u = 0; u <= HB; ++u)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                acc[u][q].x += __shfl_xor_sync(FULL, acc[u][q].x, off);
-                acc[u][q].y += __shfl_xor_sync(FULL, acc[u][q].y, off);
-            }
+                for (int q = 0; q < 4; ++q) {
+                    acc[u][q].x += __shfl_xor_sync(FULL, acc[u][q].x, off);
+                    acc[u][q].y += __shfl_xor_sync(FULL, acc[u][q].y, off);
+                }
+        }
     }
-    render_tail<N2>(acc, s_buf[warp] + grp * Cfg::REGION, s_tw, lane, prm.win_in, prm.win_out,
-                    prm.crossfade, prm.out + (size_t)s * 2 * B);
+    render_tail<N2>(acc, buf, tw, grp, l, prm.win_in, prm.win_out, prm.crossfade,
+                    prm.out + (size_t)s * 2 * B);
 }
 
 }  // namespace rtb

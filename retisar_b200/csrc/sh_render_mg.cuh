@@ -1,0 +1,228 @@
+// K-B, steady-state variant: the render kernel with the SH-coefficient sum grouped by order m.
+// Included by sh_kernels.cuh after sh_render.cuh (shares its cp.async helpers and render_tail).
+//
+// The head rotation multiplies every coefficient (n, m) by exp(-i m alpha): all signals of one m
+// share their two phases.  So instead of rotating every (signal, term) product for the current and
+// the previous yaw (sh_render_kernel: 2 complex multiplies + 4 complex MACs per term and bin), the
+// yaw-independent sums
+//     U_m(ear, f) = sum_n H1[n,m](ear, f) * Z_nm(f)
+//     V_m(ear, f) = sum_n H2[n,m](ear, f) * conj(Z_nm(N2 - f))
+// are accumulated first (2 complex MACs per term and bin), and the rotation
+//     ear_cur += e^{-i m1 a_cur} U_m + e^{-i m2 a_cur} V_m     (same for the previous yaw)
+// is applied once per group.  V_m is accumulated where bin N2-f lives after the FFT (upper half of
+// the lane's elements, H2 stored mirrored) and brought to bin f by one shuffle per group instead of
+// one per signal.  The real (m = 0) analysis rows are transformed two per complex FFT: with
+// Z = A + iB the sum H_a A + H_b B is again a two-term signal with H1 = (H_a - i H_b)/2,
+// H2 = (H_a + i H_b)/2 and both phases 1.
+//
+// Valid while the current and the previous yaw use the same SH order (always, except for the one
+// block after update_sh_processing); the plan falls back to sh_render_kernel otherwise.
+#pragma once
+
+#ifndef RTB_RENDER_MG_MIN_CTAS
+#define RTB_RENDER_MG_MIN_CTAS 2
+#endif
+
+namespace rtb {
+
+struct ShMgSignal {  // one complex FFT signal of the grouped list (sh_plan.cu: build_mg_tables)
+    int row_re;      // analysis row giving the real part
+    int row_im;      // analysis row giving the imaginary part, -1 = zero
+    int m1;          // group phase of the U sum: exp(-i*m1*alpha)
+    int m2;          // group phase of the V sum, RTB_NO_TERM = the group has no V sum
+    int has2;        // this signal contributes to V
+    int flush;       // last signal of its group
+    int pad0, pad1;
+};
+
+struct ShRenderMgParams {
+    const float *zprev, *zcur;   // [S][J][B]
+    const float4 *htab;          // [NPm][2][F]: H1[f], then H2 mirrored (index i <-> bin B - i)
+    const ShMgSignal *signals;   // [NPm]
+    const float2 *tw;
+    const float *win_in, *win_out;
+    const float *yaw_deg, *rad_last_in;
+    float *rad_last_out;
+    float *out;
+    int S, J, B;
+    int np;                      // signals
+    int last_on;                 // previous-yaw sum active (0: first block / cross-fade off)
+    int order_max;
+    int crossfade;
+    float tracker_dir, src_azim16;
+};
+
+// acc += h * conj(x)
+__device__ __forceinline__ void cfma_conj(float2 &acc, float2 h, float2 x) {
+#if RTB_PACKED_F32
+    acc = up2(fma2(pk2(h.y, -h.x), pk2(x.y, x.y), fma2(pk2(h), pk2(x.x, x.x), pk2(acc))));
+#else
+    acc.x = fmaf(h.x, x.x, acc.x);
+    acc.x = fmaf(h.y, x.y, acc.x);
+    acc.y = fmaf(h.y, x.x, acc.y);
+    acc.y = fmaf(-h.x, x.y, acc.y);
+#endif
+}
+
+template <int N2>
+__global__ void __launch_bounds__(128, RTB_RENDER_MG_MIN_CTAS)
+sh_render_mg_kernel(const ShRenderMgParams prm) {
+    using Cfg = FftCfg<N2>;
+    static_assert(Cfg::GROUPS == 1, "one transform per warp");
+    constexpr int EPL = Cfg::EPL, HB = EPL / 2;
+    constexpr int B = N2 / 2, F = B + 1;
+    constexpr int HSIG = 2 * F;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    __shared__ float2 s_tw[N2];
+    __shared__ __align__(16) float2 s_buf[4][Cfg::REGION];
+    __shared__ __align__(16) float4 s_h[2][HSIG];
+    __shared__ float2 s_cs[4][2][RTB_MAX_ORDER + 1];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+
+    const int s = blockIdx.x * 4 + warp;
+    const bool active = s < prm.S;
+    float2 *buf = s_buf[warp];
+    float *zrow = reinterpret_cast<float *>(buf);
+    const int partner = (32 - lane) & 31;
+    const int np = prm.np;
+    const size_t zoff = (size_t)(active ? s : 0) * prm.J * B;
+
+    auto prefetch_h = [&](int p, int stage) {
+        const float4 *src = prm.htab + (size_t)p * HSIG;
+        for (int i = threadIdx.x; i < HSIG; i += 128) cp_async16_ca(&s_h[stage][i], src + i);
+    };
+    auto prefetch_z = [&](int p) {
+        if (!active) return;
+        const int row_re = prm.signals[p].row_re, row_im = prm.signals[p].row_im;
+        constexpr int CH = B / 4;
+        for (int i = lane; i < 4 * CH; i += 32) {
+            const int part = i / CH, off = (i % CH) * 4;  // re-prev, re-cur, im-prev, im-cur
+            const int row = (part < 2) ? row_re : row_im;
+            float *dst = zrow + (part >> 1) * N2 + (part & 1) * B + off;
+            if (row >= 0) {
+                const float *src = ((part & 1) ? prm.zcur : prm.zprev) + zoff + (size_t)row * B + off;
+                cp_async16_cg(dst, src);
+            } else {
+                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    if (np > 0) {
+        prefetch_h(0, 0);
+        prefetch_z(0);
+    }
+    cp_async_commit();
+
+    if (active) {  // a4: (cos, sin)(m alpha) for the current and the previous yaw
+        const float rad_cur = yaw_deg_to_rad16(prm.yaw_deg[s], prm.tracker_dir, prm.src_azim16);
+        const float rad_last = prm.rad_last_in[s];
+        if (lane <= prm.order_max) {
+            float sn, cs;
+            sincosf((float)lane * rad_cur, &sn, &cs);
+            s_cs[warp][0][lane] = make_float2(cs, sn);
+            sincosf((float)lane * rad_last, &sn, &cs);
+            s_cs[warp][1][lane] = prm.last_on ? make_float2(cs, sn) : make_float2(0.f, 0.f);
+        }
+        if (prm.crossfade && lane == 0) prm.rad_last_out[s] = rad_cur;
+    }
+
+    // ear spectra [bin slot][cur ear0, cur ear1, last ear0, last ear1]; group sums U (bins
+    // l + 32u, slot HB = Nyquist on lane 0) and V (mirrored: slot v <-> element HB + v, i.e. bin
+    // N2 - f; slot HB = bin 0 on lane 0)
+    float2 acc[HB + 1][4], U[HB + 1][2], V[HB + 1][2];
+#pragma unroll
+    for (int u = 0; u <= HB; ++u) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[u][q] = make_float2(0.f, 0.f);
+        U[u][0] = U[u][1] = V[u][0] = V[u][1] = make_float2(0.f, 0.f);
+    }
+
+    int stage = 0;
+    for (int p = 0; p < np; ++p, stage ^= 1) {
+        cp_async_wait_all();
+        __syncthreads();
+        if (p + 1 < np) prefetch_h(p + 1, stage ^ 1);
+        cp_async_commit();
+        if (!active) continue;
+        const ShMgSignal sg = prm.signals[p];
+
+        float2 X[EPL];
+#pragma unroll
+        for (int u = 0; u < EPL; ++u) {
+            X[u].x = zrow[lane + 32 * u];
+            X[u].y = zrow[N2 + lane + 32 * u];
+        }
+        __syncwarp();
+        warp_fft_hook<N2, false>(X, buf, s_tw, lane, [&] {
+            if (p + 1 < np) prefetch_z(p + 1);  // the exchange buffer is idle from here on
+            cp_async_commit();
+        });
+
+        const float4 *h1 = s_h[stage], *h2 = h1 + F;
+#pragma unroll
+        for (int u = 0; u <= HB; ++u) {
+            const float4 h = h1[(u < HB) ? (lane + 32 * u) : B];
+            cfma(U[u][0], make_float2(h.x, h.y), X[u]);
+            cfma(U[u][1], make_float2(h.z, h.w), X[u]);
+        }
+        if (sg.has2) {
+#pragma unroll
+            for (int v = 0; v <= HB; ++v) {
+                const float4 h = h2[(v < HB) ? (lane + 32 * v) : B];
+                const float2 x = (v < HB) ? X[HB + v] : X[0];
+                cfma_conj(V[v][0], make_float2(h.x, h.y), x);
+                cfma_conj(V[v][1], make_float2(h.z, h.w), x);
+            }
+        }
+        if (sg.flush) {  // rotate the group sums by the two yaws and add them to the ear spectra
+            const float2 p1c = phase_of(s_cs[warp][0], sg.m1), p1l = phase_of(s_cs[warp][1], sg.m1);
+            const bool hasV = sg.m2 != RTB_NO_TERM;
+            float2 p2c = make_float2(0.f, 0.f), p2l = p2c;
+            if (hasV) {
+                p2c = phase_of(s_cs[warp][0], sg.m2);
+                p2l = phase_of(s_cs[warp][1], sg.m2);
+            }
+#pragma unroll
+            for (int u = 0; u <= HB; ++u) {
+                cfma(acc[u][0], p1c, U[u][0]);
+                cfma(acc[u][1], p1c, U[u][1]);
+                cfma(acc[u][2], p1l, U[u][0]);
+                cfma(acc[u][3], p1l, U[u][1]);
+                U[u][0] = U[u][1] = make_float2(0.f, 0.f);
+            }
+            if (hasV) {
+#pragma unroll
+                for (int u = 0; u <= HB; ++u) {
+                    // V at bin f = lane + 32u: mirrored slot HB-1-u of the partner lane; lane 0
+                    // keeps its own slots (bin 0 <-> slot HB, bin 32u <-> slot HB-u, Nyquist <-> 0)
+                    float2 v0, v1;
+                    if (u < HB) {
+                        v0.x = __shfl_sync(FULL, V[HB - 1 - u][0].x, partner);
+                        v0.y = __shfl_sync(FULL, V[HB - 1 - u][0].y, partner);
+                        v1.x = __shfl_sync(FULL, V[HB - 1 - u][1].x, partner);
+                        v1.y = __shfl_sync(FULL, V[HB - 1 - u][1].y, partner);
+                        if (lane == 0) { v0 = V[HB - u][0]; v1 = V[HB - u][1]; }
+                    } else {
+                        v0 = V[0][0]; v1 = V[0][1];
+                    }
+                    cfma(acc[u][0], p2c, v0);
+                    cfma(acc[u][1], p2c, v1);
+                    cfma(acc[u][2], p2l, v0);
+                    cfma(acc[u][3], p2l, v1);
+                }
+#pragma unroll
+                for (int u = 0; u <= HB; ++u) V[u][0] = V[u][1] = make_float2(0.f, 0.f);
+            }
+        }
+    }
+    cp_async_wait_all();
+    if (np == 0) __syncthreads();
+    if (!active) return;
+    render_tail<N2>(acc, s_buf[warp], s_tw, 0, lane, prm.win_in, prm.win_out, prm.crossfade,
+                    prm.out + (size_t)s * 2 * B);
+}
+
+}  // namespace rtb
