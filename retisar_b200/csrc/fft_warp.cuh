@@ -21,6 +21,7 @@ struct FftCfg {
     static_assert(N2 >= 64 && N2 <= 8192 && (N2 & (N2 - 1)) == 0, "unsupported FFT length");
     // lanes per transform: a fraction of a warp (N2 < 256), one warp, or -- for N2 >= 1024 -- a
     // whole CTA of N2/16 threads ("big" transforms: exchanges go through __syncthreads)
+    static constexpr int LEN = N2;
     static constexpr int G = (N2 >= 512) ? N2 / 16 : ((N2 >= 256) ? 32 : N2 / 8);
     static constexpr bool BIG = G > 32;
     static constexpr int EPL = N2 / G;                   // complex elements per lane (8 or 16)
@@ -97,10 +98,10 @@ __device__ __forceinline__ void dft_r(float2 (&v)[R]) {
 
 // One Stockham pass of radix R over sub-transforms of length NS (product of earlier radices).
 // TO_SMEM: scatter the results into the exchange buffer, otherwise keep them in X (last pass).
-template <int N2, int R, int NS, bool INV, bool TO_SMEM>
-__device__ __forceinline__ void fft_pass(float2 (&X)[FftCfg<N2>::EPL], float2 *buf,
-                                         const float2 *tw, int l) {
-    using Cfg = FftCfg<N2>;
+// Cfg: LEN (transform length), G (lanes per transform), EPL (elements per lane).
+template <class Cfg, int R, int NS, bool INV, bool TO_SMEM>
+__device__ __forceinline__ void fft_pass_c(float2 (&X)[Cfg::EPL], float2 *buf, const float2 *tw, int l) {
+    constexpr int N2 = Cfg::LEN;
     constexpr int NB = Cfg::EPL / R;  // butterflies per lane
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
@@ -141,46 +142,50 @@ __device__ __forceinline__ void fft_pass(float2 (&X)[FftCfg<N2>::EPL], float2 *b
     }
 }
 
-template <int N2>
-__device__ __forceinline__ void fft_exchange(float2 (&X)[FftCfg<N2>::EPL], const float2 *buf, int l) {
-    using Cfg = FftCfg<N2>;
-    fft_sync<N2>();
-    const int lbase = fft_swz<N2>(l);
+// gather the next pass's inputs from the exchange buffer; `sync` = barrier over the transform's lanes
+template <class Cfg, class Sync>
+__device__ __forceinline__ void fft_exchange_c(float2 (&X)[Cfg::EPL], const float2 *buf, int l, Sync &&sync) {
+    sync();
+    const int lbase = fft_swz<Cfg::LEN>(l);
 #pragma unroll
-    for (int u = 0; u < Cfg::EPL; ++u) X[u] = buf[lbase ^ fft_swz<N2>(Cfg::G * u)];
-    fft_sync<N2>();
+    for (int u = 0; u < Cfg::EPL; ++u) X[u] = buf[lbase ^ fft_swz<Cfg::LEN>(Cfg::G * u)];
+    sync();
 }
 
-// In-register transform of the group's N2 points.  `buf` = this group's REGION of shared memory,
-// `tw` = exp(-2*pi*i*q/N2), q < N2 (shared or global memory), l = lane index inside the group.
-// All lanes of the group (and of the warp) must call it together.
-// `after_last_exchange()` runs once the exchange buffer is idle (before the final register pass):
-// the place to start prefetching the next input into it.
-template <int N2, bool INV, class Hook>
-__device__ __forceinline__ void warp_fft_hook(float2 (&X)[FftCfg<N2>::EPL], float2 *buf,
-                                              const float2 *tw, int l, Hook &&after_last_exchange) {
-    using Cfg = FftCfg<N2>;
+// In-register transform of the group's points.  `buf` = this group's REGION of shared memory,
+// `tw` = exp(-2*pi*i*q/LEN), q < LEN (shared or global memory), l = lane index inside the group.
+// All lanes of the group must call it together.  `after_last_exchange()` runs once the exchange
+// buffer is idle (before the final register pass): the place to start prefetching the next input.
+template <class Cfg, bool INV, class Sync, class Hook>
+__device__ __forceinline__ void fft_run_c(float2 (&X)[Cfg::EPL], float2 *buf, const float2 *tw, int l,
+                                          Sync &&sync, Hook &&after_last_exchange) {
     constexpr int NP = Cfg::NPASS8;
     constexpr bool TAIL = Cfg::R_LAST != 0;
-    fft_pass<N2, 8, 1, INV, true>(X, buf, tw, l);
-    fft_exchange<N2>(X, buf, l);
+    fft_pass_c<Cfg, 8, 1, INV, true>(X, buf, tw, l);
+    fft_exchange_c<Cfg>(X, buf, l, sync);
     if constexpr (NP == 2 && !TAIL) after_last_exchange();
-    fft_pass<N2, 8, 8, INV, (NP > 2 || TAIL)>(X, buf, tw, l);
-    if constexpr (NP > 2 || TAIL) fft_exchange<N2>(X, buf, l);
+    fft_pass_c<Cfg, 8, 8, INV, (NP > 2 || TAIL)>(X, buf, tw, l);
+    if constexpr (NP > 2 || TAIL) fft_exchange_c<Cfg>(X, buf, l, sync);
     if constexpr (NP >= 3) {
         if constexpr (NP == 3 && !TAIL) after_last_exchange();
-        fft_pass<N2, 8, 64, INV, (NP > 3 || TAIL)>(X, buf, tw, l);
-        if constexpr (NP > 3 || TAIL) fft_exchange<N2>(X, buf, l);
+        fft_pass_c<Cfg, 8, 64, INV, (NP > 3 || TAIL)>(X, buf, tw, l);
+        if constexpr (NP > 3 || TAIL) fft_exchange_c<Cfg>(X, buf, l, sync);
     }
     if constexpr (NP >= 4) {
         if constexpr (!TAIL) after_last_exchange();
-        fft_pass<N2, 8, 512, INV, TAIL>(X, buf, tw, l);
-        if constexpr (TAIL) fft_exchange<N2>(X, buf, l);
+        fft_pass_c<Cfg, 8, 512, INV, TAIL>(X, buf, tw, l);
+        if constexpr (TAIL) fft_exchange_c<Cfg>(X, buf, l, sync);
     }
     if constexpr (TAIL) {
         after_last_exchange();
-        fft_pass<N2, Cfg::R_LAST, (1 << (3 * NP)), INV, false>(X, buf, tw, l);
+        fft_pass_c<Cfg, Cfg::R_LAST, (1 << (3 * NP)), INV, false>(X, buf, tw, l);
     }
+}
+
+template <int N2, bool INV, class Hook>
+__device__ __forceinline__ void warp_fft_hook(float2 (&X)[FftCfg<N2>::EPL], float2 *buf,
+                                              const float2 *tw, int l, Hook &&after_last_exchange) {
+    fft_run_c<FftCfg<N2>, INV>(X, buf, tw, l, [] { fft_sync<N2>(); }, after_last_exchange);
 }
 
 template <int N2, bool INV>

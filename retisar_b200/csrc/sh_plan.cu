@@ -35,7 +35,7 @@ struct rtb_sh_plan {
     float4 *d_htab = nullptr;     // [NP][2][F]
     ShSignal *d_signals = nullptr;
     // steady-state render kernel (signals grouped by m, sh_render_mg.cuh): tables for `mg_order`
-    bool mg_enabled = false;
+    bool mg_enabled = false, split_enabled = false;  // split: RTB_RENDER_SPLIT=1 (measured: no gain)
     int mg_order = -1, mg_np = 0;
     float4 *d_mg_htab = nullptr;
     ShMgSignal *d_mg_signals = nullptr;
@@ -145,10 +145,30 @@ void launch_render(const rtb_sh_plan *p, const ShRenderParams &prm, cudaStream_t
 #undef RTB_SH_LAUNCH
 }
 
+template <int N2>
+void launch_render_mg_t(const ShRenderMgParams &prm, cudaStream_t st) {
+    const size_t smem = RTB_MG_ACC_SMEM ? sizeof(float2) * 4 * (FftCfg<N2>::EPL / 2) * 4 * 32 : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sh_render_mg_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(sh_render_mg_kernel<N2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr_set = true;
+    }
+    sh_render_mg_kernel<N2><<<(unsigned)((prm.S + 3) / 4), 128, smem, st>>>(prm);
+}
+
 void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStream_t st) {
-    const unsigned grid = (unsigned)((prm.S + 3) / 4);
-    if (p->N2 == 256) sh_render_mg_kernel<256><<<grid, 128, 0, st>>>(prm);
-    else sh_render_mg_kernel<512><<<grid, 128, 0, st>>>(prm);
+    if (p->N2 == 256) launch_render_mg_t<256>(prm, st);
+    else if (p->split_enabled) {  // two warps per stream
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(sh_render_split_kernel<RTB_SPLIT_STREAMS>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            attr_set = true;
+        }
+        sh_render_split_kernel<RTB_SPLIT_STREAMS>
+            <<<(unsigned)((prm.S + RTB_SPLIT_STREAMS - 1) / RTB_SPLIT_STREAMS), 64 * RTB_SPLIT_STREAMS, 0, st>>>(prm);
+    } else launch_render_mg_t<512>(prm, st);
 }
 
 // Tables of the steady-state render kernel for SH order `order`: signals sorted by m (one group
@@ -163,8 +183,9 @@ int build_mg_tables(rtb_sh_plan *p, int order) {
     std::vector<float4> htab;
     auto add = [&](int row_re, int row_im, int m1, int m2, int has2) {
         ShMgSignal g;
-        g.row_re = row_re; g.row_im = row_im; g.m1 = m1; g.m2 = m2; g.has2 = has2; g.flush = 0;
-        g.pad0 = g.pad1 = 0;
+        g.row_re = (short)row_re; g.row_im = (short)row_im;
+        g.m1 = (signed char)m1; g.m2 = (signed char)(m2 == RTB_NO_TERM ? RTB_MG_NO_TERM : m2);
+        g.has2 = (unsigned char)has2; g.flush = 0;
         sig.push_back(g);
         htab.resize(htab.size() + 2 * (size_t)F, make_float4(0.f, 0.f, 0.f, 0.f));
         return htab.data() + htab.size() - 2 * (size_t)F;
@@ -229,6 +250,10 @@ int build_mg_tables(rtb_sh_plan *p, int order) {
     RTB_CUDA(cudaMemcpy(p->d_mg_signals, sig.data(), sizeof(ShMgSignal) * sig.size(), cudaMemcpyHostToDevice));
     p->mg_np = (int)sig.size();
     p->mg_order = order;
+    if (p->mg_np > RTB_MG_MAX_SIGNALS) {  // beyond the kernel's shared-memory signal list
+        p->mg_enabled = false;
+        p->mg_order = -1;
+    }
     return RTB_OK;
 }
 
@@ -484,6 +509,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     p->h_shm.assign(sh_m, sh_m + K);
     p->mg_enabled = p->P == 1 && (p->N2 == 256 || p->N2 == 512);
     if (const char *env = getenv("RTB_RENDER_MG")) p->mg_enabled = p->mg_enabled && env[0] != '0';
+    if (const char *env = getenv("RTB_RENDER_SPLIT")) p->split_enabled = env[0] != '0';
     if (p->mg_enabled) {
         p->h_hnm.assign(hnm, hnm + 2 * (size_t)K * 2 * F);
         const int rc = build_mg_tables(p, p->order);
@@ -692,7 +718,7 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         bool use_mg = p->mg_enabled && (np_last == 0 || np_last == np_cur);
         if (use_mg && p->mg_order != p->cur_order) {
             cudaStreamSynchronize(st);
-            use_mg = build_mg_tables(p, p->cur_order) == RTB_OK;
+            use_mg = build_mg_tables(p, p->cur_order) == RTB_OK && p->mg_enabled;
         }
         if (use_mg) {
             ShRenderMgParams prm;

@@ -19,20 +19,29 @@
 // block after update_sh_processing); the plan falls back to sh_render_kernel otherwise.
 #pragma once
 
+// Ear-spectrum accumulators: they are touched only once per m group, so they live in shared memory
+// (8 KB per stream) and the kernel keeps the register budget of three CTAs per SM; 0 = registers
+// (255 registers, two CTAs per SM).
+#ifndef RTB_MG_ACC_SMEM
+#define RTB_MG_ACC_SMEM 1
+#endif
 #ifndef RTB_RENDER_MG_MIN_CTAS
-#define RTB_RENDER_MG_MIN_CTAS 2
+#define RTB_RENDER_MG_MIN_CTAS (RTB_MG_ACC_SMEM ? 3 : 2)
 #endif
 
 namespace rtb {
 
-struct ShMgSignal {  // one complex FFT signal of the grouped list (sh_plan.cu: build_mg_tables)
-    int row_re;      // analysis row giving the real part
-    int row_im;      // analysis row giving the imaginary part, -1 = zero
-    int m1;          // group phase of the U sum: exp(-i*m1*alpha)
-    int m2;          // group phase of the V sum, RTB_NO_TERM = the group has no V sum
-    int has2;        // this signal contributes to V
-    int flush;       // last signal of its group
-    int pad0, pad1;
+#define RTB_MG_MAX_SIGNALS 96  // staged in shared memory (order 12 has 85)
+
+#define RTB_MG_NO_TERM 127
+
+struct __align__(8) ShMgSignal {  // one complex FFT signal of the grouped list (sh_plan.cu: build_mg_tables)
+    short row_re;        // analysis row giving the real part
+    short row_im;        // analysis row giving the imaginary part, -1 = zero
+    signed char m1;      // group phase of the U sum: exp(-i*m1*alpha)
+    signed char m2;      // group phase of the V sum, RTB_MG_NO_TERM = the group has no V sum
+    unsigned char has2;  // this signal contributes to V
+    unsigned char flush; // last signal of its group
 };
 
 struct ShRenderMgParams {
@@ -78,9 +87,21 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     __shared__ __align__(16) float2 s_buf[4][Cfg::REGION];
     __shared__ __align__(16) float4 s_h[2][HSIG];
     __shared__ float2 s_cs[4][2][RTB_MAX_ORDER + 1];
+    __shared__ ShMgSignal s_sig[RTB_MG_MAX_SIGNALS];  // the signal list: no dependent global load per round
+#if RTB_MG_ACC_SMEM
+    extern __shared__ __align__(16) unsigned char dyn_smem[];  // [4 warps][HB][4][32 lanes] float2
+#endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+    for (int i = threadIdx.x; i < prm.np * (int)(sizeof(ShMgSignal) / sizeof(int2)); i += 128)
+        reinterpret_cast<int2 *>(s_sig)[i] = __ldg(reinterpret_cast<const int2 *>(prm.signals) + i);
+    __syncthreads();
+#if RTB_MG_ACC_SMEM
+    float2 *sacc = reinterpret_cast<float2 *>(dyn_smem) + warp * (HB * 4 * 32) + lane;
+#pragma unroll
+    for (int i = 0; i < HB * 4; ++i) sacc[i * 32] = make_float2(0.f, 0.f);
+#endif
 
     const int s = blockIdx.x * 4 + warp;
     const bool active = s < prm.S;
@@ -96,7 +117,7 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     };
     auto prefetch_z = [&](int p) {
         if (!active) return;
-        const int row_re = prm.signals[p].row_re, row_im = prm.signals[p].row_im;
+        const int row_re = s_sig[p].row_re, row_im = s_sig[p].row_im;
         constexpr int CH = B / 4;
         for (int i = lane; i < 4 * CH; i += 32) {
             const int part = i / CH, off = (i % CH) * 4;  // re-prev, re-cur, im-prev, im-cur
@@ -132,13 +153,20 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     // ear spectra [bin slot][cur ear0, cur ear1, last ear0, last ear1]; group sums U (bins
     // l + 32u, slot HB = Nyquist on lane 0) and V (mirrored: slot v <-> element HB + v, i.e. bin
     // N2 - f; slot HB = bin 0 on lane 0)
-    float2 acc[HB + 1][4], U[HB + 1][2], V[HB + 1][2];
+    float2 U[HB + 1][2], V[HB + 1][2];
+#if RTB_MG_ACC_SMEM
+    float2 accn[4];  // Nyquist slot (lane 0)
 #pragma unroll
-    for (int u = 0; u <= HB; ++u) {
+    for (int q = 0; q < 4; ++q) accn[q] = make_float2(0.f, 0.f);
+#else
+    float2 acc[HB + 1][4];
+#pragma unroll
+    for (int u = 0; u <= HB; ++u)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[u][q] = make_float2(0.f, 0.f);
-        U[u][0] = U[u][1] = V[u][0] = V[u][1] = make_float2(0.f, 0.f);
-    }
+#endif
+#pragma unroll
+    for (int u = 0; u <= HB; ++u) U[u][0] = U[u][1] = V[u][0] = V[u][1] = make_float2(0.f, 0.f);
 
     int stage = 0;
     for (int p = 0; p < np; ++p, stage ^= 1) {
@@ -147,7 +175,7 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
         if (p + 1 < np) prefetch_h(p + 1, stage ^ 1);
         cp_async_commit();
         if (!active) continue;
-        const ShMgSignal sg = prm.signals[p];
+        const ShMgSignal sg = s_sig[p];
 
         float2 X[EPL];
 #pragma unroll
@@ -179,7 +207,7 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
         }
         if (sg.flush) {  // rotate the group sums by the two yaws and add them to the ear spectra
             const float2 p1c = phase_of(s_cs[warp][0], sg.m1), p1l = phase_of(s_cs[warp][1], sg.m1);
-            const bool hasV = sg.m2 != RTB_NO_TERM;
+            const bool hasV = sg.m2 != RTB_MG_NO_TERM;
             float2 p2c = make_float2(0.f, 0.f), p2l = p2c;
             if (hasV) {
                 p2c = phase_of(s_cs[warp][0], sg.m2);
@@ -187,18 +215,10 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
             }
 #pragma unroll
             for (int u = 0; u <= HB; ++u) {
-                cfma(acc[u][0], p1c, U[u][0]);
-                cfma(acc[u][1], p1c, U[u][1]);
-                cfma(acc[u][2], p1l, U[u][0]);
-                cfma(acc[u][3], p1l, U[u][1]);
-                U[u][0] = U[u][1] = make_float2(0.f, 0.f);
-            }
-            if (hasV) {
-#pragma unroll
-                for (int u = 0; u <= HB; ++u) {
-                    // V at bin f = lane + 32u: mirrored slot HB-1-u of the partner lane; lane 0
-                    // keeps its own slots (bin 0 <-> slot HB, bin 32u <-> slot HB-u, Nyquist <-> 0)
-                    float2 v0, v1;
+                // V at bin f = lane + 32u: mirrored slot HB-1-u of the partner lane; lane 0
+                // keeps its own slots (bin 0 <-> slot HB, bin 32u <-> slot HB-u, Nyquist <-> 0)
+                float2 v0 = make_float2(0.f, 0.f), v1 = v0;
+                if (hasV) {
                     if (u < HB) {
                         v0.x = __shfl_sync(FULL, V[HB - 1 - u][0].x, partner);
                         v0.y = __shfl_sync(FULL, V[HB - 1 - u][0].y, partner);
@@ -208,19 +228,51 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
                     } else {
                         v0 = V[0][0]; v1 = V[0][1];
                     }
-                    cfma(acc[u][0], p2c, v0);
-                    cfma(acc[u][1], p2c, v1);
-                    cfma(acc[u][2], p2l, v0);
-                    cfma(acc[u][3], p2l, v1);
                 }
+                float2 a[4];
+#if RTB_MG_ACC_SMEM
 #pragma unroll
-                for (int u = 0; u <= HB; ++u) V[u][0] = V[u][1] = make_float2(0.f, 0.f);
+                for (int q = 0; q < 4; ++q) a[q] = (u < HB) ? sacc[(u * 4 + q) * 32] : accn[q];
+#else
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] = acc[u][q];
+#endif
+                cfma(a[0], p1c, U[u][0]);
+                cfma(a[1], p1c, U[u][1]);
+                cfma(a[2], p1l, U[u][0]);
+                cfma(a[3], p1l, U[u][1]);
+                if (hasV) {
+                    cfma(a[0], p2c, v0);
+                    cfma(a[1], p2c, v1);
+                    cfma(a[2], p2l, v0);
+                    cfma(a[3], p2l, v1);
+                }
+#if RTB_MG_ACC_SMEM
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (u < HB) sacc[(u * 4 + q) * 32] = a[q];
+                    else accn[q] = a[q];
+                }
+#else
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[u][q] = a[q];
+#endif
+                U[u][0] = U[u][1] = make_float2(0.f, 0.f);
             }
+#pragma unroll
+            for (int u = 0; u <= HB; ++u) V[u][0] = V[u][1] = make_float2(0.f, 0.f);
         }
     }
     cp_async_wait_all();
     if (np == 0) __syncthreads();
     if (!active) return;
+#if RTB_MG_ACC_SMEM
+    float2 acc[HB + 1][4];
+#pragma unroll
+    for (int u = 0; u <= HB; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[u][q] = (u < HB) ? sacc[(u * 4 + q) * 32] : accn[q];
+#endif
     render_tail<N2>(acc, s_buf[warp], s_tw, 0, lane, prm.win_in, prm.win_out, prm.crossfade,
                     prm.out + (size_t)s * 2 * B);
 }
