@@ -221,6 +221,29 @@ def golden_yaw(name):
     print(name, len(yaws))
 
 
+def golden_delay(name, fs=48000, B=64, channels=3, max_sec=0.01, T=30, seed=401):
+    """DelayBuffer (`_convolver.py:11-141`): ring of blocks, delay changes while running, the
+    maximum-delay wrap (delay == ring size returns the block just written) and `None` input."""
+    ref = rh.import_reference()
+    buf = ref._convolver.DelayBuffer(sample_rate=fs, block_length=B, delay_ms=2.0)
+    buf.init(max_length_sec=max_sec, channel_count=channels)
+    x = syn.noise_blocks(T, channels, B, seed)
+    events = {5: 0.0, 8: 4.0, 14: 10.0, 18: 1000.0, 24: 1.4}  # block -> set_delay(ms)
+    ev = np.full(T, -1.0, dtype=np.float64)
+    realized = np.full(T, -1.0, dtype=np.float64)
+    outs = np.zeros((T, channels, B), dtype=np.float32)
+    for t in range(T):
+        if t in events:
+            ev[t] = events[t]
+            realized[t] = buf.set_delay(events[t])
+        outs[t] = np.array(buf.process_block(x[t].copy()))
+    assert buf.process_block(None) is None
+    np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), kind="delay", fs=fs, B=B, max_sec=max_sec,
+                        start_delay_ms=2.0, x=x, y=outs, set_delay_ms=ev, realized_ms=realized,
+                        ring_blocks=buf._buffer.shape[0])
+    print(name, "ring blocks", buf._buffer.shape[0])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     extract_grids()
@@ -268,6 +291,9 @@ def main():
     golden_ols("ols_arir_mono_6ch_b64", syn.decaying_noise_irs((6, 200), 206), 64, 10, 207,
                mono_in=True)
     golden_ols("ols_short_b256", syn.decaying_noise_irs((3, 100), 208), 256, 4, 209)
+
+    # block delay line of the JACK clients (row f4)
+    golden_delay("delay_3ch_b64")
 
 
 if __name__ == "__main__":

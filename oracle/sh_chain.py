@@ -403,3 +403,41 @@ class FdOracle:
         self.last_blocks_fd, y_out = self._roll(self.last_blocks_fd)
         self.last_filters_fd = filters_fd
         return (y_in * self.w_in) + (y_out * self.w_out)
+
+
+# --------------------------------------------------------------------------------------------
+# f4: block delay line of the JACK clients
+# --------------------------------------------------------------------------------------------
+class DelayBufferOracle:
+    """`DelayBuffer` (`_convolver.py:11-141`): ring of blocks, delay in whole blocks."""
+
+    def __init__(self, sample_rate, block_length, delay_ms=0.0):  # `:33-50`
+        self.buffer = None
+        self.ptr = 0
+        self.fs, self.B = sample_rate, block_length
+        self.delay_blocks = self._blocks(delay_ms)
+
+    def init(self, max_length_sec, channel_count):  # `:52-67`
+        n = self._blocks(max_length_sec * 1000) + 1
+        self.buffer = np.zeros((n, channel_count, self.B), dtype=np.float32)
+        self.ptr = 0
+
+    def _blocks(self, delay_ms):  # `:69-81`
+        return int(np.ceil((delay_ms / 1000) * self.fs / self.B))
+
+    def set_delay(self, new_delay_ms=0.0):  # `:89-115`
+        if self.buffer is None:
+            return self.delay_blocks
+        self.delay_blocks = min(self._blocks(new_delay_ms), self.buffer.shape[0])
+        if self.delay_blocks == 0:
+            self.buffer.fill(0)
+            self.ptr = 0
+        return (self.delay_blocks * self.B / self.fs) * 1000
+
+    def process_block(self, x):  # `:117-141`
+        if self.buffer is None or not self.delay_blocks or x is None:
+            return x
+        self.buffer[self.ptr] = x
+        y = self.buffer[self.ptr - self.delay_blocks]  # python index: -ring size wraps to 0
+        self.ptr = (self.ptr + 1) % self.buffer.shape[0]
+        return y

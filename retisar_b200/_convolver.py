@@ -23,6 +23,71 @@ def _is_torch_tensor(x):
     return type(x).__module__.startswith("torch")
 
 
+class DelayBuffer(object):
+    """Delay line of time-domain blocks in a ring buffer (reference ``DelayBuffer``,
+    ``_convolver.py:11-141``): the realised delay is a whole number of blocks, limited by the ring
+    size given to ``init``.  Same attributes and return values as the reference, including its
+    two quirks: a delay equal to the ring size returns the block just written (python index
+    ``-len`` wraps to 0, ``:134``), and ``set_delay`` before ``init`` returns the delay in blocks.
+
+    Extension: the blocks may carry a leading stream axis (``[n_streams; channels; block]``) and
+    may be torch CUDA tensors; the ring then lives in device memory (``init(..., device=...)``)
+    and ``process_block`` costs one device-to-device block copy on the current stream.
+    """
+
+    def __init__(self, sample_rate, block_length, delay_ms=0.0):
+        self._buffer = None
+        self._buffer_ptr = 0
+        self._sample_rate = sample_rate
+        self._block_length = block_length
+        self._delay_blocks = self._calculate_delay_blocks(delay_ms)
+
+    def init(self, max_length_sec, channel_count, n_streams=None, device=None):
+        # +1 to realise the maximum delay without wrapping around to the current block (`:63-66`)
+        block_count = self._calculate_delay_blocks(delay_ms=max_length_sec * 1000) + 1
+        shape = (block_count,) + (() if n_streams is None else (n_streams,)) + (channel_count, self._block_length)
+        if device is None:
+            self._buffer = np.zeros(shape=shape, dtype=np.float32)
+        else:
+            import torch
+
+            self._buffer = torch.zeros(shape, dtype=torch.float32, device=device)
+        self._reset()
+
+    def _calculate_delay_blocks(self, delay_ms):
+        return int(np.ceil((delay_ms / 1000) * self._sample_rate / self._block_length))
+
+    def _reset(self):
+        if self._buffer is not None:
+            if _is_torch_tensor(self._buffer):
+                self._buffer.zero_()
+            else:
+                self._buffer.fill(0)
+        self._buffer_ptr = 0
+
+    def set_delay(self, new_delay_ms=0.0):
+        if self._buffer is None:
+            return self._delay_blocks
+        self._delay_blocks = self._calculate_delay_blocks(new_delay_ms)  # round to full blocks
+        if self._delay_blocks > self._buffer.shape[0]:
+            self._delay_blocks = self._buffer.shape[0]
+        if self._delay_blocks == 0:
+            self._reset()
+        return (self._delay_blocks * self._block_length / self._sample_rate) * 1000
+
+    def process_block(self, input_td):
+        if self._buffer is None or not self._delay_blocks or input_td is None:
+            return input_td
+        if _is_torch_tensor(self._buffer):
+            self._buffer[self._buffer_ptr].copy_(input_td, non_blocking=True)
+        else:
+            self._buffer[self._buffer_ptr] = input_td
+        # a view into the ring, like the reference (valid until the slot is written again)
+        output_td = self._buffer[self._buffer_ptr - self._delay_blocks]
+        self._buffer_ptr = (self._buffer_ptr + 1) % self._buffer.shape[0]
+        return output_td
+
+
 class Convolver(object):
     """Base class and factory (reference ``Convolver``, ``_convolver.py:144-433``)."""
 

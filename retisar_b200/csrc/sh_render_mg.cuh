@@ -83,7 +83,7 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     constexpr int HSIG = 2 * F;
     constexpr unsigned FULL = 0xffffffffu;
 
-    __shared__ float2 s_tw[N2];
+    __shared__ __align__(16) float2 s_tw[N2];
     __shared__ __align__(16) float2 s_buf[4][Cfg::REGION];
     __shared__ __align__(16) float4 s_h[2][HSIG];
     __shared__ float2 s_cs[4][2][RTB_MAX_ORDER + 1];
@@ -93,7 +93,8 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
 #endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+    // twiddles arrive asynchronously with the first tile (waited for at the top of the first round)
+    for (int i = threadIdx.x; i < N2 / 2; i += 128) cp_async16_ca(&s_tw[2 * i], prm.tw + 2 * i);
     for (int i = threadIdx.x; i < prm.np * (int)(sizeof(ShMgSignal) / sizeof(int2)); i += 128)
         reinterpret_cast<int2 *>(s_sig)[i] = __ldg(reinterpret_cast<const int2 *>(prm.signals) + i);
     __syncthreads();
@@ -112,22 +113,33 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     const size_t zoff = (size_t)(active ? s : 0) * prm.J * B;
 
     auto prefetch_h = [&](int p, int stage) {
-        const float4 *src = prm.htab + (size_t)p * HSIG;
-        for (int i = threadIdx.x; i < HSIG; i += 128) cp_async16_ca(&s_h[stage][i], src + i);
+        const float4 *src = prm.htab + (size_t)p * HSIG + threadIdx.x;
+        float4 *dst = &s_h[stage][threadIdx.x];
+#pragma unroll
+        for (int i = 0; i < HSIG / 128; ++i) cp_async16_ca(dst + 128 * i, src + 128 * i);
+        if (threadIdx.x < HSIG % 128) cp_async16_ca(dst + (HSIG / 128) * 128, src + (HSIG / 128) * 128);
     };
+    // rows of the signal -> landing zone [re: prev | cur][im: prev | cur]; lane-contiguous 16-byte chunks
     auto prefetch_z = [&](int p) {
         if (!active) return;
         const int row_re = s_sig[p].row_re, row_im = s_sig[p].row_im;
-        constexpr int CH = B / 4;
-        for (int i = lane; i < 4 * CH; i += 32) {
-            const int part = i / CH, off = (i % CH) * 4;  // re-prev, re-cur, im-prev, im-cur
-            const int row = (part < 2) ? row_re : row_im;
-            float *dst = zrow + (part >> 1) * N2 + (part & 1) * B + off;
+        constexpr int NCH = B / 128;  // chunks per lane and row half
+#pragma unroll
+        for (int im = 0; im < 2; ++im) {
+            const int row = im ? row_im : row_re;
+            float *dst = zrow + im * N2 + lane * 4;
             if (row >= 0) {
-                const float *src = ((part & 1) ? prm.zcur : prm.zprev) + zoff + (size_t)row * B + off;
-                cp_async16_cg(dst, src);
+                const size_t o = zoff + (size_t)row * B + lane * 4;
+                const float *sp = prm.zprev + o, *sc = prm.zcur + o;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    cp_async16_cg(dst + 128 * c, sp + 128 * c);
+                    cp_async16_cg(dst + B + 128 * c, sc + 128 * c);
+                }
             } else {
-                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 2 * NCH; ++c)
+                    *reinterpret_cast<float4 *>(dst + 128 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     };
