@@ -286,6 +286,8 @@ def run_gpu_arm(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         J = plan.query(_capi.RTB_Q_ROWS)
+        render_name = _capi.RENDER_KERNEL_NAMES.get(plan.query(_capi.RTB_Q_RENDER_KERNEL), "sh_render_kernel")
+        analysis_name = "sh_analysis_tc_kernel" if plan.query(_capi.RTB_Q_TENSOR_CORE) else "sh_analysis_kernel"
         render_bytes = S * (4 * B * (2 * J + E) + 12)  # z rows of 2 blocks in, ear blocks out, yaw
         analysis_bytes = S * 4 * B * (C + J)
         chain_bytes = S * wl.chain_bytes_per_stream_block(C, B, E)
@@ -315,14 +317,13 @@ def run_gpu_arm(args):
                     "ms_per_step": e2e_s / K_e2e * 1e3,
                     "api": "AdjustableShConvolver.filter_block(numpy pinned [S,C,B], yaw[S])"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "sh_render_kernel", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": render_name, "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": render_bytes, "us_per_launch": re_us},
-            "kernels": {"sh_analysis_kernel": {"us": an_us, "bytes": analysis_bytes,
-                                               "GBps": analysis_bytes / (an_us * 1e-6) / 1e9},
-                        "sh_render_kernel": {"us": re_us, "bytes": render_bytes,
-                                             "GBps": achieved}},
+            "kernels": {analysis_name: {"us": an_us, "bytes": analysis_bytes,
+                                        "GBps": analysis_bytes / (an_us * 1e-6) / 1e9},
+                        render_name: {"us": re_us, "bytes": render_bytes, "GBps": achieved}},
             "chain": {"bytes_per_step": chain_bytes, "flops_per_step": chain_flops,
                       "GBps": chain_bytes / (dev_ms / K * 1e-3) / 1e9,
                       "TFLOPs_reference_formulation": chain_flops / (dev_ms / K * 1e-3) / 1e12},

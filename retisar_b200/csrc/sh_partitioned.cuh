@@ -223,6 +223,163 @@ sh_partition_mac_kernel(const ShPartParams prm) {
     }
 }
 
+// Second version of the partition MAC: the H rows of the CTA's 32 bins are staged through shared
+// memory (cp.async, double buffered over chunks of RTB_MAC_SC steps) and shared by 8 warps = 16
+// streams, instead of every warp pulling them through L1/L2 (first version: 5.1 long-scoreboard
+// stall cycles per issue, FMA pipe 33 %, profiles/).  Spectra are read two steps ahead.
+#define RTB_MAC_SC 8        // steps per staged chunk
+#define RTB_MAC_WARPS 8     // warps per CTA, 2 streams each
+#define RTB_MAC_MAX_STEPS 192
+
+template <int N2>
+__global__ void __launch_bounds__(32 * RTB_MAC_WARPS, 2)
+sh_partition_mac2_kernel(const ShPartParams prm) {
+    constexpr int B = N2 / 2;
+    constexpr int NT = 32 * RTB_MAC_WARPS;
+    __shared__ __align__(16) float4 s_h[2][RTB_MAC_SC][RTB_QC][32];
+    __shared__ float2 s_cs[RTB_MAC_WARPS][2][2][RTB_MAX_ORDER + 1];  // [warp][stream][cur/last][m]
+    __shared__ ShStep s_steps[RTB_MAC_MAX_STEPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f0 = blockIdx.x * 32;
+    const int f = f0 + lane;
+    const bool fvalid = f <= B;
+    const int fc = fvalid ? f : 0;                 // clamped: out-of-range lanes read bin 0
+    const int fm = (N2 - fc) & (N2 - 1);           // mirrored bin
+    const int sbase = (blockIdx.y * RTB_MAC_WARPS + warp) * 2;
+    const bool wactive = sbase < prm.S;
+    const bool has_s1 = sbase + 1 < prm.S;
+    const int nsteps = max(prm.nsteps_cur, prm.nsteps_last);
+    for (int i = threadIdx.x; i < nsteps; i += NT) s_steps[i] = prm.steps[i];
+    if (wactive) {
+        for (int i = lane; i < 4 * (prm.order_max + 1); i += 32) {
+            const int m = i % (prm.order_max + 1), which = i / (prm.order_max + 1);
+            const int st = which >> 1, cl = which & 1;
+            const int s = min(sbase + st, prm.S - 1);
+            const float rad = cl ? prm.rad_last_in[s]
+                                 : yaw_deg_to_rad16(prm.yaw_deg[s], prm.tracker_dir, prm.src_azim16);
+            float sn, cs;
+            sincosf((float)m * rad, &sn, &cs);
+            s_cs[warp][st][cl][m] = make_float2(cs, sn);
+        }
+    }
+    __syncthreads();
+    const float2 *z0 = prm.zspec + (size_t)(wactive ? sbase : 0) * prm.NPT * N2;
+    const float2 *z1 = prm.zspec + (size_t)(has_s1 ? sbase + 1 : (wactive ? sbase : 0)) * prm.NPT * N2;
+    const size_t hq = (size_t)prm.NPT * 2 * prm.Fp;  // H stride between partitions
+    const int nchunks = (nsteps + RTB_MAC_SC - 1) / RTB_MAC_SC;
+    // the last bin block holds the Nyquist bin only: clamp the staged columns into the row
+    const int fcol = min(f0 + lane, prm.Fp - 1);
+
+    for (int q0 = 0; q0 < prm.P; q0 += RTB_QC) {
+        // stage chunk c of this partition group: rows (step, partition) x 32 bins
+        auto stage_h = [&](int c, int buf) {
+            for (int i = threadIdx.x; i < RTB_MAC_SC * RTB_QC * 32; i += NT) {
+                const int col = i & 31, a = (i >> 5) % RTB_QC, jj = i / (32 * RTB_QC);
+                const int j = c * RTB_MAC_SC + jj;
+                float4 *dst = &s_h[buf][jj][a][col];
+                if (j < nsteps && q0 + a < prm.P) {
+                    const ShStep st_ = s_steps[j];
+                    const float4 *src = prm.htab + (size_t)(q0 + a) * hq + ((size_t)st_.p * 2 + st_.term) * prm.Fp
+                                        + min(f0 + col, prm.Fp - 1);
+                    cp_async16_cg(dst, src);
+                } else {
+                    *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        (void)fcol;
+        float2 acc[RTB_QC][2][2][2];  // [partition][ear][cur/last][stream]
+#pragma unroll
+        for (int a = 0; a < RTB_QC; ++a)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) acc[a][e][c][0] = acc[a][e][c][1] = make_float2(0.f, 0.f);
+        if (nchunks > 0) stage_h(0, 0);
+        cp_async_commit();
+        // spectra two steps ahead
+        float2 za[2], zb[2];
+        auto load_z = [&](int j, float2 (&z)[2]) {
+            if (j < nsteps && wactive) {
+                const ShStep st_ = s_steps[j];
+                const size_t zo = (size_t)st_.p * N2 + (st_.term ? fm : fc);
+                z[0] = __ldg(z0 + zo);
+                z[1] = __ldg(z1 + zo);
+            } else {
+                z[0] = z[1] = make_float2(0.f, 0.f);
+            }
+        };
+        load_z(0, za);
+        load_z(1, zb);
+        for (int c = 0; c < nchunks; ++c) {
+            cp_async_wait_all();
+            __syncthreads();  // chunk c has landed; everyone has left chunk c-1 (its buffer is free)
+            if (c + 1 < nchunks) stage_h(c + 1, (c + 1) & 1);
+            cp_async_commit();
+            if (!wactive) continue;
+#pragma unroll 2
+            for (int jj = 0; jj < RTB_MAC_SC; ++jj) {
+                const int j = c * RTB_MAC_SC + jj;
+                if (j >= nsteps) break;
+                const ShStep stp = s_steps[j];
+                float2 zz[2] = {za[0], za[1]};
+                za[0] = zb[0]; za[1] = zb[1];
+                load_z(j + 2, zb);
+                const bool in_cur = j < prm.nsteps_cur, in_last = j < prm.nsteps_last;
+                float2 A[2][2];  // [cur/last][stream]
+#pragma unroll
+                for (int st = 0; st < 2; ++st) {
+                    float2 z = zz[st];
+                    if (stp.term) z.y = -z.y;
+                    const float2 pc = in_cur ? phase_of(s_cs[warp][st][0], stp.m) : make_float2(0.f, 0.f);
+                    const float2 pl = in_last ? phase_of(s_cs[warp][st][1], stp.m) : make_float2(0.f, 0.f);
+                    A[0][st] = cmul(pc, z);
+                    A[1][st] = cmul(pl, z);
+                }
+#pragma unroll
+                for (int a = 0; a < RTB_QC; ++a) {
+                    const float4 h = s_h[c & 1][jj][a][lane];
+#pragma unroll
+                    for (int cl = 0; cl < 2; ++cl)
+#pragma unroll
+                        for (int st = 0; st < 2; ++st) {
+                            cfma(acc[a][0][cl][st], make_float2(h.x, h.y), A[cl][st]);
+                            cfma(acc[a][1][cl][st], make_float2(h.z, h.w), A[cl][st]);
+                        }
+                }
+            }
+        }
+        __syncthreads();  // the next partition group restages buffer 0
+        if (fvalid && wactive) {
+#pragma unroll
+            for (int a = 0; a < RTB_QC; ++a) {
+                if (q0 + a < prm.P) {
+                    const int sc = (prm.head_cur + q0 + a) % prm.P, sl = (prm.head_last + q0 + a) % prm.P;
+#pragma unroll
+                    for (int st = 0; st < 2; ++st) {
+                        if (st == 0 || has_s1) {
+                            const size_t sq = (size_t)(sbase + st) * prm.P;
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                float2 *qc = prm.qcur + ((sq + sc) * 2 + e) * prm.Fp + f;
+                                float2 v = *qc;
+                                v.x += acc[a][e][0][st].x; v.y += acc[a][e][0][st].y;
+                                *qc = v;
+                                if (prm.crossfade) {
+                                    float2 *ql = prm.qlast + ((sq + sl) * 2 + e) * prm.Fp + f;
+                                    float2 w = *ql;
+                                    w.x += acc[a][e][1][st].x; w.y += acc[a][e][1][st].y;
+                                    *ql = w;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int N2>
 __global__ void __launch_bounds__(128)
 sh_partition_tail_kernel(const ShPartParams prm) {

@@ -69,6 +69,7 @@ struct rtb_sh_plan {
     float src_azim16 = 0.f;       // _sources_deg[0, 0], already rounded to float16
     float tracker_dir = 1.f;      // +1 HRIR, -1 BRIR
     long long launches = 0;
+    int last_render_kernel = 0;   // RTB_Q_RENDER_KERNEL
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -667,6 +668,7 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
     p->launches++;
     if (p->profiling && s0 == 0) cudaEventRecord(p->ev[1], st);
     if (p->passthrough) {
+        p->last_render_kernel = 4;
         const long long total = (long long)count * p->E * p->B;
         sh_passthrough_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_in, d_out, count, p->C, p->E, p->B);
         if (p->P > 1) {  // queue slot 0 is overwritten and leaves the queue (_convolver.py:558-562, :653-659)
@@ -676,6 +678,7 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
             p->launches++;
         }
     } else if (p->P > 1) {
+        p->last_render_kernel = 3;
         ShPartParams prm;
         prm.zprev = zprev; prm.zcur = zcur;
         prm.zspec = p->d_zspec + (size_t)s0 * p->NP * p->N2;
@@ -699,16 +702,21 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
         const unsigned gw = (unsigned)((count + 3) / 4);
         const dim3 gmac((unsigned)((p->F + 31) / 32), (unsigned)((count + 7) / 8));
+        const dim3 gmac2((unsigned)((p->F + 31) / 32), (unsigned)((count + 2 * RTB_MAC_WARPS - 1) / (2 * RTB_MAC_WARPS)));
+        static const bool mac_v1 = getenv("RTB_MAC_V1") && getenv("RTB_MAC_V1")[0] != '0';
+        const bool mac2 = !mac_v1 && (int)p->steps_prefix.back() <= RTB_MAC_MAX_STEPS;
+#define RTB_PART_LAUNCH(N)                                                                  \
+    case N:                                                                                 \
+        sh_spectra_kernel<N><<<gw, 128, 0, st>>>(prm);                                      \
+        if (mac2) sh_partition_mac2_kernel<N><<<gmac2, 32 * RTB_MAC_WARPS, 0, st>>>(prm);   \
+        else sh_partition_mac_kernel<N><<<gmac, 128, 0, st>>>(prm);                         \
+        sh_partition_tail_kernel<N><<<gw, 128, 0, st>>>(prm);                               \
+        break;
         switch (p->N2) {
-            case 64: sh_spectra_kernel<64><<<gw, 128, 0, st>>>(prm); sh_partition_mac_kernel<64><<<gmac, 128, 0, st>>>(prm);
-                     sh_partition_tail_kernel<64><<<gw, 128, 0, st>>>(prm); break;
-            case 128: sh_spectra_kernel<128><<<gw, 128, 0, st>>>(prm); sh_partition_mac_kernel<128><<<gmac, 128, 0, st>>>(prm);
-                      sh_partition_tail_kernel<128><<<gw, 128, 0, st>>>(prm); break;
-            case 256: sh_spectra_kernel<256><<<gw, 128, 0, st>>>(prm); sh_partition_mac_kernel<256><<<gmac, 128, 0, st>>>(prm);
-                      sh_partition_tail_kernel<256><<<gw, 128, 0, st>>>(prm); break;
-            default: sh_spectra_kernel<512><<<gw, 128, 0, st>>>(prm); sh_partition_mac_kernel<512><<<gmac, 128, 0, st>>>(prm);
-                     sh_partition_tail_kernel<512><<<gw, 128, 0, st>>>(prm); break;
+            RTB_PART_LAUNCH(64) RTB_PART_LAUNCH(128) RTB_PART_LAUNCH(256)
+            default: RTB_PART_LAUNCH(512)
         }
+#undef RTB_PART_LAUNCH
         p->launches += 2;
     } else {
         const int np_cur = signals_for_order(p, p->cur_order);
@@ -720,6 +728,7 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
             cudaStreamSynchronize(st);
             use_mg = build_mg_tables(p, p->cur_order) == RTB_OK && p->mg_enabled;
         }
+        p->last_render_kernel = use_mg ? ((p->split_enabled && p->N2 == 512) ? 2 : 1) : 0;
         if (use_mg) {
             ShRenderMgParams prm;
             prm.zprev = zprev; prm.zcur = zcur;
@@ -843,6 +852,7 @@ int rtb_sh_plan_query(rtb_sh_plan *p, int what, int64_t *value) {
         case RTB_Q_SIGNALS: *value = p->NP; break;
         case RTB_Q_LAUNCHES: *value = p->launches; break;
         case RTB_Q_TENSOR_CORE: *value = p->tc_enabled ? 1 : 0; break;
+        case RTB_Q_RENDER_KERNEL: *value = p->last_render_kernel; break;
         case RTB_Q_STATE_BYTES: *value = (int64_t)sizeof(float) * (2 * (int64_t)p->J * p->B + 2); break;
         case RTB_Q_ANALYSIS_NS:
         case RTB_Q_RENDER_NS: {
