@@ -22,6 +22,13 @@
 //   warp 12          one thread issues the MMAs of a chunk and commits the stage back
 //   warps 8-11       epilogue: TMEM lane quarter -> registers -> analysis rows (coalesced 128 B)
 // Two operand stages and two TMEM accumulators let the three roles overlap.
+//
+// Tile rows are the flattened (stream, sample) index, so blocks shorter than 128 samples put 2 or 4
+// streams into one M = 128 tile (low-latency 64-sample blocks, config c4).  When the split analysis
+// matrix does not fit in shared memory next to the operand stages (434 channels x 169 rows: 630 KB)
+// its K-chunks are streamed with cp.async.bulk into the same two stages as the input (STREAM_B):
+// the chunk of a stage is requested by the loader group that fills the stage, completion is counted
+// on the stage's `full` mbarrier together with the loader warps' arrivals.
 #pragma once
 
 namespace rtb {
@@ -67,7 +74,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
 #define RTB_TC_MAX_KC 64   // channels per pipeline chunk (register staging of the loaders)
 #define RTB_TC_THREADS 416
 
-template <int KC>
+template <int KC, bool STREAM_B>
 __global__ void __launch_bounds__(RTB_TC_THREADS, 1)
 sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                       const float *__restrict__ bsrc,  // [2][Kpad/4][Npad/8][8][4]: hi then lo
@@ -75,17 +82,21 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                       int S, int C, int J, int B, int Kpad, int Npad, int acc_cols) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *a_stage = reinterpret_cast<float *>(smem_raw);   // [2 stages][hi, lo][KC/4][16][8][4]
-    float *b_hi = a_stage + (size_t)4 * KC * RTB_TC_M;      // [Kpad/4][Npad/8][8][4]
+    // resident: [Kpad/4][Npad/8][8][4] hi, then lo; streamed: [2 stages][hi, lo][KC/4][Npad/8][8][4]
+    float *b_hi = a_stage + (size_t)4 * KC * RTB_TC_M;
     float *b_lo = b_hi + (size_t)Kpad * Npad;
+    const size_t bchunk_floats = (size_t)KC * Npad;         // one K-chunk of hi (or lo)
     __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < Kpad * Npad / 2; i += RTB_TC_THREADS)  // hi and lo halves are contiguous
-        reinterpret_cast<float4 *>(b_hi)[i] = __ldg(reinterpret_cast<const float4 *>(bsrc) + i);
+    if (!STREAM_B)
+        for (int i = tid; i < Kpad * Npad / 2; i += RTB_TC_THREADS)  // hi and lo halves are contiguous
+            reinterpret_cast<float4 *>(b_hi)[i] = __ldg(reinterpret_cast<const float4 *>(bsrc) + i);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&full_bar[i], 4);    // one arrival per loader warp of the stage's group
+            // one arrival per loader warp of the stage's group (+ the expect_tx arrival of the B chunk)
+            mbar_init(&full_bar[i], STREAM_B ? 5 : 4);
             mbar_init(&empty_bar[i], 1);   // tcgen05.commit
             mbar_init(&tfull_bar[i], 1);   // tcgen05.commit
             mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
@@ -102,8 +113,9 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    const int tiles_per_stream = B / RTB_TC_M;
-    const long long n_tiles = (long long)S * tiles_per_stream;
+    // tile = 128 consecutive rows of the flattened [S][B] sample index
+    const long long n_rows = (long long)S * B;
+    const long long n_tiles = (n_rows + RTB_TC_M - 1) / RTB_TC_M;
     const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int n_chunks = Kpad / KC;
     const long long my_chunks = my_tiles * n_chunks;
@@ -116,12 +128,14 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
         auto issue_loads = [&](long long n, float (&xr)[KC]) {
             const long long tile = blockIdx.x + (n / n_chunks) * gridDim.x;
             const int h = (int)(n % n_chunks);
-            const long long s = tile / tiles_per_stream;
-            const int t0 = (int)(tile % tiles_per_stream) * RTB_TC_M;
-            const float *xp = x + ((size_t)s * C + (size_t)h * KC) * B + t0 + t_in;
-            const int cmax = C - h * KC;
+            const long long g = tile * RTB_TC_M + t_in;     // flattened (stream, sample) row
+            const bool row_ok = g < n_rows;
+            const long long s = row_ok ? g / B : 0;
+            const int t = row_ok ? (int)(g % B) : 0;
+            const float *xp = x + ((size_t)s * C + (size_t)h * KC) * B + t;
+            const int cmax = row_ok ? C - h * KC : 0;
 #pragma unroll
-            for (int i = 0; i < KC; ++i) {  // predicated: channels beyond C read as zero
+            for (int i = 0; i < KC; ++i) {  // predicated: channels beyond C (and rows beyond S*B) read as zero
                 asm volatile(
                     "{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\tmov.f32 %0, 0f00000000;\n\t"
                     "@p ld.global.nc.f32 %0, [%1];\n\t}"
@@ -132,6 +146,15 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
         auto process = [&](long long n, float (&xr)[KC]) {
             const int st = (int)(n & 1);
             mbar_wait(&empty_bar[st], (unsigned)(((n >> 1) & 1) ^ 1));
+            if (STREAM_B && t_in == 0) {  // this chunk's rows of the split analysis matrix -> stage st
+                const int h = (int)(n % n_chunks);
+                const unsigned bytes = (unsigned)(bchunk_floats * sizeof(float));
+                float *bst = b_hi + (size_t)st * 2 * bchunk_floats;
+                mbar_expect_tx(&full_bar[st], 2 * bytes);
+                bulk_copy_g2s(bst, bsrc + (size_t)h * bchunk_floats, bytes, &full_bar[st]);
+                bulk_copy_g2s(bst + bchunk_floats, bsrc + (size_t)Kpad * Npad + (size_t)h * bchunk_floats, bytes,
+                              &full_bar[st]);
+            }
             float *ahi = a_stage + st * stage_floats, *alo = ahi + (size_t)KC * RTB_TC_M;
 #pragma unroll
             for (int u = 0; u < KC / 4; ++u) {
@@ -178,10 +201,14 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                     // chunk and step the field by a constant (no carry: shared memory is < 256 KB)
                     const uint32_t ahi = smem_u32(a_stage + st * stage_floats);
                     const uint32_t alo = ahi + (uint32_t)(KC * RTB_TC_M * sizeof(float));
-                    const uint32_t boff = (uint32_t)h * (KC / 4) * lbo_b;  // this chunk's k-range of B
                     const uint64_t da_hi = umma_desc(ahi, lbo_a, sbo), da_lo = umma_desc(alo, lbo_a, sbo);
-                    const uint64_t db_hi = umma_desc(smem_u32(b_hi) + boff, lbo_b, sbo);
-                    const uint64_t db_lo = umma_desc(smem_u32(b_lo) + boff, lbo_b, sbo);
+                    // this chunk's k-range of B: inside the resident matrix, or the stage's own copy
+                    const uint32_t bhi_a = STREAM_B ? smem_u32(b_hi + (size_t)st * 2 * bchunk_floats)
+                                                    : smem_u32(b_hi) + (uint32_t)h * (KC / 4) * lbo_b;
+                    const uint32_t blo_a = STREAM_B ? bhi_a + (uint32_t)(bchunk_floats * sizeof(float))
+                                                    : smem_u32(b_lo) + (uint32_t)h * (KC / 4) * lbo_b;
+                    const uint64_t db_hi = umma_desc(bhi_a, lbo_b, sbo);
+                    const uint64_t db_lo = umma_desc(blo_a, lbo_b, sbo);
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
                         const uint64_t da0 = pass == 1 ? da_lo : da_hi;
@@ -201,16 +228,18 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
         const int q = warp & 3;
         for (long long it = 0; it < my_tiles; ++it) {
             const long long tile = blockIdx.x + it * gridDim.x;
-            const long long s = tile / tiles_per_stream;
-            const int t0 = (int)(tile % tiles_per_stream) * RTB_TC_M;
+            const long long g = tile * RTB_TC_M + q * 32 + lane;  // this lane's (stream, sample) row
+            const bool row_ok = g < n_rows;
+            const long long s = row_ok ? g / B : 0;
+            const int t = row_ok ? (int)(g % B) : 0;
             const int acc = (int)(it & 1);
             mbar_wait(&tfull_bar[acc], (unsigned)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float *zp = zcur + ((size_t)s * J) * B + t0 + q * 32 + lane;
+            float *zp = zcur + ((size_t)s * J) * B + t;
             for (int cb = 0; cb < Npad; cb += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * acc_cols + cb, v);
-                const int nrow = J - cb;  // rows of this chunk that exist (uniform)
+                const int nrow = row_ok ? J - cb : 0;  // rows of this chunk that exist
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {  // predicated stores, pointer stepped by one row
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p st.global.b32 [%0], %1;\n\t}"

@@ -26,7 +26,7 @@ struct rtb_sh_plan {
     int an_TW = 0, an_stages = 0, an_grid = 0, an_smem = 0, an_nrun = 2;
     bool an_rsmem = true;
     // tensor-core analysis kernel (wide arrays): padded sizes, operand table, launch config
-    bool tc_enabled = false;
+    bool tc_enabled = false, tc_stream_b = false;
     int tc_Kpad = 0, tc_Npad = 0, tc_KC = 0, tc_smem = 0, tc_cols = 0, tc_grid = 0;
     float *d_tc_b = nullptr;      // [2][Kpad/4][Npad/8][8][4] analysis matrix split into TF32 hi / lo
     // device memory
@@ -111,24 +111,28 @@ void launch_analysis_j(const rtb_sh_plan *p, const float *d_in, float *zcur, int
 
 void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int count, cudaStream_t st) {
     if (p->tc_enabled) {
-        const long long tiles = (long long)count * (p->B / RTB_TC_M);
+        const long long tiles = ((long long)count * p->B + RTB_TC_M - 1) / RTB_TC_M;
         const int grid = (int)std::min<long long>(tiles, (long long)p->tc_grid);
-#define RTB_TC_LAUNCH(KCV)                                                                           \
-    case KCV: {                                                                                      \
+#define RTB_TC_LAUNCH_T(KCV, SB)                                                                      \
+    {                                                                                                \
         static bool attr_set = false;                                                                \
         if (!attr_set) {                                                                             \
-            cudaFuncSetAttribute(sh_analysis_tc_kernel<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
+            cudaFuncSetAttribute(sh_analysis_tc_kernel<KCV, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
             attr_set = true;                                                                         \
         }                                                                                            \
-        sh_analysis_tc_kernel<KCV><<<grid, RTB_TC_THREADS, p->tc_smem, st>>>(                        \
+        sh_analysis_tc_kernel<KCV, SB><<<grid, RTB_TC_THREADS, p->tc_smem, st>>>(                    \
             d_in, p->d_tc_b, zcur, count, p->C, p->J, p->B, p->tc_Kpad, p->tc_Npad, p->tc_cols);      \
-        break;                                                                                       \
     }
+#define RTB_TC_LAUNCH(KCV)                                                                           \
+    case KCV:                                                                                        \
+        if (p->tc_stream_b) RTB_TC_LAUNCH_T(KCV, true) else RTB_TC_LAUNCH_T(KCV, false)              \
+        break;
         switch (p->tc_KC) {
             RTB_TC_LAUNCH(8) RTB_TC_LAUNCH(16) RTB_TC_LAUNCH(24) RTB_TC_LAUNCH(32)
             RTB_TC_LAUNCH(40) RTB_TC_LAUNCH(48) RTB_TC_LAUNCH(56) RTB_TC_LAUNCH(64)
         }
 #undef RTB_TC_LAUNCH
+#undef RTB_TC_LAUNCH_T
         return;
     }
     switch (p->JT) {
@@ -543,12 +547,28 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
         p->tc_enabled = false;
         const char *env = getenv("RTB_ANALYSIS_TC");
         const bool want = env ? (env[0] != '0') : (C >= 64);
-        // K is cut into pipeline chunks of KC channels (multiple of 8, at most RTB_TC_MAX_KC)
-        const int n_kchunks = std::max(2, (C + RTB_TC_MAX_KC - 1) / RTB_TC_MAX_KC);
-        const int KC = ((C + n_kchunks - 1) / n_kchunks + 7) / 8 * 8;
-        const int Kpad = KC * n_kchunks, Npad = (J + 15) / 16 * 16;
-        const size_t tc_smem = sizeof(float) * ((size_t)4 * KC * RTB_TC_M + 2 * (size_t)Kpad * Npad);
-        if (want && B % RTB_TC_M == 0 && Npad <= 256 && tc_smem <= 216 * 1024) {
+        // K is cut into pipeline chunks of KC channels (multiple of 8, at most RTB_TC_MAX_KC).  If the
+        // split analysis matrix fits next to the two operand stages it stays resident, otherwise its
+        // K-chunks are streamed through the stages (largest KC that fits).
+        const int Npad = (J + 15) / 16 * 16;
+        int n_kchunks = std::max(2, (C + RTB_TC_MAX_KC - 1) / RTB_TC_MAX_KC);
+        int KC = ((C + n_kchunks - 1) / n_kchunks + 7) / 8 * 8;
+        int Kpad = KC * n_kchunks;
+        size_t tc_smem = sizeof(float) * ((size_t)4 * KC * RTB_TC_M + 2 * (size_t)Kpad * Npad);
+        bool stream_b = false;
+        if (tc_smem > 216 * 1024) {
+            stream_b = true;
+            KC = 0;
+            for (int kc = RTB_TC_MAX_KC; kc >= 8; kc -= 8)
+                if (sizeof(float) * (size_t)kc * (4 * RTB_TC_M + 4 * Npad) <= 216 * 1024) { KC = kc; break; }
+            if (KC) {
+                n_kchunks = (C + KC - 1) / KC;
+                KC = ((C + n_kchunks - 1) / n_kchunks + 7) / 8 * 8;  // even out the chunks
+                Kpad = KC * n_kchunks;
+                tc_smem = sizeof(float) * (size_t)KC * (4 * RTB_TC_M + 4 * Npad);
+            }
+        }
+        if (want && KC > 0 && Npad <= 256 && tc_smem <= 216 * 1024) {
             std::vector<float> bsrc(2 * (size_t)Kpad * Npad, 0.f);
             for (int j = 0; j < J; ++j)
                 for (int c = 0; c < C; ++c) {
@@ -567,6 +587,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
                 e2 = cudaMemcpy(p->d_tc_b, bsrc.data(), sizeof(float) * bsrc.size(), cudaMemcpyHostToDevice);
             if (e2 != cudaSuccess) return fail(RTB_ERR_CUDA, "tensor-core table upload failed: %s", cudaGetErrorString(e2));
             p->tc_enabled = true;
+            p->tc_stream_b = stream_b;
             p->tc_Kpad = Kpad; p->tc_Npad = Npad; p->tc_KC = KC; p->tc_smem = (int)tc_smem;
             p->tc_cols = Npad <= 32 ? 32 : (Npad <= 64 ? 64 : (Npad <= 128 ? 128 : 256));  // per accumulator
             p->tc_grid = n_sm;
