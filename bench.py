@@ -289,6 +289,9 @@ def run_gpu_arm(args):
         render_name = _capi.RENDER_KERNEL_NAMES.get(plan.query(_capi.RTB_Q_RENDER_KERNEL), "sh_render_kernel")
         analysis_name = "sh_analysis_tc_kernel" if plan.query(_capi.RTB_Q_TENSOR_CORE) else "sh_analysis_kernel"
         render_bytes = S * (4 * B * (2 * J + E) + 12)  # z rows of 2 blocks in, ear blocks out, yaw
+        P = -(-wl.CONFIGS[args.workload]["hrir_taps"] // B)
+        if P > 1:  # a-X: plus both output-side queues [P][E][Fp] c64, read and written once per block
+            render_bytes += S * 2 * 2 * 8 * P * E * ((B + 1 + 3) // 4 * 4)
         analysis_bytes = S * 4 * B * (C + J)
         chain_bytes = S * wl.chain_bytes_per_stream_block(C, B, E)
         chain_flops = S * wl.chain_flops_per_stream_block(C, tb["K"], B, E)

@@ -34,6 +34,26 @@ struct DeviceGuard {
     }
 };
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still draining; everything before
+// pdl_wait() (table staging, barrier setup) overlaps the predecessor's tail, everything after it sees
+// the predecessor's memory.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Packed FP32 (sm_100a FFMA2 / FADD2 / FMUL2, PTX *.f32x2): a complex value lives in an aligned
 // register pair and every complex add / scale / multiply-accumulate is one or two instructions.
 // The FP32 pipe does the same flops per cycle either way (tools/f32x2_probe.cu: 70.6 vs 71.3

@@ -82,6 +82,11 @@ sh_analysis_kernel(const float *__restrict__ x,    // [S][C][B]
             reinterpret_cast<float4 *>(rsm)[i] = __ldg(reinterpret_cast<const float4 *>(rmP) + i);
     }
     __syncthreads();
+    // PDL: the setup above overlapped the tail of the previous kernel in the stream; its output
+    // (the other half of the z ring is still being read by the previous block's render kernel)
+    // and the caller's input block are touched only from here on
+    pdl_wait();
+    pdl_trigger();
 
     auto issue = [&](long long it) {  // warp 0: bulk copies of tile `it` into its stage
         const long long tile = blockIdx.x + it * gridDim.x;

@@ -35,6 +35,9 @@ struct rtb_sh_plan {
     float4 *d_htab = nullptr;     // [NP][2][F]
     ShSignal *d_signals = nullptr;
     // steady-state render kernel (signals grouped by m, sh_render_mg.cuh): tables for `mg_order`
+    // programmatic dependent launch of the chain's kernels: RTB_PDL=1 enables.  Measured on B200:
+    // 1 024 streams 55.4 -> 62.8 us per block (worse), 10 240 streams 385 -> 380 us: off by default
+    bool pdl = false;
     bool mg_enabled = false, split_enabled = false;  // split: RTB_RENDER_SPLIT=1 (measured: no gain)
     int mg_order = -1, mg_np = 0;
     float4 *d_mg_htab = nullptr;
@@ -94,8 +97,8 @@ void launch_analysis_t(const rtb_sh_plan *p, const float *d_in, float *zcur, int
     }
     const long long tiles = (long long)count * (p->B / p->an_TW);
     const int grid = (int)std::min<long long>(tiles, (long long)p->an_grid);
-    sh_analysis_kernel<JTH, NRUN, R_SMEM><<<grid, 128, p->an_smem, st>>>(
-        d_in, p->d_rmT, zcur, count, p->C, p->J, p->B, p->an_TW, p->n_jchunks, p->an_stages);
+    launch_pdl(sh_analysis_kernel<JTH, NRUN, R_SMEM>, dim3(grid), dim3(128), (size_t)p->an_smem, st, p->pdl,
+               d_in, (const float *)p->d_rmT, zcur, count, p->C, p->J, p->B, p->an_TW, p->n_jchunks, p->an_stages);
 }
 
 template <int JTH>
@@ -151,7 +154,7 @@ void launch_render(const rtb_sh_plan *p, const ShRenderParams &prm, cudaStream_t
 }
 
 template <int N2>
-void launch_render_mg_t(const ShRenderMgParams &prm, cudaStream_t st) {
+void launch_render_mg_t(const ShRenderMgParams &prm, cudaStream_t st, bool pdl) {
     const size_t smem = RTB_MG_ACC_SMEM ? sizeof(float2) * 4 * (FftCfg<N2>::EPL / 2) * 4 * 32 : 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -159,11 +162,11 @@ void launch_render_mg_t(const ShRenderMgParams &prm, cudaStream_t st) {
         cudaFuncSetAttribute(sh_render_mg_kernel<N2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set = true;
     }
-    sh_render_mg_kernel<N2><<<(unsigned)((prm.S + 3) / 4), 128, smem, st>>>(prm);
+    launch_pdl(sh_render_mg_kernel<N2>, dim3((unsigned)((prm.S + 3) / 4)), dim3(128), smem, st, pdl, prm);
 }
 
 void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStream_t st) {
-    if (p->N2 == 256) launch_render_mg_t<256>(prm, st);
+    if (p->N2 == 256) launch_render_mg_t<256>(prm, st, p->pdl);
     else if (p->split_enabled) {  // two warps per stream
         static bool attr_set = false;
         if (!attr_set) {
@@ -173,7 +176,7 @@ void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStr
         }
         sh_render_split_kernel<RTB_SPLIT_STREAMS>
             <<<(unsigned)((prm.S + RTB_SPLIT_STREAMS - 1) / RTB_SPLIT_STREAMS), 64 * RTB_SPLIT_STREAMS, 0, st>>>(prm);
-    } else launch_render_mg_t<512>(prm, st);
+    } else launch_render_mg_t<512>(prm, st, p->pdl);
 }
 
 // Tables of the steady-state render kernel for SH order `order`: signals sorted by m (one group
@@ -515,6 +518,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     p->mg_enabled = p->P == 1 && (p->N2 == 256 || p->N2 == 512);
     if (const char *env = getenv("RTB_RENDER_MG")) p->mg_enabled = p->mg_enabled && env[0] != '0';
     if (const char *env = getenv("RTB_RENDER_SPLIT")) p->split_enabled = env[0] != '0';
+    if (const char *env = getenv("RTB_PDL")) p->pdl = env[0] != '0';
     if (p->mg_enabled) {
         p->h_hnm.assign(hnm, hnm + 2 * (size_t)K * 2 * F);
         const int rc = build_mg_tables(p, p->order);

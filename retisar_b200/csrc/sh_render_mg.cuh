@@ -143,10 +143,12 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
             }
         }
     };
-    if (np > 0) {
-        prefetch_h(0, 0);
-        prefetch_z(0);
-    }
+    if (np > 0) prefetch_h(0, 0);
+    // PDL: twiddles, signal list and the first HRIR tile were requested while the analysis kernel
+    // was still draining; its rows (and the caller's yaw angles) are read only after the wait
+    pdl_wait();
+    pdl_trigger();
+    if (np > 0) prefetch_z(0);
     cp_async_commit();
 
     if (active) {  // a4: (cos, sin)(m alpha) for the current and the previous yaw
