@@ -145,6 +145,16 @@ int rtb_fd_process_block_host(rtb_fd_plan *plan, const float *h_in, const float 
 int rtb_fd_plan_query(rtb_fd_plan *plan, int what, int64_t *value);
 int rtb_fd_plan_destroy(rtb_fd_plan *plan);
 
+/* ---- output stage of a client (reference: JackClient._process_deliver,
+ * ReTiSAR/_jack_client.py:770-867; levels as tools.calculate_rms / calculate_peak,
+ * tools.py:1117-1169).  In place: d_out[s][c][:] *= d_gain[c] (output volume x per-channel
+ * relative volume); d_rms / d_peak [n_streams][n_channels] receive the level of the scaled block
+ * (dB with zeros reported as -200 when as_level != 0; either may be NULL); *d_clip_count is
+ * incremented once per channel block whose peak exceeds 1 (the reference logs a warning). */
+int rtb_output_stage(float *d_out, const float *d_gain, float *d_rms, float *d_peak,
+                     unsigned int *d_clip_count, long long n_streams, int n_channels,
+                     int block_length, int as_level, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -244,6 +244,25 @@ def golden_delay(name, fs=48000, B=64, channels=3, max_sec=0.01, T=30, seed=401)
     print(name, "ring blocks", buf._buffer.shape[0])
 
 
+def golden_levels(name, seed=402):
+    """`tools.calculate_rms` / `calculate_peak` (`tools.py:1117-1169`) on output blocks scaled like
+    `_process_deliver` (`_jack_client.py:795`), incl. an all-zero channel and a clipping one."""
+    ref = rh.import_reference()
+    x = syn.noise_blocks(6, 4, 256, seed, scale=0.3)
+    x[2, 1] = 0.0
+    x[4, 3] *= 9.0
+    volume, rel = 10 ** (-3.0 / 20.0), np.array([[1.0], [0.5], [2.0], [1.0]])
+    y = x.copy()
+    rms, peak = [], []
+    for t in range(x.shape[0]):
+        y[t] *= volume * rel
+        rms.append(ref.tools.calculate_rms(y[t], is_level=True))
+        peak.append(ref.tools.calculate_peak(y[t], is_level=True))
+    np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), kind="levels", x=x, y=y, volume=volume,
+                        relative=rel, rms=np.stack(rms), peak=np.stack(peak))
+    print(name, "rms", rms[0])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     extract_grids()
@@ -294,6 +313,7 @@ def main():
 
     # block delay line of the JACK clients (row f4)
     golden_delay("delay_3ch_b64")
+    golden_levels("levels_4ch_b256")
 
 
 if __name__ == "__main__":

@@ -441,3 +441,32 @@ class DelayBufferOracle:
         y = self.buffer[self.ptr - self.delay_blocks]  # python index: -ring size wraps to 0
         self.ptr = (self.ptr + 1) % self.buffer.shape[0]
         return y
+
+
+def calculate_rms(data, is_level=False):
+    """`tools.calculate_rms` (`tools.py:1117-1145`), real data."""
+    rms = np.sqrt(np.mean(np.square(np.abs(data)), axis=-1))
+    if is_level:
+        rms[np.nonzero(rms == 0)] = np.nan
+        with np.errstate(divide="ignore"):
+            rms = 20 * np.log10(rms)
+        rms[np.isnan(rms)] = -200
+    return rms
+
+
+def calculate_peak(data_td, is_level=False):
+    """`tools.calculate_peak` (`tools.py:1148-1169`)."""
+    peak = np.nanmax(np.abs(data_td), axis=-1)
+    if is_level:
+        peak[np.nonzero(peak == 0)] = np.nan
+        with np.errstate(divide="ignore"):
+            peak = 20 * np.log10(peak)
+        peak[np.isnan(peak)] = -200
+    return peak
+
+
+def deliver(output_td, volume, volume_relative):
+    """Output stage of `JackClient._process_deliver` (`_jack_client.py:789-824`): in-place volume,
+    then RMS / peak levels in dBFS of the scaled block."""
+    output_td *= volume * volume_relative
+    return calculate_rms(output_td, is_level=True), calculate_peak(output_td, is_level=True)

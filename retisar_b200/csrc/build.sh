@@ -9,6 +9,6 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
     -Xcompiler -fPIC -shared \
     -Xptxas -v "$@" \
     -o "$out/libretisar_b200.so" \
-    "$here/capi.cu" "$here/sh_plan.cu" "$here/ols_plan.cu" "$here/fd_plan.cu" \
+    "$here/capi.cu" "$here/sh_plan.cu" "$here/ols_plan.cu" "$here/fd_plan.cu" "$here/output_stage.cu" \
     -cudart static
 echo "built $out/libretisar_b200.so"
