@@ -97,7 +97,8 @@ int rtb_sh_process_block_host(rtb_sh_plan *plan, const float *h_in, const float 
 #define RTB_Q_TENSOR_CORE 8 /* 1 if the analysis GEMM runs on tcgen05 (wide arrays)             */
 #define RTB_Q_RENDER_KERNEL 9 /* render kernel of the last block: 0 sh_render_kernel (term-wise),
                                  1 sh_render_mg_kernel (grouped by m), 2 sh_render_split_kernel,
-                                 3 partitioned (spectra + partition MAC + tail), 4 passthrough      */
+                                 3 partitioned (spectra + partition MAC + tail), 4 passthrough,
+                                 5 sh_render_eo_kernel (even / odd bins on two warps per stream)   */
 int rtb_sh_plan_query(rtb_sh_plan *plan, int what, int64_t *value);
 /* record CUDA events around each kernel of process_block (measurement aid, no reference
  * counterpart; the reference reports load through JACK, _jack_client.py:869-895) */
