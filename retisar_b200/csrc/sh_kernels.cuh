@@ -235,6 +235,7 @@ __device__ __forceinline__ float2 phase_of(const float2 *cs, int m) {
 }  // namespace rtb
 
 #include "sh_analysis_tc.cuh"
+#include "sh_analysis_mma.cuh"
 #include "sh_render.cuh"
 #include "sh_render_mg.cuh"
 #include "sh_render_split.cuh"

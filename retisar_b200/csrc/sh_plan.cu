@@ -27,6 +27,10 @@ struct rtb_sh_plan {
     bool an_rsmem = true;
     // tensor-core analysis kernel (wide arrays): padded sizes, operand table, launch config
     bool tc_enabled = false, tc_stream_b = false;
+    // warp-level tensor-core analysis kernel (narrow arrays, sh_analysis_mma.cuh)
+    bool mma_enabled = false;
+    int mma_TW = 0, mma_jchunks = 0, mma_smem = 0, mma_grid = 0, mma_stages = 2;
+    float *d_mma_r = nullptr;     // [n_jchunks][hi, lo][32 rows][32 channels]
     int tc_Kpad = 0, tc_Npad = 0, tc_KC = 0, tc_smem = 0, tc_cols = 0, tc_grid = 0;
     float *d_tc_b = nullptr;      // [2][Kpad/4][Npad/8][8][4] analysis matrix split into TF32 hi / lo
     // device memory
@@ -121,6 +125,18 @@ void launch_analysis_j(const rtb_sh_plan *p, const float *d_in, float *zcur, int
 }
 
 void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int count, cudaStream_t st) {
+    if (p->mma_enabled) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(sh_analysis_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        const long long tiles = (long long)count * (p->B / p->mma_TW);
+        const int grid = (int)std::min<long long>(tiles, (long long)p->mma_grid);
+        sh_analysis_mma_kernel<<<grid, 128, p->mma_smem, st>>>(d_in, p->d_mma_r, zcur, count, p->C, p->J, p->B,
+                                                              p->mma_TW, p->mma_jchunks, p->mma_stages);
+        return;
+    }
     if (p->tc_enabled) {
         const long long tiles = ((long long)count * p->B + RTB_TC_M - 1) / RTB_TC_M;
         const int grid = (int)std::min<long long>(tiles, (long long)p->tc_grid);
@@ -344,6 +360,8 @@ void free_tables(rtb_sh_plan *p) {
     p->mg_order = -1;
     cudaFree(p->d_steps); p->d_steps = nullptr;
     cudaFree(p->d_tc_b); p->d_tc_b = nullptr;
+    cudaFree(p->d_mma_r); p->d_mma_r = nullptr;
+    p->mma_enabled = false;
     cudaFree(p->d_zspec); p->d_zspec = nullptr;
     cudaFree(p->d_qcur); p->d_qcur = nullptr;
     cudaFree(p->d_qlast); p->d_qlast = nullptr;
@@ -637,6 +655,38 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
             p->tc_Kpad = Kpad; p->tc_Npad = Npad; p->tc_KC = KC; p->tc_smem = (int)tc_smem;
             p->tc_cols = Npad <= 32 ? 32 : (Npad <= 64 ? 64 : (Npad <= 128 ? 128 : 256));  // per accumulator
             p->tc_grid = n_sm;
+        }
+    }
+    {   // warp-level tensor-core variant for narrow arrays (RTB_ANALYSIS_MMA=0 disables)
+        const char *env = getenv("RTB_ANALYSIS_MMA");
+        const bool want = env ? env[0] != '0' : true;
+        if (want && !p->tc_enabled && C <= RTB_MMA_CP && B >= 64) {
+            const int njc = (J + RTB_MMA_JP - 1) / RTB_MMA_JP;
+            std::vector<float> r((size_t)njc * 2 * RTB_MMA_JP * RTB_MMA_CP, 0.f);
+            for (int j = 0; j < J; ++j)
+                for (int c = 0; c < C; ++c) {
+                    const float v = rows[j][c];
+                    uint32_t u;
+                    memcpy(&u, &v, 4);
+                    u = (u + 0x1000u) & 0xffffe000u;  // round to nearest TF32
+                    float hi;
+                    memcpy(&hi, &u, 4);
+                    const size_t o = ((size_t)(j / RTB_MMA_JP) * 2 * RTB_MMA_JP + j % RTB_MMA_JP) * RTB_MMA_CP + c;
+                    r[o] = hi;
+                    r[o + (size_t)RTB_MMA_JP * RTB_MMA_CP] = v - hi;
+                }
+            cudaError_t e2 = cudaMalloc(&p->d_mma_r, sizeof(float) * r.size());
+            if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_mma_r, r.data(), sizeof(float) * r.size(), cudaMemcpyHostToDevice);
+            if (e2 != cudaSuccess) return fail(RTB_ERR_CUDA, "analysis table upload failed: %s", cudaGetErrorString(e2));
+            p->mma_enabled = true;
+            p->mma_jchunks = njc;
+            p->mma_TW = std::min(B, RTB_MMA_TW);
+            p->mma_stages = 2;
+            if (const char *e3 = getenv("RTB_MMA_STAGES")) p->mma_stages = std::max(2, std::min(RTB_AN_MAX_STAGES, atoi(e3)));
+            p->mma_smem = p->mma_stages * RTB_MMA_CP * (p->mma_TW + RTB_MMA_PAD) * (int)sizeof(float);
+            int n_sm = 148;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device);
+            p->mma_grid = n_sm * std::max(1, std::min(3, (224 * 1024) / (p->mma_smem + 2048)));
         }
     }
     p->slot = 0; p->rad_idx = 0;
