@@ -146,6 +146,12 @@ int rtb_fd_process_block_host(rtb_fd_plan *plan, const float *h_in, const float 
 int rtb_fd_plan_query(rtb_fd_plan *plan, int what, int64_t *value);
 int rtb_fd_plan_destroy(rtb_fd_plan *plan);
 
+/* ---- page-locked host buffers for the *_process_block_host entry points (the reference hands
+ * numpy blocks to filter_block, ReTiSAR/_jack_renderer.py:315; pinned blocks make the host-to-device
+ * copy a single DMA).  write_combined != 0: write-combined memory, for input blocks only. */
+int rtb_host_alloc(void **ptr, unsigned long long bytes, int write_combined);
+int rtb_host_free(void *ptr);
+
 /* ---- output stage of a client (reference: JackClient._process_deliver,
  * ReTiSAR/_jack_client.py:770-867; levels as tools.calculate_rms / calculate_peak,
  * tools.py:1117-1169).  In place: d_out[s][c][:] *= d_gain[c] (output volume x per-channel

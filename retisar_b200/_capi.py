@@ -57,6 +57,8 @@ SIGNATURES = {
     "rtb_fd_process_block_host": (_i, [_vp, _vp, _vp, _vp]),
     "rtb_fd_plan_query": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
     "rtb_fd_plan_destroy": (_i, [_vp]),
+    "rtb_host_alloc": (_i, [ctypes.POINTER(_vp), ctypes.c_ulonglong, _i]),
+    "rtb_host_free": (_i, [_vp]),
     "rtb_output_stage": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _i, _i, _vp]),
 }
 

@@ -34,4 +34,23 @@ int rtb_device_count(void) {
     return n;
 }
 
+// Page-locked host buffers for the host-buffer entry points (rtb_*_process_block_host): blocks that
+// the caller fills on the CPU and the library copies to the device.  write_combined != 0 allocates
+// write-combined memory (not cached by the CPU: fast to fill sequentially and to DMA, slow to read
+// back on the host -- use it for input blocks only).
+int rtb_host_alloc(void **ptr, unsigned long long bytes, int write_combined) {
+    if (!ptr || bytes == 0) return rtb::fail(RTB_ERR_INVALID, "bad host allocation request");
+    cudaError_t err = cudaHostAlloc(ptr, (size_t)bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (err != cudaSuccess) {
+        *ptr = nullptr;
+        return rtb::fail(RTB_ERR_NOMEM, "cudaHostAlloc(%llu) failed: %s", bytes, cudaGetErrorString(err));
+    }
+    return RTB_OK;
+}
+
+int rtb_host_free(void *ptr) {
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) return rtb::fail(RTB_ERR_CUDA, "cudaFreeHost failed");
+    return RTB_OK;
+}
+
 }  // extern "C"

@@ -223,3 +223,25 @@ class FdPlan:
     def process_device(self, d_x, d_yaw, d_out, stream=None):
         check(lib.rtb_fd_process_block(self._h, _dev_ptr(d_x), _dev_ptr(d_yaw), _dev_ptr(d_out),
                                        _stream_ptr(stream)))
+
+
+class PinnedBuffer:
+    """Page-locked host block buffer from ``rtb_host_alloc``; ``.array`` is a numpy view.  Blocks
+    handed to ``filter_block`` / ``process_host`` from such a buffer are copied to the device by a
+    single DMA.  ``write_combined=True`` is for input blocks only (slow to read on the host)."""
+
+    def __init__(self, shape, dtype=np.float32, write_combined=False):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._ptr = ctypes.c_void_p()
+        check(lib.rtb_host_alloc(ctypes.byref(self._ptr), n, int(bool(write_combined))))
+        buf = (ctypes.c_char * n).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "_ptr", None) is not None and self._ptr.value:
+            self.array = None
+            lib.rtb_host_free(self._ptr)
+            self._ptr = ctypes.c_void_p()
+
+    __del__ = close
