@@ -1,7 +1,20 @@
 // Library-level entry points of the C ABI (include/retisar_b200.h) and the error channel.
 #include "rtb_common.cuh"
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 namespace rtb {
+
+bool first_use_on_device(const void *func) {
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    return seen.insert(std::make_pair(func, dev)).second;
+}
 
 char *last_error_buffer() {
     static thread_local char buf[512] = "";

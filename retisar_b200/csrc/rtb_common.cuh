@@ -34,6 +34,16 @@ struct DeviceGuard {
     }
 };
 
+// Function attributes are per device: set them once per (kernel, device) pair, so that plans on
+// several devices of one process all get their large dynamic shared-memory windows.
+bool first_use_on_device(const void *func);  // capi.cu
+template <class K>
+inline void kernel_attrs_once(K kernel, int max_dynamic_smem, bool prefer_smem_carveout = false) {
+    if (!first_use_on_device(reinterpret_cast<const void *>(kernel))) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem);
+    if (prefer_smem_carveout) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
 // attribute may start while its predecessor in the stream is still draining; everything before
 // pdl_wait() (table staging, barrier setup) overlaps the predecessor's tail, everything after it sees

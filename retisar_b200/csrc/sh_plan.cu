@@ -101,12 +101,7 @@ int signals_for_order(const rtb_sh_plan *p, int order) {
 
 template <int JTH, int NRUN, bool R_SMEM>
 void launch_analysis_t(const rtb_sh_plan *p, const float *d_in, float *zcur, int count, cudaStream_t st) {
-    static bool attr_set = false;  // once per instantiation
-    if (!attr_set) {
-        cudaFuncSetAttribute(sh_analysis_kernel<JTH, NRUN, R_SMEM>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_set = true;
-    }
+    kernel_attrs_once(sh_analysis_kernel<JTH, NRUN, R_SMEM>, 220 * 1024);
     const long long tiles = (long long)count * (p->B / p->an_TW);
     const int grid = (int)std::min<long long>(tiles, (long long)p->an_grid);
     launch_pdl(sh_analysis_kernel<JTH, NRUN, R_SMEM>, dim3(grid), dim3(128), (size_t)p->an_smem, st, p->pdl,
@@ -126,11 +121,7 @@ void launch_analysis_j(const rtb_sh_plan *p, const float *d_in, float *zcur, int
 
 void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int count, cudaStream_t st) {
     if (p->mma_enabled) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(sh_analysis_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
-        }
+        kernel_attrs_once(sh_analysis_mma_kernel, 200 * 1024);
         const long long tiles = (long long)count * (p->B / p->mma_TW);
         const int grid = (int)std::min<long long>(tiles, (long long)p->mma_grid);
         sh_analysis_mma_kernel<<<grid, 128, p->mma_smem, st>>>(d_in, p->d_mma_r, zcur, count, p->C, p->J, p->B,
@@ -142,11 +133,7 @@ void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int c
         const int grid = (int)std::min<long long>(tiles, (long long)p->tc_grid);
 #define RTB_TC_LAUNCH_T(KCV, SB)                                                                      \
     {                                                                                                \
-        static bool attr_set = false;                                                                \
-        if (!attr_set) {                                                                             \
-            cudaFuncSetAttribute(sh_analysis_tc_kernel<KCV, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); \
-            attr_set = true;                                                                         \
-        }                                                                                            \
+        kernel_attrs_once(sh_analysis_tc_kernel<KCV, SB>, 224 * 1024);                                \
         sh_analysis_tc_kernel<KCV, SB><<<grid, RTB_TC_THREADS, p->tc_smem, st>>>(                    \
             d_in, p->d_tc_b, zcur, count, p->C, p->J, p->B, p->tc_Kpad, p->tc_Npad, p->tc_cols);      \
     }
@@ -180,12 +167,7 @@ void launch_render(const rtb_sh_plan *p, const ShRenderParams &prm, cudaStream_t
 template <int N2>
 void launch_render_mg_t(const ShRenderMgParams &prm, cudaStream_t st, bool pdl) {
     const size_t smem = RTB_MG_ACC_SMEM ? sizeof(float2) * 4 * (FftCfg<N2>::EPL / 2) * 4 * 32 : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(sh_render_mg_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute(sh_render_mg_kernel<N2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr_set = true;
-    }
+    kernel_attrs_once(sh_render_mg_kernel<N2>, 100 * 1024, true);
     launch_pdl(sh_render_mg_kernel<N2>, dim3((unsigned)((prm.S + 3) / 4)), dim3(128), smem, st, pdl, prm);
 }
 
@@ -194,12 +176,7 @@ void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStr
         constexpr int NST = RTB_EO_STREAMS;
         const size_t smem = sizeof(float2) * (2 * NST) * (4 * 4 * 32) + sizeof(float) * NST * 4 * 256 +
                             sizeof(float2) * (2 * NST) * 256;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(sh_render_eo_kernel<NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(sh_render_eo_kernel<NST>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            attr_set = true;
-        }
+        kernel_attrs_once(sh_render_eo_kernel<NST>, (int)smem, true);
         ShRenderMgParams q = prm;
         q.htab = p->d_eo_htab;
         sh_render_eo_kernel<NST><<<(unsigned)((prm.S + NST - 1) / NST), 64 * NST, smem, st>>>(q);
@@ -207,12 +184,7 @@ void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStr
     }
     if (p->N2 == 256) launch_render_mg_t<256>(prm, st, p->pdl);
     else if (p->split_enabled) {  // two warps per stream
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(sh_render_split_kernel<RTB_SPLIT_STREAMS>,
-                                 cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            attr_set = true;
-        }
+        kernel_attrs_once(sh_render_split_kernel<RTB_SPLIT_STREAMS>, 48 * 1024, true);
         sh_render_split_kernel<RTB_SPLIT_STREAMS>
             <<<(unsigned)((prm.S + RTB_SPLIT_STREAMS - 1) / RTB_SPLIT_STREAMS), 64 * RTB_SPLIT_STREAMS, 0, st>>>(prm);
     } else launch_render_mg_t<512>(prm, st, p->pdl);
