@@ -157,3 +157,26 @@ def test_reference_default_block_length_through_the_classes():
     for c in range(2):
         ref = np.convolve(xs[c], irs[c].astype(np.float64))[: 3 * B]
         assert np.abs(y[c] - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("order,C,B", [(5, 30, 128), (6, 32, 256), (7, 24, 64)])
+def test_narrow_array_more_rows_than_one_mma_pass(order, C, B):
+    """Narrow arrays (C <= 32) with more than 32 real analysis rows: the warp-level tensor-core
+    analysis kernel streams its tiles once per chunk of 32 rows."""
+    from oracle import sh_chain as oc
+    from retisar_b200 import _capi
+    from retisar_b200.plans import ShPlan
+
+    S, T = 5, 4
+    sh_m, Yw, Hnm = _sh_tables(B, order, C, min(100, B), 300 + order)
+    plan = ShPlan(S, B, C, order)
+    plan.set_tables(Yw, Hnm, sh_m, oc.reverse_mn_ids(order), *oc.crossfade_windows(B))
+    assert plan.query(_capi.RTB_Q_ROWS) > 32
+    oracles = [oc.ShOracle(sh_m, Yw, Hnm, B, order) for _ in range(S)]
+    rng = np.random.default_rng(order)
+    for t in range(T):
+        x = (rng.standard_normal((S, C, B)) * 0.1).astype(np.float32)
+        yaw = rng.uniform(0, 360, S).astype(np.float32)
+        y = plan.process_host(x, yaw)
+        ref = np.stack([o.filter_block(x[s], yaw[s]) for s, o in enumerate(oracles)])
+        assert np.abs(y - ref).max() <= TOL, (order, t, np.abs(y - ref).max())
