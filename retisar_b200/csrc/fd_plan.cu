@@ -55,9 +55,9 @@ fd_render_kernel(const FdParams prm) {
     using Cfg = FftCfg<N2>;
     constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS, B = N2 / 2;
     constexpr bool BIG = Cfg::BIG;  // one stream per CTA, exchange buffer in dynamic smem
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ float2 s_tw[BIG ? 1 : N2];
-    __shared__ __align__(16) float2 s_buf[BIG ? 1 : 4 * GROUPS * Cfg::REGION];
+    __shared__ __align__(128) float2 s_buf[BIG ? 1 : 4 * GROUPS * Cfg::REGION];
     const int warp = BIG ? 0 : (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int grp = BIG ? 0 : lane / G, l = BIG ? (int)threadIdx.x : lane % G;
     const float2 *tw = prm.tw;

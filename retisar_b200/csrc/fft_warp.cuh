@@ -59,6 +59,25 @@ __host__ __device__ __forceinline__ constexpr int fft_swz(int i) {
 //   fft_swz(lane_part + const_part) == fft_swz(lane_part) ^ fft_swz(const_part)
 // : one XOR with an immediate per access instead of recomputing the swizzle.
 
+// Shared-memory accesses by 32-bit shared address.  The swizzle only changes index bits 0..3, and
+// the lane part and the compile-time part of every index occupy disjoint bit fields above them, so
+//   address(lane ^ const) = ((base + 8 * lane) ^ (8 * const & 0x78)) + (8 * const & ~0x78)
+// for any exchange buffer aligned to 128 bytes: one LOP3 per distinct low part (a handful per
+// pass) and an immediate offset per access, instead of XOR + scale + add for each of them.
+// (RTB_FFT_XORADDR = 0 restores plain indexing; transforms of 64 points always use it.)
+#ifndef RTB_FFT_XORADDR
+#define RTB_FFT_XORADDR 1
+#endif
+__device__ __forceinline__ unsigned smem_addr32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts64(unsigned addr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float2 lds64(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
 // multiply by -i (forward) / +i (inverse)
 template <bool INV>
 __device__ __forceinline__ float2 rot90(float2 a) {
@@ -106,7 +125,7 @@ __device__ __forceinline__ void dft_r(float2 (&v)[R]) {
 // One Stockham pass of radix R over sub-transforms of length NS (product of earlier radices).
 // TO_SMEM: scatter the results into the exchange buffer, otherwise keep them in X (last pass).
 // Cfg: LEN (transform length), G (lanes per transform), EPL (elements per lane).
-template <class Cfg, int R, int NS, bool INV, bool TO_SMEM>
+template <class Cfg, int R, int NS, bool INV, bool TO_SMEM, bool AL = (RTB_FFT_XORADDR && Cfg::LEN >= 128)>
 __device__ __forceinline__ void fft_pass_c(float2 (&X)[Cfg::EPL], float2 *buf, const float2 *tw, int l) {
     constexpr int N2 = Cfg::LEN;
     constexpr int NB = Cfg::EPL / R;  // butterflies per lane
@@ -152,8 +171,17 @@ __device__ __forceinline__ void fft_pass_c(float2 (&X)[Cfg::EPL], float2 *buf, c
             static_assert((Cfg::G % NS) == 0, "lane and butterfly fields must not overlap");
             const int lbase = fft_swz<N2>((l / NS) * NS * R + (l & (NS - 1)));
             const int cb = (Cfg::G * b / NS) * NS * R;
+            if constexpr (AL) {
+                const unsigned pre = smem_addr32(buf) + (unsigned)lbase * 8u;
 #pragma unroll
-            for (int t = 0; t < R; ++t) buf[lbase ^ fft_swz<N2>(cb + t * NS)] = v[t];
+                for (int t = 0; t < R; ++t) {
+                    const unsigned c8 = (unsigned)fft_swz<N2>(cb + t * NS) * 8u;
+                    sts64((pre ^ (c8 & 0x78u)) + (c8 & ~0x78u), v[t]);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < R; ++t) buf[lbase ^ fft_swz<N2>(cb + t * NS)] = v[t];
+            }
         } else {
 #pragma unroll
             for (int t = 0; t < R; ++t) X[b + t * NB] = v[t];
@@ -162,12 +190,21 @@ __device__ __forceinline__ void fft_pass_c(float2 (&X)[Cfg::EPL], float2 *buf, c
 }
 
 // gather the next pass's inputs from the exchange buffer; `sync` = barrier over the transform's lanes
-template <class Cfg, class Sync>
+template <class Cfg, bool AL = (RTB_FFT_XORADDR && Cfg::LEN >= 128), class Sync>
 __device__ __forceinline__ void fft_exchange_c(float2 (&X)[Cfg::EPL], const float2 *buf, int l, Sync &&sync) {
     sync();
     const int lbase = fft_swz<Cfg::LEN>(l);
+    if constexpr (AL) {
+        const unsigned pre = smem_addr32(buf) + (unsigned)lbase * 8u;
 #pragma unroll
-    for (int u = 0; u < Cfg::EPL; ++u) X[u] = buf[lbase ^ fft_swz<Cfg::LEN>(Cfg::G * u)];
+        for (int u = 0; u < Cfg::EPL; ++u) {
+            const unsigned c8 = (unsigned)fft_swz<Cfg::LEN>(Cfg::G * u) * 8u;
+            X[u] = lds64((pre ^ (c8 & 0x78u)) + (c8 & ~0x78u));
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < Cfg::EPL; ++u) X[u] = buf[lbase ^ fft_swz<Cfg::LEN>(Cfg::G * u)];
+    }
     sync();
 }
 
@@ -175,25 +212,25 @@ __device__ __forceinline__ void fft_exchange_c(float2 (&X)[Cfg::EPL], const floa
 // `tw` = exp(-2*pi*i*q/LEN), q < LEN (shared or global memory), l = lane index inside the group.
 // All lanes of the group must call it together.  `after_last_exchange()` runs once the exchange
 // buffer is idle (before the final register pass): the place to start prefetching the next input.
-template <class Cfg, bool INV, class Sync, class Hook>
+template <class Cfg, bool INV, bool AL = (RTB_FFT_XORADDR && Cfg::LEN >= 128), class Sync, class Hook>
 __device__ __forceinline__ void fft_run_c(float2 (&X)[Cfg::EPL], float2 *buf, const float2 *tw, int l,
                                           Sync &&sync, Hook &&after_last_exchange) {
     constexpr int NP = Cfg::NPASS8;
     constexpr bool TAIL = Cfg::R_LAST != 0;
-    fft_pass_c<Cfg, 8, 1, INV, true>(X, buf, tw, l);
-    fft_exchange_c<Cfg>(X, buf, l, sync);
+    fft_pass_c<Cfg, 8, 1, INV, true, AL>(X, buf, tw, l);
+    fft_exchange_c<Cfg, AL>(X, buf, l, sync);
     if constexpr (NP == 2 && !TAIL) after_last_exchange();
-    fft_pass_c<Cfg, 8, 8, INV, (NP > 2 || TAIL)>(X, buf, tw, l);
-    if constexpr (NP > 2 || TAIL) fft_exchange_c<Cfg>(X, buf, l, sync);
+    fft_pass_c<Cfg, 8, 8, INV, (NP > 2 || TAIL), AL>(X, buf, tw, l);
+    if constexpr (NP > 2 || TAIL) fft_exchange_c<Cfg, AL>(X, buf, l, sync);
     if constexpr (NP >= 3) {
         if constexpr (NP == 3 && !TAIL) after_last_exchange();
-        fft_pass_c<Cfg, 8, 64, INV, (NP > 3 || TAIL)>(X, buf, tw, l);
-        if constexpr (NP > 3 || TAIL) fft_exchange_c<Cfg>(X, buf, l, sync);
+        fft_pass_c<Cfg, 8, 64, INV, (NP > 3 || TAIL), AL>(X, buf, tw, l);
+        if constexpr (NP > 3 || TAIL) fft_exchange_c<Cfg, AL>(X, buf, l, sync);
     }
     if constexpr (NP >= 4) {
         if constexpr (!TAIL) after_last_exchange();
-        fft_pass_c<Cfg, 8, 512, INV, TAIL>(X, buf, tw, l);
-        if constexpr (TAIL) fft_exchange_c<Cfg>(X, buf, l, sync);
+        fft_pass_c<Cfg, 8, 512, INV, TAIL, AL>(X, buf, tw, l);
+        if constexpr (TAIL) fft_exchange_c<Cfg, AL>(X, buf, l, sync);
     }
     if constexpr (TAIL) {
         after_last_exchange();
@@ -201,16 +238,16 @@ __device__ __forceinline__ void fft_run_c(float2 (&X)[Cfg::EPL], float2 *buf, co
     }
 }
 
-template <int N2, bool INV, class Hook>
+template <int N2, bool INV, bool AL = (RTB_FFT_XORADDR && N2 >= 128), class Hook>
 __device__ __forceinline__ void warp_fft_hook(float2 (&X)[FftCfg<N2>::EPL], float2 *buf,
                                               const float2 *tw, int l, Hook &&after_last_exchange) {
-    fft_run_c<FftCfg<N2>, INV>(X, buf, tw, l, [] { fft_sync<N2>(); }, after_last_exchange);
+    fft_run_c<FftCfg<N2>, INV, AL>(X, buf, tw, l, [] { fft_sync<N2>(); }, after_last_exchange);
 }
 
-template <int N2, bool INV>
+template <int N2, bool INV, bool AL = (RTB_FFT_XORADDR && N2 >= 128)>
 __device__ __forceinline__ void warp_fft(float2 (&X)[FftCfg<N2>::EPL], float2 *buf,
                                          const float2 *tw, int l) {
-    warp_fft_hook<N2, INV>(X, buf, tw, l, [] {});
+    warp_fft_hook<N2, INV, AL>(X, buf, tw, l, [] {});
 }
 
 // After a forward transform lane l holds element l + G*u in X[u].  Mirror access: the element at

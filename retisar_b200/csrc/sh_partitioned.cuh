@@ -50,7 +50,7 @@ sh_spectra_kernel(const ShPartParams prm) {
     using Cfg = FftCfg<N2>;
     constexpr int G = Cfg::G, EPL = Cfg::EPL, GROUPS = Cfg::GROUPS, B = N2 / 2;
     __shared__ float2 s_tw[N2];
-    __shared__ __align__(16) float2 s_buf[4][GROUPS * Cfg::REGION];
+    __shared__ __align__(128) float2 s_buf[4][GROUPS * Cfg::REGION];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, l = lane % G;
     for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
@@ -386,7 +386,7 @@ sh_partition_tail_kernel(const ShPartParams prm) {
     using Cfg = FftCfg<N2>;
     constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS, B = N2 / 2;
     __shared__ float2 s_tw[N2];
-    __shared__ __align__(16) float2 s_buf[4][GROUPS * Cfg::REGION];
+    __shared__ __align__(128) float2 s_buf[4][GROUPS * Cfg::REGION];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, l = lane % G;
     for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];

@@ -101,9 +101,9 @@ sh_render_kernel(const ShRenderParams prm) {
     constexpr int NW = BIG ? 1 : 4;  // streams per CTA
     constexpr unsigned FULL = 0xffffffffu;
 
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ float2 s_tw[BIG ? 1 : N2];
-    __shared__ __align__(16) float2 s_buf[BIG ? 1 : 4 * GROUPS * Cfg::REGION];
+    __shared__ __align__(128) float2 s_buf[BIG ? 1 : 4 * GROUPS * Cfg::REGION];
     __shared__ __align__(16) float4 s_h[2][BIG ? 1 : GROUPS * HSIG];
     __shared__ float2 s_cs[NW][2][RTB_MAX_ORDER + 1];
 

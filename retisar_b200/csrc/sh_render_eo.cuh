@@ -48,7 +48,7 @@ sh_render_eo_kernel(const ShRenderMgParams prm) {
     constexpr int NT = 64 * NST, NW = 2 * NST;
     constexpr unsigned FULL = 0xffffffffu;
 
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     float2 *s_acc_all = reinterpret_cast<float2 *>(dyn_smem);                 // [NW][HB*4*32]
     float *s_land_all = reinterpret_cast<float *>(s_acc_all + NW * HB * 4 * 32);  // [NST][4][B] rows
     float2 *s_buf_all = reinterpret_cast<float2 *>(s_land_all + NST * 4 * B);     // [NW][NH] exchange

@@ -84,12 +84,12 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     constexpr unsigned FULL = 0xffffffffu;
 
     __shared__ __align__(16) float2 s_tw[N2];
-    __shared__ __align__(16) float2 s_buf[4][Cfg::REGION];
+    __shared__ __align__(128) float2 s_buf[4][Cfg::REGION];
     __shared__ __align__(16) float4 s_h[2][HSIG];
     __shared__ float2 s_cs[4][2][RTB_MAX_ORDER + 1];
     __shared__ ShMgSignal s_sig[RTB_MG_MAX_SIGNALS];  // the signal list: no dependent global load per round
 #if RTB_MG_ACC_SMEM
-    extern __shared__ __align__(16) unsigned char dyn_smem[];  // [4 warps][HB][4][32 lanes] float2
+    extern __shared__ __align__(128) unsigned char dyn_smem[];  // [4 warps][HB][4][32 lanes] float2
 #endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -38,7 +38,7 @@ sh_render_split_kernel(const ShRenderMgParams prm) {
     constexpr int NT = 64 * NST;
 
     __shared__ float2 s_tw[N2];
-    __shared__ __align__(16) float2 s_buf[NST][Cfg::REGION];
+    __shared__ __align__(128) float2 s_buf[NST][Cfg::REGION];
     __shared__ __align__(16) float4 s_h[2][HSIG];
     __shared__ float2 s_cs[NST][2][RTB_MAX_ORDER + 1];
     __shared__ ShMgSignal s_sig[RTB_MG_MAX_SIGNALS];  // the signal list: no dependent global load per round
