@@ -653,6 +653,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
             p->mma_enabled = true;
             p->mma_jchunks = njc;
             p->mma_TW = std::min(B, RTB_MMA_TW);
+            if (const char *e4 = getenv("RTB_MMA_TW")) p->mma_TW = std::max(64, std::min(p->mma_TW, atoi(e4)));
             p->mma_stages = 2;
             if (const char *e3 = getenv("RTB_MMA_STAGES")) p->mma_stages = std::max(2, std::min(RTB_AN_MAX_STAGES, atoi(e3)));
             p->mma_smem = p->mma_stages * RTB_MMA_CP * (p->mma_TW + RTB_MMA_PAD) * (int)sizeof(float);
