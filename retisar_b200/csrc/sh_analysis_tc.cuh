@@ -21,7 +21,9 @@
 //                    current one is processed), TF32 split, scatter, fence.proxy.async
 //   warp 12          one thread issues the MMAs of a chunk and commits the stage back
 //   warps 8-11       epilogue: TMEM lane quarter -> registers -> analysis rows (coalesced 128 B)
-// Two operand stages and two TMEM accumulators let the three roles overlap.
+// A ring of 2-4 operand stages and two TMEM accumulators let the three roles overlap (with two
+// stages the loaders could only start on a stage once its MMAs had retired: a clock64 trace showed
+// the MMA issuer waiting ~3000 of the 7000 cycles per tile for them).
 //
 // Tile rows are the flattened (stream, sample) index, so blocks shorter than 128 samples put 2 or 4
 // streams into one M = 128 tile (low-latency 64-sample blocks, config c4).  When the split analysis
@@ -70,23 +72,32 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
         ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// -DRTB_TRACE_TC: CTA 0 logs clock64 stamps per role and tile (tools/tc_trace.py)
+#ifdef RTB_TRACE_TC
+__device__ long long g_tc_trace[4096];
+#define TC_STAMP(role, it, k) do { if (blockIdx.x == 0 && (it) < 100) g_tc_trace[(role) * 1000 + (it) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TC_STAMP(role, it, k) do {} while (0)
+#endif
+
 #define RTB_TC_M 128
 #define RTB_TC_MAX_KC 64   // channels per pipeline chunk (register staging of the loaders)
 #define RTB_TC_THREADS 416
+#define RTB_TC_MAX_ST 4     // operand stages (ring): the loaders run up to nst - 1 chunks ahead of the MMAs
 
 template <int KC, bool STREAM_B>
 __global__ void __launch_bounds__(RTB_TC_THREADS, 1)
 sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                       const float *__restrict__ bsrc,  // [2][Kpad/4][Npad/8][8][4]: hi then lo
                       float *__restrict__ zcur,        // [S][J][B]
-                      int S, int C, int J, int B, int Kpad, int Npad, int acc_cols) {
+                      int S, int C, int J, int B, int Kpad, int Npad, int acc_cols, int nst) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *a_stage = reinterpret_cast<float *>(smem_raw);   // [2 stages][hi, lo][KC/4][16][8][4]
+    float *a_stage = reinterpret_cast<float *>(smem_raw);   // [nst stages][hi, lo][KC/4][16][8][4]
     // resident: [Kpad/4][Npad/8][8][4] hi, then lo; streamed: [2 stages][hi, lo][KC/4][Npad/8][8][4]
-    float *b_hi = a_stage + (size_t)4 * KC * RTB_TC_M;
+    float *b_hi = a_stage + (size_t)nst * 2 * KC * RTB_TC_M;
     float *b_lo = b_hi + (size_t)Kpad * Npad;
     const size_t bchunk_floats = (size_t)KC * Npad;         // one K-chunk of hi (or lo)
-    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[RTB_TC_MAX_ST], empty_bar[RTB_TC_MAX_ST], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -94,10 +105,12 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
         for (int i = tid; i < Kpad * Npad / 2; i += RTB_TC_THREADS)  // hi and lo halves are contiguous
             reinterpret_cast<float4 *>(b_hi)[i] = __ldg(reinterpret_cast<const float4 *>(bsrc) + i);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < RTB_TC_MAX_ST; ++i) {
             // one arrival per loader warp of the stage's group (+ the expect_tx arrival of the B chunk)
             mbar_init(&full_bar[i], STREAM_B ? 5 : 4);
             mbar_init(&empty_bar[i], 1);   // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);   // tcgen05.commit
             mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
         }
@@ -144,8 +157,10 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             }
         };
         auto process = [&](long long n, float (&xr)[KC]) {
-            const int st = (int)(n & 1);
-            mbar_wait(&empty_bar[st], (unsigned)(((n >> 1) & 1) ^ 1));
+            const int st = (int)(n % nst);
+            if (t_in == 0) TC_STAMP(grp_l, (int)(n >> 1), 0);
+            mbar_wait(&empty_bar[st], (unsigned)(((n / nst) & 1) ^ 1));
+            if (t_in == 0) TC_STAMP(grp_l, (int)(n >> 1), 1);
             if (STREAM_B && t_in == 0) {  // this chunk's rows of the split analysis matrix -> stage st
                 const int h = (int)(n % n_chunks);
                 const unsigned bytes = (unsigned)(bchunk_floats * sizeof(float));
@@ -168,6 +183,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor core reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[st]);
+            if (t_in == 0) TC_STAMP(grp_l, (int)(n >> 1), 2);
         };
         float xa[KC], xb[KC];
         long long n = grp_l;  // this group's chunks: grp_l, grp_l + 2, ...
@@ -190,12 +206,15 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             long long n = 0;
             for (long long it = 0; it < my_tiles; ++it) {
                 const int acc = (int)(it & 1);
+                TC_STAMP(2, (int)it, 0);
                 mbar_wait(&tempty_bar[acc], (unsigned)(((it >> 1) & 1) ^ 1));
+                TC_STAMP(2, (int)it, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem + acc * acc_cols;
                 for (int h = 0; h < n_chunks; ++h, ++n) {
-                    const int st = (int)(n & 1);
-                    mbar_wait(&full_bar[st], (unsigned)((n >> 1) & 1));
+                    const int st = (int)(n % nst);
+                    mbar_wait(&full_bar[st], (unsigned)((n / nst) & 1));
+                    TC_STAMP(2, (int)it, 2 + h);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     // descriptors differ only in the 14-bit start-address field: build them once per
                     // chunk and step the field by a constant (no carry: shared memory is < 256 KB)
@@ -221,6 +240,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                     umma_commit(&empty_bar[st]);  // the stage is free once these MMAs have read it
                 }
                 umma_commit(&tfull_bar[acc]);
+                TC_STAMP(2, (int)it, 6);
             }
         }
     } else {
@@ -233,7 +253,9 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             const long long s = row_ok ? g / B : 0;
             const int t = row_ok ? (int)(g % B) : 0;
             const int acc = (int)(it & 1);
+            if (q == 0 && lane == 0) TC_STAMP(3, (int)it, 0);
             mbar_wait(&tfull_bar[acc], (unsigned)((it >> 1) & 1));
+            if (q == 0 && lane == 0) TC_STAMP(3, (int)it, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float *zp = zcur + ((size_t)s * J) * B + t;
             for (int cb = 0; cb < Npad; cb += 32) {
@@ -250,6 +272,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (q == 0 && lane == 0) TC_STAMP(3, (int)it, 2);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

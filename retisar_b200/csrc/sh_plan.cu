@@ -31,7 +31,7 @@ struct rtb_sh_plan {
     bool mma_enabled = false;
     int mma_TW = 0, mma_jchunks = 0, mma_smem = 0, mma_grid = 0, mma_stages = 2;
     float *d_mma_r = nullptr;     // [n_jchunks][hi, lo][32 rows][32 channels]
-    int tc_Kpad = 0, tc_Npad = 0, tc_KC = 0, tc_smem = 0, tc_cols = 0, tc_grid = 0;
+    int tc_Kpad = 0, tc_Npad = 0, tc_KC = 0, tc_smem = 0, tc_cols = 0, tc_grid = 0, tc_nst = 2;
     float *d_tc_b = nullptr;      // [2][Kpad/4][Npad/8][8][4] analysis matrix split into TF32 hi / lo
     // device memory
     float *d_rmT = nullptr;       // [C][Jpad]
@@ -135,7 +135,7 @@ void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int c
     {                                                                                                \
         kernel_attrs_once(sh_analysis_tc_kernel<KCV, SB>, 224 * 1024);                                \
         sh_analysis_tc_kernel<KCV, SB><<<grid, RTB_TC_THREADS, p->tc_smem, st>>>(                    \
-            d_in, p->d_tc_b, zcur, count, p->C, p->J, p->B, p->tc_Kpad, p->tc_Npad, p->tc_cols);      \
+            d_in, p->d_tc_b, zcur, count, p->C, p->J, p->B, p->tc_Kpad, p->tc_Npad, p->tc_cols, p->tc_nst); \
     }
 #define RTB_TC_LAUNCH(KCV)                                                                           \
     case KCV:                                                                                        \
@@ -587,21 +587,35 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
         // split analysis matrix fits next to the two operand stages it stays resident, otherwise its
         // K-chunks are streamed through the stages (largest KC that fits).
         const int Npad = (J + 15) / 16 * 16;
-        int n_kchunks = std::max(2, (C + RTB_TC_MAX_KC - 1) / RTB_TC_MAX_KC);
-        int KC = ((C + n_kchunks - 1) / n_kchunks + 7) / 8 * 8;
-        int Kpad = KC * n_kchunks;
-        size_t tc_smem = sizeof(float) * ((size_t)4 * KC * RTB_TC_M + 2 * (size_t)Kpad * Npad);
+        // Search (operand stages nst, chunk width KC): the widest chunk that fits; resident B if it
+        // fits, else B streamed per stage.  Ring depth: 2 stages unless RTB_TC_NST asks for 3 or 4
+        // (measured on c5 / c4: 502.6 / 59.5 us with 2 stages, 503.1 / 61.3 us with 4).
+        int KC = 0, Kpad = 0, nst = 2;
+        size_t tc_smem = 0;
         bool stream_b = false;
-        if (tc_smem > 216 * 1024) {
-            stream_b = true;
-            KC = 0;
-            for (int kc = RTB_TC_MAX_KC; kc >= 8; kc -= 8)
-                if (sizeof(float) * (size_t)kc * (4 * RTB_TC_M + 4 * Npad) <= 216 * 1024) { KC = kc; break; }
-            if (KC) {
-                n_kchunks = (C + KC - 1) / KC;
-                KC = ((C + n_kchunks - 1) / n_kchunks + 7) / 8 * 8;  // even out the chunks
-                Kpad = KC * n_kchunks;
-                tc_smem = sizeof(float) * (size_t)KC * (4 * RTB_TC_M + 4 * Npad);
+        const size_t tc_budget = 216 * 1024;
+        int want_nst = 0, want_kc = 0;
+        if (const char *e5 = getenv("RTB_TC_NST")) want_nst = atoi(e5);
+        if (want_nst < 2 || want_nst > RTB_TC_MAX_ST) want_nst = 2;
+        if (const char *e6 = getenv("RTB_TC_KC")) want_kc = atoi(e6);
+        for (int pass = 0; pass < 2 && !KC; ++pass) {  // pass 0: resident B, pass 1: streamed B
+            for (int ns = RTB_TC_MAX_ST; ns >= 2 && !KC; --ns) {
+                if (want_nst && ns != want_nst) continue;
+                for (int kc = RTB_TC_MAX_KC; kc >= 16; kc -= 8) {
+                    if (want_kc && kc != want_kc) continue;
+                    if (kc >= C + 8 && C > 8) continue;  // at most one padded group of 8
+                    const int nk = (C + kc - 1) / kc;
+                    if (nk < 2 && C > 32) continue;      // at least two chunks per tile (two loader groups)
+                    if (!want_kc) kc = std::min(kc, ((C + nk - 1) / nk + 7) / 8 * 8);  // even out the chunks
+                    const int kp = kc * nk;
+                    const size_t a_bytes = sizeof(float) * (size_t)ns * 2 * kc * RTB_TC_M;
+                    const size_t b_bytes = pass == 0 ? sizeof(float) * 2 * (size_t)kp * Npad
+                                                     : sizeof(float) * (size_t)ns * 2 * kc * Npad;
+                    if (a_bytes + b_bytes <= tc_budget) {
+                        KC = kc; Kpad = kp; nst = ns; tc_smem = a_bytes + b_bytes; stream_b = pass == 1;
+                        break;
+                    }
+                }
             }
         }
         if (want && KC > 0 && Npad <= 256 && tc_smem <= 216 * 1024) {
@@ -624,6 +638,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
             if (e2 != cudaSuccess) return fail(RTB_ERR_CUDA, "tensor-core table upload failed: %s", cudaGetErrorString(e2));
             p->tc_enabled = true;
             p->tc_stream_b = stream_b;
+            p->tc_nst = nst;
             p->tc_Kpad = Kpad; p->tc_Npad = Npad; p->tc_KC = KC; p->tc_smem = (int)tc_smem;
             p->tc_cols = Npad <= 32 ? 32 : (Npad <= 64 ? 64 : (Npad <= 128 ? 128 : 256));  // per accumulator
             p->tc_grid = n_sm;
@@ -997,6 +1012,11 @@ int rtb_sh_plan_query(rtb_sh_plan *p, int what, int64_t *value) {
     return RTB_OK;
 }
 
+#ifdef RTB_TRACE_TC
+int rtb_debug_tc_trace(long long *h_out, int n) {  // trace builds only (not part of the public ABI)
+    return cudaMemcpyFromSymbol(h_out, rtb::g_tc_trace, sizeof(long long) * n) == cudaSuccess ? RTB_OK : RTB_ERR_CUDA;
+}
+#endif
 #ifdef RTB_TRACE
 int rtb_debug_eo_trace(long long *h_out, int n) {  // trace builds only (not part of the public ABI)
     return cudaMemcpyFromSymbol(h_out, rtb::g_eo_trace, sizeof(long long) * n) == cudaSuccess ? RTB_OK : RTB_ERR_CUDA;
