@@ -1,36 +1,47 @@
-// K-A on the 5th-generation tensor cores (tcgen05, accumulator in TMEM) for wide arrays / high SH
-// orders, where the analysis GEMM  z[j][t] = sum_c Rm[j][c] x[c][t]  is FP32-pipe bound on SIMT
-// (order 8, 110 channels: 23 flop/B).  Included by sh_kernels.cuh.
+// K-A on the 5th-generation tensor cores (tcgen05, accumulator in TMEM): the analysis GEMM
+// z[j][t] = sum_c Rm[j][c] x[c][t]  for arrays of 32 channels and more.  Included by sh_kernels.cuh.
 //
 //   D[t][j] (TMEM, fp32)  =  A[t][c] (smem, K-major)  x  B[j][c]^T (smem, K-major)
-//   M = 128 samples of one stream, N = rows padded to 16, K = channels in chunks of KC, kind::tf32.
+//   M = 128 samples, N = rows padded to 16, K = channels in chunks of 32 (one operand stage), kind::tf32.
 //
 // Plain TF32 (10-bit mantissa) would break the 1e-5 parity bar, so both operands are split
 // a = a_hi + a_lo (hi = a rounded to TF32, lo = a - hi, exact in fp32) and three MMAs accumulate
 // hi*hi + lo*hi + hi*lo in the fp32 accumulator; measured max error 2e-6 relative
 // (tools/tc_probe.cu).  The analysis matrix is split and laid out on the host; the input tile is
-// split on the fly while it is scattered from coalesced global loads into the un-swizzled
-// core-matrix layout [c/4][t/8][t%8][c%4] (a thread's four channels form one 16-byte run, a warp
-// writes 512 contiguous bytes).  MN-major operands would avoid that transposition but produced
-// zeros with un-swizzled TF32 descriptors on this part (tools/tc_probe.cu, variant 0), so both
-// operands are K-major.
+// split on the fly while it is transposed from 16-byte global loads into the un-swizzled
+// core-matrix layout [c/4][t/8][t%8][c%4].  MN-major operands would avoid that transposition but
+// produced zeros with TF32 descriptors on this part (tools/tc_probe_mn.cu), so both operands are
+// K-major; the 128-byte-swizzled K-major layout issues at the same rate as the un-swizzled one
+// (tools/tc_rate.cu: a K = 8 TF32 MMA takes max(48, N/2) cycles, i.e. for N <= 96 it is bound by
+// the 4 KB A-operand fetch from shared memory).
 //
 // Warp-specialised, persistent (one CTA per SM, 13 warps):
-//   warps 0-3 / 4-7  two loader groups alternating over the K-chunks, each filling its own
-//                    operand stage: row reads (the group's next chunk is requested before the
-//                    current one is processed), TF32 split, scatter, fence.proxy.async
-//   warp 12          one thread issues the MMAs of a chunk and commits the stage back
-//   warps 8-11       epilogue: TMEM lane quarter -> registers -> analysis rows (coalesced 128 B)
-// A ring of 2-4 operand stages and two TMEM accumulators let the three roles overlap (with two
-// stages the loaders could only start on a stage once its MMAs had retired: a clock64 trace showed
-// the MMA issuer waiting ~3000 of the 7000 cycles per tile for them).
+//   warps 0-7   loaders: one group of warps per operand stage (4 stages: pairs), groups run out of
+//               phase -- 16-byte row loads, TF32 split, conflict-free transposed stores,
+//               fence.proxy.async, arrive on the stage's `full` mbarrier
+//   warp 12     MMA issuer: warp-uniform loop, one elected lane issues the MMAs of a stage and
+//               commits the stage back (`empty`) / the accumulator to the epilogue (`tfull`)
+//   warps 8-11  epilogue: TMEM lane quarter -> registers -> analysis rows (coalesced 128 B)
+// Two TMEM accumulators let the epilogue of a tile overlap the MMAs of the next.
+//
+// What the clock64 traces (tools/tc_trace.py) and the SASS showed on the way here (c5, 8 192 streams:
+// 503 -> 353 us; c2, 10 240 streams: 239 -> 106 us, the mma.sync kernel takes 132 us):
+//   * every LDG of a loader loop sits on ONE scoreboard, so a register prefetch ring never overlapped
+//     anything: the first use of the oldest buffer waited for the youngest load (one memory round trip
+//     per stage, whatever the ring depth, load width, cache hint or tile shape).  The loaders now
+//     run a plain load / wait / split / store cycle and overlap ACROSS warp groups instead.
+//   * fence.proxy.async is lowered to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC; the MEMBAR waits for the
+//     thread's loads in flight (second reason the prefetch ring was useless).
+//   * with `if (lane == 0)` around the issue loop every tcgen05.mma was wrapped in an elect / R2UR
+//     broadcast loop (~110 cycles per MMA against the MMA's own 49): the issue loop must be
+//     warp-uniform with the warp index taken from a shuffle.
 //
 // Tile rows are the flattened (stream, sample) index, so blocks shorter than 128 samples put 2 or 4
 // streams into one M = 128 tile (low-latency 64-sample blocks, config c4).  When the split analysis
 // matrix does not fit in shared memory next to the operand stages (434 channels x 169 rows: 630 KB)
-// its K-chunks are streamed with cp.async.bulk into the same two stages as the input (STREAM_B):
-// the chunk of a stage is requested by the loader group that fills the stage, completion is counted
-// on the stage's `full` mbarrier together with the loader warps' arrivals.
+// its K-chunks are streamed with cp.async.bulk into the stages next to the input (STREAM_B): the
+// chunk of a stage is requested by the loader group that fills the stage, completion is counted on
+// the stage's `full` mbarrier together with the loader warps' arrivals.
 #pragma once
 
 namespace rtb {
@@ -60,6 +71,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
         : "r"(addr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(smem_u32(bar)) : "memory");
@@ -72,7 +88,8 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
         ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// -DRTB_TRACE_TC: CTA 0 logs clock64 stamps per role and tile (tools/tc_trace.py)
+// -DRTB_TRACE_TC: CTA 0 logs clock64 stamps per role (tools/tc_trace.py): role 0 = loader warp 0
+// (indexed by chunk), role 2 = MMA issuer, role 3 = epilogue warp 8 (indexed by tile)
 #ifdef RTB_TRACE_TC
 __device__ long long g_tc_trace[4096];
 #define TC_STAMP(role, it, k) do { if (blockIdx.x == 0 && (it) < 100) g_tc_trace[(role) * 1000 + (it) * 8 + (k)] = clock64(); } while (0)
@@ -81,33 +98,61 @@ __device__ long long g_tc_trace[4096];
 #endif
 
 #define RTB_TC_M 128
-#define RTB_TC_MAX_KC 64   // channels per pipeline chunk (register staging of the loaders)
+#define RTB_TC_KC 32       // channels per pipeline chunk (operand stage): 16 per warp of a loader pair
 #define RTB_TC_THREADS 416
-#define RTB_TC_MAX_ST 4     // operand stages (ring): the loaders run up to nst - 1 chunks ahead of the MMAs
+#define RTB_TC_MAX_ST 4    // operand stages (ring)
+// Where the generic-proxy -> async-proxy fence between the loaders' st.shared and the tensor core's
+// operand reads sits.  nvcc lowers fence.proxy.async to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the
+// MEMBAR waits for everything the executing thread has in flight:
+//   1 (default) in the loader warps after their stores: their loads have all been consumed by then
+//     (no register prefetch, see the loader comment), so only the stores drain;
+//   0 in the MMA-issuing thread after it has acquired the stage through the `full` mbarrier (also on
+//     the causality path between the stores and the reads): measured slower, the MEMBAR drains the
+//     MMAs of the previous stage before the next ones are issued (112 instead of 49 cycles per MMA).
+#ifndef RTB_TC_FENCE_WRITER
+#define RTB_TC_FENCE_WRITER 1
+#endif
 
-template <int KC, bool STREAM_B>
+// 16 bytes of one channel row (4 consecutive samples), zero when the predicate is off (the
+// predicate is folded into the address).
+__device__ float4 g_tc_zero4;  // zero-initialised
+__device__ __forceinline__ float4 ldg_nc_v4_pred(const float *p, bool pred) {
+    return __ldg(reinterpret_cast<const float4 *>(pred ? p : reinterpret_cast<const float *>(&g_tc_zero4)));
+}
+
+template <bool STREAM_B>
 __global__ void __launch_bounds__(RTB_TC_THREADS, 1)
 sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                       const float *__restrict__ bsrc,  // [2][Kpad/4][Npad/8][8][4]: hi then lo
                       float *__restrict__ zcur,        // [S][J][B]
                       int S, int C, int J, int B, int Kpad, int Npad, int acc_cols, int nst) {
+    constexpr int KC = RTB_TC_KC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *a_stage = reinterpret_cast<float *>(smem_raw);   // [nst stages][hi, lo][KC/4][16][8][4]
-    // resident: [Kpad/4][Npad/8][8][4] hi, then lo; streamed: [2 stages][hi, lo][KC/4][Npad/8][8][4]
+    // resident: [Kres/4][Npad/8][8][4] hi, then lo (Kres = C rounded up to 8: the k-steps that are
+    // issued); streamed: [nst stages][hi, lo][KC/4][Npad/8][8][4]
+    const int Kres = (C + 7) / 8 * 8;
     float *b_hi = a_stage + (size_t)nst * 2 * KC * RTB_TC_M;
-    float *b_lo = b_hi + (size_t)Kpad * Npad;
+    float *b_lo = b_hi + (size_t)Kres * Npad;
     const size_t bchunk_floats = (size_t)KC * Npad;         // one K-chunk of hi (or lo)
     __shared__ __align__(8) uint64_t full_bar[RTB_TC_MAX_ST], empty_bar[RTB_TC_MAX_ST], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: provably warp-uniform, so that the role branches are uniform and
+    // the MMA issuer's descriptors live in uniform registers (with `tid >> 5` and an `if (lane == 0)`
+    // around the issue loop ptxas wrapped every tcgen05.mma into an elect / R2UR broadcast loop:
+    // ~22 instructions and ~110 cycles per MMA, twice the MMA's own 49 cycles)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
     if (!STREAM_B)
-        for (int i = tid; i < Kpad * Npad / 2; i += RTB_TC_THREADS)  // hi and lo halves are contiguous
+        for (int i = tid; i < Kres * Npad / 4; i += RTB_TC_THREADS) {
             reinterpret_cast<float4 *>(b_hi)[i] = __ldg(reinterpret_cast<const float4 *>(bsrc) + i);
+            reinterpret_cast<float4 *>(b_lo)[i] = __ldg(reinterpret_cast<const float4 *>(bsrc + (size_t)Kpad * Npad) + i);
+        }
     if (tid == 0) {
         for (int i = 0; i < RTB_TC_MAX_ST; ++i) {
-            // one arrival per loader warp of the stage's group (+ the expect_tx arrival of the B chunk)
-            mbar_init(&full_bar[i], STREAM_B ? 5 : 4);
+            // one arrival per warp of the stage's loader group (+ the expect_tx arrival of the B chunk)
+            mbar_init(&full_bar[i], 8 / nst + (STREAM_B ? 1 : 0));
             mbar_init(&empty_bar[i], 1);   // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
@@ -126,43 +171,59 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    // tile = 128 consecutive rows of the flattened [S][B] sample index
+    // tile = 128 consecutive rows of the flattened [S][B] sample index.  (256-row tiles that take whole
+    // 1 KB channel rows at once, as two M = 128 halves with an accumulator each, were measured equal
+    // or slightly slower: c5 358.9 vs 352.7 us, c2 106.0 vs 107.4 us.)
     const long long n_rows = (long long)S * B;
     const long long n_tiles = (n_rows + RTB_TC_M - 1) / RTB_TC_M;
     const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int n_chunks = Kpad / KC;
-    const long long my_chunks = my_tiles * n_chunks;
+    const long long my_units = my_tiles * n_chunks;   // unit = (tile, chunk): one operand stage
     const size_t stage_floats = (size_t)2 * KC * RTB_TC_M;
+    const int log2B = 31 - __clz(B);  // block lengths are powers of two
 
     if (warp < 8) {
-        // ===== loaders: thread = sample t of the tile.  Group g = warp / 4 takes the chunks with
-        // n % 2 == g, i.e. always fills stage g.
-        const int t_in = tid & 127, grp_l = warp >> 2;
-        auto issue_loads = [&](long long n, float (&xr)[KC]) {
-            const long long tile = blockIdx.x + (n / n_chunks) * gridDim.x;
-            const int h = (int)(n % n_chunks);
-            const long long g = tile * RTB_TC_M + t_in;     // flattened (stream, sample) row
+        // ===== loaders.  A stage (32 channels x 128 rows) is filled by a group of warps (a PAIR with 16
+        // channels each when there are four stages); group p takes the units n = p, p + nst, ...  Lane l owns rows 4l .. 4l+3 of the stage (one
+        // 16-byte load per channel: a warp request covers the 512 contiguous bytes of a channel row).
+        // ptxas puts every LDG of this loop on one scoreboard, so a warp cannot overlap its own
+        // loads with its own stores (the first use of any loaded register waits for all loads in
+        // flight; measured: a register prefetch ring ran at one memory round trip per stage whatever
+        // its depth).  Each warp therefore runs a plain issue-16-loads / wait / split / store cycle
+        // and the four pairs run out of phase: while one pair splits and stores, the other three
+        // have their 16 KB in flight.
+        // The 4 x 4 register block of a channel quad is transposed on the way to shared memory:
+        // step s stores row 4l + (s + rot) % 4 with rot = (l / 2) % 4, so that the eight lanes of a
+        // 128-bit store phase hit eight different 16-byte bank groups (rows 4l + s for all lanes
+        // would be a 4-way conflict).
+        // Loader groups = stages (2 or 4): group g fills stage g only, so it sees every phase of the
+        // stage's `empty` barrier (a group that skipped phases would misread the parity).  With 2
+        // stages a group is 4 warps of 8 channels, with 4 stages a pair of 16 channels.
+        const int wpg = 8 / nst, qpw = 8 / wpg;            // warps per group, channel quads per warp
+        const int pair = warp / wpg, sub = warp - pair * wpg;
+        const int rot = (lane >> 1) & 3;
+        const bool r1 = rot & 1, r2 = rot & 2;
+        for (long long n = pair; n < my_units; n += nst) {
+            const long long it = n / n_chunks;
+            const int h = (int)(n - it * n_chunks);
+            const long long g = ((long long)blockIdx.x + it * gridDim.x) * RTB_TC_M + 4 * lane;
             const bool row_ok = g < n_rows;
-            const long long s = row_ok ? g / B : 0;
-            const int t = row_ok ? (int)(g % B) : 0;
-            const float *xp = x + ((size_t)s * C + (size_t)h * KC) * B + t;
-            const int cmax = row_ok ? C - h * KC : 0;
+            const long long s = row_ok ? (g >> log2B) : 0;
+            const int t = row_ok ? (int)(g & (B - 1)) : 0;
+            const int c0 = h * KC + 4 * qpw * sub;
+            const float *xp = x + ((size_t)s * C + c0) * B + t;
+            // channels beyond C or beyond this warp's share (and rows beyond S*B) read as zero
+            const int cmax = row_ok ? min(C - c0, 4 * qpw) : 0;
+            float4 v[4][4];
 #pragma unroll
-            for (int i = 0; i < KC; ++i) {  // predicated: channels beyond C (and rows beyond S*B) read as zero
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\tmov.f32 %0, 0f00000000;\n\t"
-                    "@p ld.global.nc.f32 %0, [%1];\n\t}"
-                    : "=f"(xr[i]) : "l"(xp), "r"(i), "r"(cmax));
-                xp += B;
-            }
-        };
-        auto process = [&](long long n, float (&xr)[KC]) {
-            const int st = (int)(n % nst);
-            if (t_in == 0) TC_STAMP(grp_l, (int)(n >> 1), 0);
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[q][i] = ldg_nc_v4_pred(xp + (size_t)(4 * q + i) * B, 4 * q + i < cmax);
+            const int st = pair;
+            if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 0);
             mbar_wait(&empty_bar[st], (unsigned)(((n / nst) & 1) ^ 1));
-            if (t_in == 0) TC_STAMP(grp_l, (int)(n >> 1), 1);
-            if (STREAM_B && t_in == 0) {  // this chunk's rows of the split analysis matrix -> stage st
-                const int h = (int)(n % n_chunks);
+            if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 1);
+            if (STREAM_B && sub == 0 && lane == 0) {  // this chunk's rows of the split analysis matrix -> stage st
                 const unsigned bytes = (unsigned)(bchunk_floats * sizeof(float));
                 float *bst = b_hi + (size_t)st * 2 * bchunk_floats;
                 mbar_expect_tx(&full_bar[st], 2 * bytes);
@@ -170,77 +231,94 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                 bulk_copy_g2s(bst + bchunk_floats, bsrc + (size_t)Kpad * Npad + (size_t)h * bchunk_floats, bytes,
                               &full_bar[st]);
             }
-            float *ahi = a_stage + st * stage_floats, *alo = ahi + (size_t)KC * RTB_TC_M;
 #pragma unroll
-            for (int u = 0; u < KC / 4; ++u) {
-                float hi[4], lo[4];
+            for (int q = 0; q < 4; ++q) {
+                if (q < qpw && c0 + 4 * q < Kres) {  // quads beyond the issued k-steps are never read
+                    float *ahi = a_stage + st * stage_floats + (qpw * sub + q) * (4 * RTB_TC_M);
+                    float *alo = ahi + (size_t)KC * RTB_TC_M;
+                    float w[4][4];  // w[i][sidx] = component (sidx + rot) % 4 of channel i
 #pragma unroll
-                for (int i = 0; i < 4; ++i) split_tf32(xr[4 * u + i], hi[i], lo[i]);
-                const size_t off = (((size_t)u * (RTB_TC_M / 8) + (t_in >> 3)) * 8 + (t_in & 7)) * 4;
-                *reinterpret_cast<float4 *>(ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4 *>(alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    for (int i = 0; i < 4; ++i) {
+                        const float a1 = r1 ? v[q][i].y : v[q][i].x, b1 = r1 ? v[q][i].z : v[q][i].y;
+                        const float c1 = r1 ? v[q][i].w : v[q][i].z, d1 = r1 ? v[q][i].x : v[q][i].w;
+                        w[i][0] = r2 ? c1 : a1; w[i][1] = r2 ? d1 : b1;
+                        w[i][2] = r2 ? a1 : c1; w[i][3] = r2 ? b1 : d1;
+                    }
+#pragma unroll
+                    for (int sidx = 0; sidx < 4; ++sidx) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_tf32(w[i][sidx], hi[i], lo[i]);
+                        const int off = (4 * lane + ((sidx + rot) & 3)) * 4;
+                        *reinterpret_cast<float4 *>(ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4 *>(alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
             }
+#if RTB_TC_FENCE_WRITER
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor core reads
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[st]);
-            if (t_in == 0) TC_STAMP(grp_l, (int)(n >> 1), 2);
-        };
-        float xa[KC], xb[KC];
-        long long n = grp_l;  // this group's chunks: grp_l, grp_l + 2, ...
-        if (n < my_chunks) issue_loads(n, xa);
-        for (; n < my_chunks; n += 4) {
-            if (n + 2 < my_chunks) issue_loads(n + 2, xb);
-            process(n, xa);
-            if (n + 2 < my_chunks) {
-                if (n + 4 < my_chunks) issue_loads(n + 4, xa);
-                process(n + 2, xb);
-            }
+            if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 2);
         }
     } else if (warp == 12) {
-        // ===== MMA issuer (one thread): hi*hi + lo*hi + hi*lo per chunk, accumulating in TMEM
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues
+        // hi*hi + lo*hi + hi*lo per stage, accumulating in TMEM
+        {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Npad >> 3) << 17) |
                                    ((uint32_t)(RTB_TC_M >> 4) << 24);  // D f32, A/B tf32, K-major, N, M
             const uint32_t lbo_a = (RTB_TC_M / 8) * 128, lbo_b = (Npad / 8) * 128, sbo = 128;
             const uint64_t step_a = (2 * lbo_a) >> 4, step_b = (2 * lbo_b) >> 4;
-            long long n = 0;
+            int st = 0;
+            unsigned ph = 0;
             for (long long it = 0; it < my_tiles; ++it) {
                 const int acc = (int)(it & 1);
-                TC_STAMP(2, (int)it, 0);
+                if (lane == 0) TC_STAMP(2, (int)it, 0);
                 mbar_wait(&tempty_bar[acc], (unsigned)(((it >> 1) & 1) ^ 1));
-                TC_STAMP(2, (int)it, 1);
+                if (lane == 0) TC_STAMP(2, (int)it, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem + acc * acc_cols;
-                for (int h = 0; h < n_chunks; ++h, ++n) {
-                    const int st = (int)(n % nst);
-                    mbar_wait(&full_bar[st], (unsigned)((n / nst) & 1));
-                    TC_STAMP(2, (int)it, 2 + h);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    // descriptors differ only in the 14-bit start-address field: build them once per
-                    // chunk and step the field by a constant (no carry: shared memory is < 256 KB)
-                    const uint32_t ahi = smem_u32(a_stage + st * stage_floats);
-                    const uint32_t alo = ahi + (uint32_t)(KC * RTB_TC_M * sizeof(float));
-                    const uint64_t da_hi = umma_desc(ahi, lbo_a, sbo), da_lo = umma_desc(alo, lbo_a, sbo);
-                    // this chunk's k-range of B: inside the resident matrix, or the stage's own copy
-                    const uint32_t bhi_a = STREAM_B ? smem_u32(b_hi + (size_t)st * 2 * bchunk_floats)
-                                                    : smem_u32(b_hi) + (uint32_t)h * (KC / 4) * lbo_b;
-                    const uint32_t blo_a = STREAM_B ? bhi_a + (uint32_t)(bchunk_floats * sizeof(float))
-                                                    : smem_u32(b_lo) + (uint32_t)h * (KC / 4) * lbo_b;
-                    const uint64_t db_hi = umma_desc(bhi_a, lbo_b, sbo);
-                    const uint64_t db_lo = umma_desc(blo_a, lbo_b, sbo);
+                for (int h = 0; h < n_chunks; ++h) {
+                    const int ksteps = min(KC / 8, (C - h * KC + 7) / 8);  // the last chunk may be short
+                    {
+                        const uint32_t d_tmem = tmem + acc * acc_cols;
+                        mbar_wait(&full_bar[st], ph);
+                        if (h == 0 && lane == 0) TC_STAMP(2, (int)it, 2);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#if !RTB_TC_FENCE_WRITER
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // loaders' stores -> tensor core reads
+#endif
+                        // descriptors differ only in the 14-bit start-address field: build them once per
+                        // stage and step the field by a constant (no carry: shared memory is < 256 KB)
+                        const uint32_t ahi = smem_u32(a_stage + st * stage_floats);
+                        const uint32_t alo = ahi + (uint32_t)(KC * RTB_TC_M * sizeof(float));
+                        const uint64_t da_hi = umma_desc(ahi, lbo_a, sbo), da_lo = umma_desc(alo, lbo_a, sbo);
+                        // this chunk's k-range of B: inside the resident matrix, or the stage's own copy
+                        const uint32_t bhi_a = STREAM_B ? smem_u32(b_hi + (size_t)st * 2 * bchunk_floats)
+                                                        : smem_u32(b_hi) + (uint32_t)h * (KC / 4) * lbo_b;
+                        const uint32_t blo_a = STREAM_B ? bhi_a + (uint32_t)(bchunk_floats * sizeof(float))
+                                                        : smem_u32(b_lo) + (uint32_t)h * (KC / 4) * lbo_b;
+                        const uint64_t db_hi = umma_desc(bhi_a, lbo_b, sbo);
+                        const uint64_t db_lo = umma_desc(blo_a, lbo_b, sbo);
+                        if (elect_one_sync()) {
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint64_t da0 = pass == 1 ? da_lo : da_hi;
-                        const uint64_t db0 = pass == 2 ? db_lo : db_hi;
+                            for (int pass = 0; pass < 3; ++pass) {
+                                const uint64_t da0 = pass == 1 ? da_lo : da_hi;
+                                const uint64_t db0 = pass == 2 ? db_lo : db_hi;
 #pragma unroll
-                        for (int ks = 0; ks < KC / 8; ++ks)
-                            umma_tf32(d_tmem, da0 + ks * step_a, db0 + ks * step_b, idesc,
-                                      (h | pass | ks) ? 1u : 0u);
+                                for (int ks = 0; ks < KC / 8; ++ks)
+                                    if (ks < ksteps)
+                                        umma_tf32(d_tmem, da0 + ks * step_a, db0 + ks * step_b, idesc,
+                                                  (h | pass | ks) ? 1u : 0u);
+                            }
+                            umma_commit(&empty_bar[st]);  // the stage is free once these MMAs have read it
+                            if (h == n_chunks - 1) umma_commit(&tfull_bar[acc]);
+                        }
+                        __syncwarp();
+                        if (++st == nst) { st = 0; ph ^= 1; }
                     }
-                    umma_commit(&empty_bar[st]);  // the stage is free once these MMAs have read it
                 }
-                umma_commit(&tfull_bar[acc]);
-                TC_STAMP(2, (int)it, 6);
+                if (lane == 0) TC_STAMP(2, (int)it, 6);
             }
         }
     } else {
@@ -248,25 +326,27 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
         const int q = warp & 3;
         for (long long it = 0; it < my_tiles; ++it) {
             const long long tile = blockIdx.x + it * gridDim.x;
-            const long long g = tile * RTB_TC_M + q * 32 + lane;  // this lane's (stream, sample) row
-            const bool row_ok = g < n_rows;
-            const long long s = row_ok ? g / B : 0;
-            const int t = row_ok ? (int)(g % B) : 0;
             const int acc = (int)(it & 1);
             if (q == 0 && lane == 0) TC_STAMP(3, (int)it, 0);
             mbar_wait(&tfull_bar[acc], (unsigned)((it >> 1) & 1));
             if (q == 0 && lane == 0) TC_STAMP(3, (int)it, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float *zp = zcur + ((size_t)s * J) * B + t;
-            for (int cb = 0; cb < Npad; cb += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * acc_cols + cb, v);
-                const int nrow = row_ok ? J - cb : 0;  // rows of this chunk that exist
+            {
+                const long long g = tile * RTB_TC_M + q * 32 + lane;  // this lane's (stream, sample) row
+                const bool row_ok = g < n_rows;
+                const long long s = row_ok ? (g >> log2B) : 0;
+                const int t = row_ok ? (int)(g & (B - 1)) : 0;
+                float *zp = zcur + ((size_t)s * J) * B + t;
+                for (int cb = 0; cb < Npad; cb += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * acc_cols + cb, v);
+                    const int nrow = row_ok ? J - cb : 0;  // rows of this chunk that exist
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {  // predicated stores, pointer stepped by one row
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p st.global.b32 [%0], %1;\n\t}"
-                                 ::"l"(zp), "r"(v[j]), "r"(j), "r"(nrow) : "memory");
-                    zp += B;
+                    for (int j = 0; j < 32; ++j) {  // predicated stores, pointer stepped by one row
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p st.global.b32 [%0], %1;\n\t}"
+                                     ::"l"(zp), "r"(v[j]), "r"(j), "r"(nrow) : "memory");
+                        zp += B;
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

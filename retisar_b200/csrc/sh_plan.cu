@@ -131,21 +131,13 @@ void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int c
     if (p->tc_enabled) {
         const long long tiles = ((long long)count * p->B + RTB_TC_M - 1) / RTB_TC_M;
         const int grid = (int)std::min<long long>(tiles, (long long)p->tc_grid);
-#define RTB_TC_LAUNCH_T(KCV, SB)                                                                      \
+#define RTB_TC_LAUNCH_T(SB)                                                                          \
     {                                                                                                \
-        kernel_attrs_once(sh_analysis_tc_kernel<KCV, SB>, 224 * 1024);                                \
-        sh_analysis_tc_kernel<KCV, SB><<<grid, RTB_TC_THREADS, p->tc_smem, st>>>(                    \
+        kernel_attrs_once(sh_analysis_tc_kernel<SB>, 224 * 1024);                                    \
+        sh_analysis_tc_kernel<SB><<<grid, RTB_TC_THREADS, p->tc_smem, st>>>(                         \
             d_in, p->d_tc_b, zcur, count, p->C, p->J, p->B, p->tc_Kpad, p->tc_Npad, p->tc_cols, p->tc_nst); \
     }
-#define RTB_TC_LAUNCH(KCV)                                                                           \
-    case KCV:                                                                                        \
-        if (p->tc_stream_b) RTB_TC_LAUNCH_T(KCV, true) else RTB_TC_LAUNCH_T(KCV, false)              \
-        break;
-        switch (p->tc_KC) {
-            RTB_TC_LAUNCH(8) RTB_TC_LAUNCH(16) RTB_TC_LAUNCH(24) RTB_TC_LAUNCH(32)
-            RTB_TC_LAUNCH(40) RTB_TC_LAUNCH(48) RTB_TC_LAUNCH(56) RTB_TC_LAUNCH(64)
-        }
-#undef RTB_TC_LAUNCH
+        if (p->tc_stream_b) RTB_TC_LAUNCH_T(true) else RTB_TC_LAUNCH_T(false)
 #undef RTB_TC_LAUNCH_T
         return;
     }
@@ -582,43 +574,33 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
         // tensor-core variant: wide arrays (FP32-bound on SIMT), whole analysis matrix resident in smem
         p->tc_enabled = false;
         const char *env = getenv("RTB_ANALYSIS_TC");
-        const bool want = env ? (env[0] != '0') : (C >= 64);
-        // K is cut into pipeline chunks of KC channels (multiple of 8, at most RTB_TC_MAX_KC).  If the
-        // split analysis matrix fits next to the two operand stages it stays resident, otherwise its
-        // K-chunks are streamed through the stages (largest KC that fits).
+        const bool want = env ? (env[0] != '0') : (C >= 32);
+        // K is cut into pipeline chunks of RTB_TC_KC = 32 channels (one channel quad per loader warp;
+        // the last chunk issues only the k-steps that hold channels).  If the split analysis matrix
+        // fits next to two operand stages it stays resident, otherwise its K-chunks are streamed
+        // through the stages.  The operand ring takes the stages that fit (2 - 4, RTB_TC_NST caps it).
         const int Npad = (J + 15) / 16 * 16;
-        // Search (operand stages nst, chunk width KC): the widest chunk that fits; resident B if it
-        // fits, else B streamed per stage.  Ring depth: 2 stages unless RTB_TC_NST asks for 3 or 4
-        // (measured on c5 / c4: 502.6 / 59.5 us with 2 stages, 503.1 / 61.3 us with 4).
-        int KC = 0, Kpad = 0, nst = 2;
+        const int KC = RTB_TC_KC, Kpad = (C + KC - 1) / KC * KC, Kres = (C + 7) / 8 * 8;
+        int nst = 0;
         size_t tc_smem = 0;
         bool stream_b = false;
         const size_t tc_budget = 216 * 1024;
-        int want_nst = 0, want_kc = 0;
-        if (const char *e5 = getenv("RTB_TC_NST")) want_nst = atoi(e5);
-        if (want_nst < 2 || want_nst > RTB_TC_MAX_ST) want_nst = 2;
-        if (const char *e6 = getenv("RTB_TC_KC")) want_kc = atoi(e6);
-        for (int pass = 0; pass < 2 && !KC; ++pass) {  // pass 0: resident B, pass 1: streamed B
-            for (int ns = RTB_TC_MAX_ST; ns >= 2 && !KC; --ns) {
-                if (want_nst && ns != want_nst) continue;
-                for (int kc = RTB_TC_MAX_KC; kc >= 16; kc -= 8) {
-                    if (want_kc && kc != want_kc) continue;
-                    if (kc >= C + 8 && C > 8) continue;  // at most one padded group of 8
-                    const int nk = (C + kc - 1) / kc;
-                    if (nk < 2 && C > 32) continue;      // at least two chunks per tile (two loader groups)
-                    if (!want_kc) kc = std::min(kc, ((C + nk - 1) / nk + 7) / 8 * 8);  // even out the chunks
-                    const int kp = kc * nk;
-                    const size_t a_bytes = sizeof(float) * (size_t)ns * 2 * kc * RTB_TC_M;
-                    const size_t b_bytes = pass == 0 ? sizeof(float) * 2 * (size_t)kp * Npad
-                                                     : sizeof(float) * (size_t)ns * 2 * kc * Npad;
-                    if (a_bytes + b_bytes <= tc_budget) {
-                        KC = kc; Kpad = kp; nst = ns; tc_smem = a_bytes + b_bytes; stream_b = pass == 1;
-                        break;
-                    }
-                }
+        int max_nst = RTB_TC_MAX_ST;
+        if (const char *e5 = getenv("RTB_TC_NST")) max_nst = std::max(2, std::min(RTB_TC_MAX_ST, atoi(e5)));
+        {
+            const size_t a_stage = sizeof(float) * 2 * KC * RTB_TC_M;       // hi + lo
+            const size_t b_res = sizeof(float) * 2 * (size_t)Kres * Npad;   // hi + lo
+            const size_t b_stage = sizeof(float) * 2 * (size_t)KC * Npad;
+            if (b_res + 2 * a_stage <= tc_budget) {
+                nst = (int)std::min<size_t>(max_nst, (tc_budget - b_res) / a_stage) >= 4 ? 4 : 2;  // one loader group per stage
+                tc_smem = b_res + nst * a_stage;
+            } else if (2 * (a_stage + b_stage) <= tc_budget) {
+                stream_b = true;
+                nst = (int)std::min<size_t>(max_nst, tc_budget / (a_stage + b_stage)) >= 4 ? 4 : 2;
+                tc_smem = nst * (a_stage + b_stage);
             }
         }
-        if (want && KC > 0 && Npad <= 256 && tc_smem <= 216 * 1024) {
+        if (want && nst >= 2 && Npad <= 256 && B >= 32 && (B & (B - 1)) == 0) {
             std::vector<float> bsrc(2 * (size_t)Kpad * Npad, 0.f);
             for (int j = 0; j < J; ++j)
                 for (int c = 0; c < C; ++c) {

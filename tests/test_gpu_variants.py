@@ -1,5 +1,5 @@
-"""The kernel variants that are off by default (measured without gain, kept as documented
-experiments) stay parity-green: each is switched on through its environment variable before the
+"""The kernel variants that are off by default (measured without gain or superseded, kept as
+documented experiments / fallbacks) stay parity-green: each is switched on through its environment variable before the
 plan is created and run against a reference golden with control events."""
 import numpy as np
 import pytest
@@ -17,8 +17,9 @@ TOL = 1e-5
     {"RTB_RENDER_MG": "0"},            # term-wise render kernel only
     {"RTB_PDL": "1"},                  # programmatic dependent launch
     {"RTB_OVERLAP_CHUNKS": "3"},       # analysis | render on two streams
-    {"RTB_ANALYSIS_MMA": "0"},         # FFMA2 SIMT analysis GEMM
-    {"RTB_ANALYSIS_MMA": "0", "RTB_ANALYSIS_TC": "1"},  # tcgen05 analysis for the narrow array
+    {"RTB_ANALYSIS_TC": "0"},          # mma.sync (warp-level tensor core) analysis GEMM
+    {"RTB_ANALYSIS_TC": "0", "RTB_ANALYSIS_MMA": "0"},  # FFMA2 SIMT analysis GEMM
+    {"RTB_TC_NST": "2"},               # tcgen05 analysis with two operand stages (4-warp loader groups)
 ])
 def test_variant_matches_reference_golden(env, monkeypatch):
     for k, v in env.items():

@@ -28,19 +28,12 @@ fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert fn(buf.ctypes.data, 4096) == 0
 t0 = buf[2000]
 def rel(v): return int(v - t0)
-print("tile | loader g0: wait_empty done-wait arrive | loader g1 ... | mma: start gotacc full0 full1 committed | epi: start gotfull released")
-for it in range(20, 26):
-    l0 = [rel(buf[0 * 1000 + it * 8 + k]) for k in range(3)]
-    l1 = [rel(buf[1 * 1000 + it * 8 + k]) for k in range(3)]
-    m = [rel(buf[2 * 1000 + it * 8 + k]) for k in (0, 1, 2, 3, 6)]
-    e = [rel(buf[3 * 1000 + it * 8 + k]) for k in range(3)]
-    print(it, l0, l1, m, e)
 T = np.arange(20, 60)
-def st(role, k): return buf[role * 1000 + T * 8 + k].astype(np.float64)
+def st(role, k, idx=T): return buf[role * 1000 + idx * 8 + k].astype(np.float64)
 print("cycles per tile (mma start to start):", np.diff(st(2, 0)).mean())
-for g in (0, 1):
-    print(f"loader g{g}: wait_empty {np.mean(st(g,1)-st(g,0)):.0f}  split+scatter {np.mean(st(g,2)-st(g,1)):.0f}  "
-          f"arrive->next wait_empty (load issue + data wait of the other buffer) {np.mean(st(g,0)[1:]-st(g,2)[:-1]):.0f}")
-print(f"mma: wait acc {np.mean(st(2,1)-st(2,0)):.0f}  wait full0 {np.mean(st(2,2)-st(2,1)):.0f}  "
-      f"chunk0 issue + wait full1 {np.mean(st(2,3)-st(2,2)):.0f}  chunk1 issue {np.mean(st(2,6)-st(2,3)):.0f}")
-print(f"epilogue: wait tfull {np.mean(st(3,1)-st(3,0)):.0f}  drain {np.mean(st(3,2)-st(3,1)):.0f}")
+N = np.arange(40, 99)
+print(f"loader warp 0 per chunk: wait_empty {np.mean(st(0,1,N)-st(0,0,N)):.0f}  data wait + split + scatter {np.mean(st(0,2,N)-st(0,1,N)):.0f}  "
+      f"load issue {np.mean(st(0,0,N)[1:]-st(0,2,N)[:-1]):.0f}  period {np.diff(st(0,0,N)).mean():.0f}")
+print(f"mma per tile: wait acc {np.mean(st(2,1)-st(2,0)):.0f}  wait first chunk {np.mean(st(2,2)-st(2,1)):.0f}  "
+      f"chunks issued {np.mean(st(2,6)-st(2,2)):.0f}")
+print(f"epilogue per tile: wait tfull {np.mean(st(3,1)-st(3,0)):.0f}  drain {np.mean(st(3,2)-st(3,1)):.0f}")
