@@ -78,7 +78,8 @@ int rtb_sh_plan_reset(rtb_sh_plan *plan);
 
 /* AdjustableShConvolver.filter_block (_convolver.py:1231-1316) for all S streams.
  *   d_in  [S][C][B] float32, d_yaw_deg [S] float32 (tracker AZIM in degrees, _tracker.py:73-81),
- *   d_out [S][E][B] float32.  Asynchronous on `cuda_stream` (a cudaStream_t, NULL = default). */
+ *   d_out [S][E][B] float32; d_in and d_out 16-byte aligned (RTB_ERR_INVALID otherwise).
+ *   Asynchronous on `cuda_stream` (a cudaStream_t, NULL = default). */
 int rtb_sh_process_block(rtb_sh_plan *plan, const float *d_in, const float *d_yaw_deg,
                          float *d_out, void *cuda_stream);
 /* Same with host buffers: H2D copy, render, D2H copy, synchronise (the JACK-callback shape of

@@ -875,6 +875,8 @@ void advance_block(rtb_sh_plan *p) {
 int rtb_sh_process_block(rtb_sh_plan *p, const float *d_in, const float *d_yaw_deg, float *d_out,
                          void *cuda_stream) {
     if (!p || !d_in || !d_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15)
+        return fail(RTB_ERR_INVALID, "device buffers must be 16-byte aligned (bulk copies, 16-byte loads and stores)");
     if (!p->tables_set)
         return fail(RTB_ERR_STATE, "blocks in spherical harmonics domain have not been calculated yet.");
     if (!d_yaw_deg && !p->passthrough) return fail(RTB_ERR_INVALID, "NULL yaw pointer");

@@ -120,6 +120,27 @@ def test_errors_match_reference(tables):
         plan.set_order(7)
 
 
+def test_misaligned_device_buffer_is_refused(tables):
+    """The kernels use bulk copies and 16-byte loads: a device pointer off a 16-byte boundary is
+    refused with the C ABI's invalid-argument status (ValueError), not faulted on."""
+    import torch
+
+    from retisar_b200 import workloads as wl
+
+    S = 2
+    conv = wl.make_renderer(tables, S)
+    C, B = tables["C"], tables["B"]
+    dev = torch.device("cuda", 0)
+    flat = torch.zeros(S * C * B + 4, device=dev)
+    yaw = torch.zeros(S, device=dev)
+    out = torch.empty((S, 2, B), device=dev)
+    with pytest.raises(ValueError):
+        conv._plan.process_device(flat[1:1 + S * C * B].view(S, C, B), yaw, out, torch.cuda.current_stream())
+    conv._plan.process_device(flat[4:4 + S * C * B].view(S, C, B), yaw, out, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert float(out.abs().max()) == 0.0
+
+
 def test_torch_device_path_and_batched_ols(tables):
     import torch
 
