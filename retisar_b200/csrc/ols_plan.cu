@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "fft_warp.cuh"
+#include "sh_analysis_tc.cuh"
 
 using namespace rtb;
 
@@ -36,6 +37,7 @@ struct OlsParams {
     const float2 *tw;          // [N2]
     float *out;                // [S][Cout][B]
     int S, Cin, Cout, P, Fp, slot, passthrough;
+    int TS, TP, tiles_s;       // CTA tile: TS streams x TP channel pairs; tiles along the stream axis
 };
 
 template <int N2>
@@ -61,14 +63,24 @@ ols_fdl_kernel(const OlsParams prm) {
         buf = s_buf + (warp * GROUPS + grp) * Cfg::REGION;
     }
 
+    // A CTA covers a tile of TS streams x TP channel pairs (TS * TP = transforms per CTA): the
+    // groups of a warp are different streams of the same pair, so their filter loads coalesce, and
+    // the warps of a CTA share the streams' delay lines through L1 (mono-in ARIR case: the filter
+    // and the delay line are each re-read from L2 1 / TS and 1 / TP as often as with one task per
+    // (stream, pair) in stream order; measured 1.46 -> ... ms for 1 024 streams x 434 channels x 64 partitions).
     const int npairs = (prm.Cout + 1) / 2;
-    const long long wtask = BIG ? (long long)blockIdx.x : ((long long)blockIdx.x * 4 + warp) * GROUPS;
-    const long long task = wtask + grp;
-    const bool valid = task < (long long)prm.S * npairs;
+    const int local = BIG ? 0 : warp * GROUPS + grp;
+    const int tile_s = (int)(blockIdx.x % (unsigned)prm.tiles_s), tile_p = (int)(blockIdx.x / (unsigned)prm.tiles_s);
+    const int s_raw = tile_s * prm.TS + local % prm.TS, pair_raw = tile_p * prm.TP + local / prm.TS;
+    const bool valid = s_raw < prm.S && pair_raw < npairs;
     // a warp whose groups are all out of range has nothing to do (uniform exit)
-    if (wtask >= (long long)prm.S * npairs) return;
-    const int s = valid ? (int)(task / npairs) : 0;
-    const int pair = valid ? (int)(task % npairs) : 0;
+    if constexpr (!BIG) {
+        if (!__any_sync(0xffffffffu, valid)) return;
+    } else {
+        if (!valid) return;
+    }
+    const int s = valid ? s_raw : 0;
+    const int pair = valid ? pair_raw : 0;
     const int co0 = 2 * pair, co1 = 2 * pair + 1;
     const bool has1 = co1 < prm.Cout;
     const bool mono = prm.Cin == 1 && prm.Cout > 1;
@@ -196,6 +208,158 @@ ols_fdl_kernel(const OlsParams prm) {
     if (blockIdx.x == 0 && threadIdx.x == 0) prm.incl[prm.slot] = prm.passthrough ? 0 : 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Mono input, many outputs (the ARIR pre-renderer: 1 -> 434 channels, 64 partitions at 64-sample
+// blocks).  With one warp group per (stream, channel pair) the kernel above re-reads every filter
+// partition per stream and runs at the load-issue rate (15 loads for 20 packed FMAs per partition:
+// 1.46 ms per block of 1 024 streams, 1 % of the HBM roofline).  Batched over streams the sum over
+// partitions is a GEMM per frequency bin f,
+//     Y[f][c][s] = sum_p H[p][c][f] * X[s][t-p][f]      (complex; M = streams, K = partitions, N = channels)
+// so it runs on the tcgen05 kernel of the SH analysis (sh_analysis_tc.cuh) with the bin in the role
+// of the "stream" (one operand matrix per bin, streamed through the stages), the streams in the
+// role of the samples and the complex product embedded in real arithmetic:
+//     [Yr Yi] = [Xr Xi] [[Hr, Hi], [-Hi, Hr]],  K index = (age p, re / im), N index = (channel, re / im).
+//   ols_mono_spectrum_kernel  FFT of the mono overlap-save buffer -> delay line [f][k][s] (age 0 rows)
+//   (cudaMemcpy2D)            ages the delay line by one partition (ping-pong buffers)
+//   sh_analysis_tc_kernel     one launch per chunk of 112 channels (N <= 256 TMEM columns)
+//   ols_mono_ifft_kernel      gathers the bins of a channel pair for 32 streams through shared
+//                             memory, Hermitian extension, inverse FFT, overlap-save discard
+// ---------------------------------------------------------------------------------------------
+struct OlsMonoParams {
+    const float *x, *xprev;    // [S][B]
+    float *xnext;
+    float *histT;              // [F][Kpad][Spad]: rows 0 / 1 of every bin = Re / Im of X_t
+    const float2 *tw;
+    int S, Spad, Kpad, passthrough;
+};
+
+template <int N2>
+__global__ void __launch_bounds__(128)
+ols_mono_spectrum_kernel(const OlsMonoParams prm) {
+    using Cfg = FftCfg<N2>;
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS, B = N2 / 2;
+    __shared__ float2 s_tw[N2];
+    __shared__ __align__(128) float2 s_buf[4 * GROUPS * Cfg::REGION];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, l = lane % G;
+    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+    __syncthreads();
+    float2 *buf = s_buf + (warp * GROUPS + grp) * Cfg::REGION;
+    const int s_raw = (blockIdx.x * 4 + warp) * GROUPS + grp;
+    const bool valid = s_raw < prm.S;
+    if (!__any_sync(0xffffffffu, valid)) return;
+    const int s = valid ? s_raw : 0;
+    float2 X[EPL];
+    const size_t r0 = (size_t)s * B + l;
+#pragma unroll
+    for (int u = 0; u < HB; ++u) {
+        X[u] = make_float2(valid ? prm.xprev[r0 + G * u] : 0.f, 0.f);
+        X[u + HB] = make_float2(valid ? prm.x[r0 + G * u] : 0.f, 0.f);
+    }
+    if (valid) {
+#pragma unroll
+        for (int u = 0; u < HB; ++u) prm.xnext[r0 + G * u] = X[u + HB].x;
+    }
+    warp_fft<N2, false>(X, buf, s_tw, l);
+    if (valid) {
+        // a passthrough block takes no part in later sums (_convolver.py:558-562): store zeros
+        const float keep = prm.passthrough ? 0.f : 1.f;
+        const size_t fstride = (size_t)prm.Kpad * prm.Spad;
+#pragma unroll
+        for (int u = 0; u <= HB; ++u) {
+            const int f = (u < HB) ? l + G * u : B;
+            if (u < HB || l == 0) {
+                // the input is real, so bin f of the transform is the spectrum itself; the Nyquist
+                // bin sits in element HB of lane 0
+                const float2 z = (u < HB) ? X[u] : X[HB];
+                prm.histT[(size_t)f * fstride + s] = z.x * keep;
+                prm.histT[(size_t)f * fstride + prm.Spad + s] = z.y * keep;
+            }
+        }
+    }
+}
+
+struct OlsMonoIfftParams {
+    const float *Y;            // chunk: [F][Jc][Spad], rows (2 * local channel, + 1) = Re, Im
+    const float *x;            // [S][B] (passthrough: the input block is the output of every channel)
+    const float2 *tw;
+    float *out;                // [S][Cout][B]
+    int S, Spad, Jc, Cout, c0, nch, passthrough;  // chunk covers channels c0 .. c0 + nch - 1
+};
+
+#define RTB_OLS_MONO_ST 32  // streams per CTA of the gather kernel
+
+template <int N2>
+__global__ void __launch_bounds__(128)
+ols_mono_ifft_kernel(const OlsMonoIfftParams prm) {
+    using Cfg = FftCfg<N2>;
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS, B = N2 / 2, F = B + 1;
+    constexpr int ST = RTB_OLS_MONO_ST, TASKS = 4 * GROUPS;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    float *tile = reinterpret_cast<float *>(dyn_smem);  // [F][4 rows: re0 im0 re1 im1][ST + 1]
+    __shared__ float2 s_tw[N2];
+    __shared__ __align__(128) float2 s_buf[4 * GROUPS * Cfg::REGION];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, l = lane % G;
+    const int s0 = blockIdx.x * ST;
+    const int pair = blockIdx.y;                 // channel pair inside the chunk
+    const int cl0 = 2 * pair, cl1 = 2 * pair + 1;
+    const bool has1 = cl1 < prm.nch;
+    for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
+    // coalesced gather: for every bin the four rows of the pair, ST consecutive streams each
+    for (int i = threadIdx.x; i < F * 4 * ST; i += 128) {
+        const int sl = i % ST, r = (i / ST) & 3, f = i / (4 * ST);
+        const int row = 2 * cl0 + r;  // rows of channel cl0 then cl1
+        float v = 0.f;
+        if ((r < 2 || has1) && s0 + sl < prm.Spad)
+            v = prm.Y[((size_t)f * prm.Jc + row) * prm.Spad + s0 + sl];
+        tile[(f * 4 + r) * (ST + 1) + sl] = v;
+    }
+    __syncthreads();
+    float2 *buf = s_buf + (warp * GROUPS + grp) * Cfg::REGION;
+    for (int base = 0; base < ST; base += TASKS) {
+        const int sl = base + warp * GROUPS + grp;
+        const int s = s0 + sl;
+        const bool valid = sl < ST && s < prm.S;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        const int slc = valid ? sl : 0;
+        float2 X[EPL], V[HB];
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            const int f = l + G * u;
+            float2 eL = make_float2(tile[(f * 4 + 0) * (ST + 1) + slc], tile[(f * 4 + 1) * (ST + 1) + slc]);
+            float2 eR = make_float2(tile[(f * 4 + 2) * (ST + 1) + slc], tile[(f * 4 + 3) * (ST + 1) + slc]);
+            if (u == 0 && l == 0) { eL.y = 0.f; eR.y = 0.f; }
+            X[u] = make_float2(eL.x - eR.y, eL.y + eR.x);
+            V[u] = make_float2(eL.x + eR.y, eR.x - eL.y);
+        }
+        const float2 nyq = make_float2(tile[(B * 4 + 0) * (ST + 1) + slc], tile[(B * 4 + 2) * (ST + 1) + slc]);
+        fft_hermitian_fill<N2>(X, V, nyq, buf, l);
+        fft_sync<N2>();
+        warp_fft<N2, true>(X, buf, s_tw, l);
+        if (valid) {
+            const float sc = 1.0f / (float)N2;
+            float *o0 = prm.out + ((size_t)s * prm.Cout + prm.c0 + cl0) * B + l;
+#pragma unroll
+            for (int u = 0; u < HB; ++u) {
+                o0[G * u] = X[u + HB].x * sc;
+                if (has1) o0[B + G * u] = X[u + HB].y * sc;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// passthrough of the mono convolver: every output channel carries the input block
+__global__ void ols_mono_passthrough_kernel(const float *x, float *out, int S, int Cout, int B) {
+    const size_t n = (size_t)S * Cout * B;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t s = i / ((size_t)Cout * B);
+        out[i] = x[s * B + i % B];
+    }
+}
+
 }  // namespace
 
 struct rtb_ols_plan {
@@ -215,11 +379,76 @@ struct rtb_ols_plan {
     bool profiling = false;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     bool ev_valid = false;
+    // mono-in / many-out on the tensor cores (see ols_mono_* above)
+    bool tc_mono = false;
+    int tc_Spad = 0, tc_Kpad = 0, tc_nchunks = 0, tc_hpar = 0;
+    int tc_nch[8] = {0}, tc_Jc[8] = {0}, tc_Npad[8] = {0}, tc_cols[8] = {0}, tc_smem[8] = {0};
+    float *d_histT[2] = {nullptr, nullptr};   // [F][Kpad][Spad], ping-pong (aged by one partition per block)
+    float *d_bmat[8] = {nullptr};             // per chunk: [F][hi, lo][Kpad/4][Npad/8][8][4]
+    float *d_Y[8] = {nullptr};                // per chunk: [F][Jc][Spad]
 };
 
 namespace {
 size_t hist_elems(const rtb_ols_plan *p) { return (size_t)p->S * p->P * p->Cin * p->Fp; }
 size_t state_elems(const rtb_ols_plan *p) { return (size_t)p->S * p->Cin * p->B; }
+
+// one block of the mono-in / many-out convolver on the tensor cores (see ols_mono_* above)
+int process_mono_tc(rtb_ols_plan *p, const float *d_in, float *d_out, cudaStream_t st) {
+    const int F = p->F, Kpad = p->tc_Kpad, Spad = p->tc_Spad;
+    float *cur = p->d_histT[p->tc_hpar], *nxt = p->d_histT[p->tc_hpar ^ 1];
+    // age the delay line by one partition: rows (2p, 2p+1) -> (2p+2, 2p+3) of every bin
+    const size_t row = sizeof(float) * (size_t)Spad, pitch = row * Kpad;
+    RTB_CUDA(cudaMemcpy2DAsync(nxt + 2 * (size_t)Spad, pitch, cur, pitch, row * (Kpad - 2), F,
+                               cudaMemcpyDeviceToDevice, st));
+    OlsMonoParams mp;
+    mp.x = d_in;
+    mp.xprev = p->d_xstate + (size_t)p->par * state_elems(p);
+    mp.xnext = p->d_xstate + (size_t)(p->par ^ 1) * state_elems(p);
+    mp.histT = nxt; mp.tw = p->d_tw; mp.S = p->S; mp.Spad = Spad; mp.Kpad = Kpad;
+    mp.passthrough = p->passthrough ? 1 : 0;
+#define RTB_MONO_SPEC(N) fft_kernel_launch<N>(ols_mono_spectrum_kernel<N>, mp, (long long)p->S, st)
+    switch (p->N2) {
+        case 64: RTB_MONO_SPEC(64); break;   case 128: RTB_MONO_SPEC(128); break;
+        case 256: RTB_MONO_SPEC(256); break; default: RTB_MONO_SPEC(512); break;
+    }
+#undef RTB_MONO_SPEC
+    p->tc_hpar ^= 1;
+    p->launches++;
+    if (p->passthrough) {
+        ols_mono_passthrough_kernel<<<1184, 256, 0, st>>>(d_in, d_out, p->S, p->Cout, p->B);
+        p->launches++;
+        return RTB_OK;
+    }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device);
+    const long long tiles = (long long)F * Spad / RTB_TC_M;
+    const int grid = (int)std::min<long long>(tiles, n_sm);
+    kernel_attrs_once(sh_analysis_tc_kernel<true>, 224 * 1024);
+    for (int ch = 0, c0 = 0; ch < p->tc_nchunks; c0 += p->tc_nch[ch], ++ch) {
+        const int Npad = p->tc_Npad[ch];
+        sh_analysis_tc_kernel<true><<<grid, RTB_TC_THREADS, p->tc_smem[ch], st>>>(
+            nxt, p->d_bmat[ch], p->d_Y[ch], F, Kpad, p->tc_Jc[ch], Spad, Kpad, Npad, p->tc_cols[ch], 2,
+            (long long)2 * Kpad * Npad);
+        OlsMonoIfftParams ip;
+        ip.Y = p->d_Y[ch]; ip.x = d_in; ip.tw = p->d_tw; ip.out = d_out;
+        ip.S = p->S; ip.Spad = Spad; ip.Jc = p->tc_Jc[ch]; ip.Cout = p->Cout; ip.c0 = c0; ip.nch = p->tc_nch[ch];
+        ip.passthrough = 0;
+        const dim3 g2((p->S + RTB_OLS_MONO_ST - 1) / RTB_OLS_MONO_ST, (p->tc_nch[ch] + 1) / 2);
+        const size_t smem = sizeof(float) * (size_t)F * 4 * (RTB_OLS_MONO_ST + 1);
+#define RTB_MONO_IFFT(N)                                                                             \
+    {                                                                                                \
+        if (smem > 48 * 1024) kernel_attrs_once(ols_mono_ifft_kernel<N>, (int)smem);                 \
+        ols_mono_ifft_kernel<N><<<g2, 128, smem, st>>>(ip);                                          \
+    }
+        switch (p->N2) {
+            case 64: RTB_MONO_IFFT(64) break;   case 128: RTB_MONO_IFFT(128) break;
+            case 256: RTB_MONO_IFFT(256) break; default: RTB_MONO_IFFT(512) break;
+        }
+#undef RTB_MONO_IFFT
+        p->launches += 2;
+    }
+    return RTB_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -253,6 +482,40 @@ int rtb_ols_plan_create(rtb_ols_plan **out, int device, int n_streams, int block
         return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
                     "plan allocation failed: %s", cudaGetErrorString(err));
     }
+    {   // mono-in / many-out: per-bin GEMM on the tensor cores (RTB_OLS_TC=0 keeps the SIMT kernel)
+        const char *env = getenv("RTB_OLS_TC");
+        const bool want = env ? env[0] != '0' : true;
+        if (want && p->Cin == 1 && p->Cout >= 32 && p->N2 <= 512) {
+            int spad = 128;
+            while (spad < p->S) spad *= 2;             // tile rows = streams: power of two, >= one M = 128 tile
+            p->tc_Spad = spad;
+            p->tc_Kpad = (2 * p->P + RTB_TC_KC - 1) / RTB_TC_KC * RTB_TC_KC;
+            const int per_chunk = 112;                  // channels per launch: N = 224 <= 256 TMEM columns
+            p->tc_nchunks = (p->Cout + per_chunk - 1) / per_chunk;
+            if (p->tc_nchunks <= 8) {
+                p->tc_mono = true;
+                const size_t hbytes = sizeof(float) * (size_t)p->F * p->tc_Kpad * spad;
+                for (int i = 0; i < 2 && err == cudaSuccess; ++i) err = cudaMalloc(&p->d_histT[i], hbytes);
+                for (int ch = 0; ch < p->tc_nchunks && err == cudaSuccess; ++ch) {
+                    const int nch = std::min(per_chunk, p->Cout - ch * per_chunk);
+                    p->tc_nch[ch] = nch;
+                    p->tc_Jc[ch] = 2 * nch;
+                    p->tc_Npad[ch] = (2 * nch + 15) / 16 * 16;
+                    const int np_ = p->tc_Npad[ch];
+                    p->tc_cols[ch] = np_ <= 32 ? 32 : (np_ <= 64 ? 64 : (np_ <= 128 ? 128 : 256));
+                    p->tc_smem[ch] = 2 * (int)sizeof(float) * (2 * RTB_TC_KC * RTB_TC_M + 2 * RTB_TC_KC * np_);
+                    err = cudaMalloc(&p->d_bmat[ch], sizeof(float) * (size_t)p->F * 2 * p->tc_Kpad * np_);
+                    if (err == cudaSuccess)
+                        err = cudaMalloc(&p->d_Y[ch], sizeof(float) * (size_t)p->F * p->tc_Jc[ch] * spad);
+                }
+                if (err != cudaSuccess) {
+                    rtb_ols_plan_destroy(p);
+                    return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
+                                "plan allocation failed: %s", cudaGetErrorString(err));
+                }
+            }
+        }
+    }
     std::vector<float2> tw(p->N2);
     for (int q = 0; q < p->N2; ++q) {
         const double a = -2.0 * M_PI * q / p->N2;
@@ -275,6 +538,37 @@ int rtb_ols_plan_set_filter(rtb_ols_plan *p, const float *hfd) {
             }
     RTB_CUDA(cudaDeviceSynchronize());
     RTB_CUDA(cudaMemcpy(p->d_hfd, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+    if (p->tc_mono) {
+        // B operand of bin f, K-major core-matrix layout [k/4][n/8][8][4], split into TF32 hi / lo:
+        // row n = (channel, re / im), column k = (age p, re / im):
+        //   Yr = sum_p Hr Xr - Hi Xi,   Yi = sum_p Hi Xr + Hr Xi
+        const int Kpad = p->tc_Kpad;
+        for (int ch = 0, c0 = 0; ch < p->tc_nchunks; c0 += p->tc_nch[ch], ++ch) {
+            const int Npad = p->tc_Npad[ch];
+            const size_t per_f = (size_t)2 * Kpad * Npad;
+            std::vector<float> bm((size_t)p->F * per_f, 0.f);
+            for (int f = 0; f < p->F; ++f)
+                for (int cl = 0; cl < p->tc_nch[ch]; ++cl)
+                    for (int q = 0; q < p->P; ++q) {
+                        const float2 hv = h[((size_t)q * p->Cout + c0 + cl) * p->Fp + f];
+                        const float vals[2][2] = {{hv.x, -hv.y}, {hv.y, hv.x}};  // [n re/im][k re/im]
+                        for (int nr = 0; nr < 2; ++nr)
+                            for (int kr = 0; kr < 2; ++kr) {
+                                const int n = 2 * cl + nr, k = 2 * q + kr;
+                                const float v = vals[nr][kr];
+                                uint32_t u;
+                                memcpy(&u, &v, 4);
+                                u = (u + 0x1000u) & 0xffffe000u;  // round to nearest TF32
+                                float hi;
+                                memcpy(&hi, &u, 4);
+                                const size_t off = (((size_t)(k / 4) * (Npad / 8) + n / 8) * 8 + n % 8) * 4 + k % 4;
+                                bm[f * per_f + off] = hi;
+                                bm[f * per_f + (size_t)Kpad * Npad + off] = v - hi;
+                            }
+                    }
+            RTB_CUDA(cudaMemcpy(p->d_bmat[ch], bm.data(), sizeof(float) * bm.size(), cudaMemcpyHostToDevice));
+        }
+    }
     p->filter_set = true;
     return RTB_OK;
 }
@@ -292,6 +586,9 @@ int rtb_ols_plan_reset(rtb_ols_plan *p) {
     RTB_CUDA(cudaMemset(p->d_xstate, 0, sizeof(float) * 2 * state_elems(p)));
     RTB_CUDA(cudaMemset(p->d_hist, 0, sizeof(float2) * hist_elems(p)));
     RTB_CUDA(cudaMemset(p->d_incl, 0, p->P));
+    if (p->tc_mono)
+        for (int i = 0; i < 2; ++i)
+            RTB_CUDA(cudaMemset(p->d_histT[i], 0, sizeof(float) * (size_t)p->F * p->tc_Kpad * p->tc_Spad));
     return RTB_OK;
 }
 
@@ -307,9 +604,28 @@ int rtb_ols_process_block(rtb_ols_plan *p, const float *d_in, float *d_out, void
     prm.hist = p->d_hist; prm.hfd = p->d_hfd; prm.incl = p->d_incl; prm.tw = p->d_tw; prm.out = d_out;
     prm.S = p->S; prm.Cin = p->Cin; prm.Cout = p->Cout; prm.P = p->P; prm.Fp = p->Fp;
     prm.slot = p->slot; prm.passthrough = p->passthrough ? 1 : 0;
-    const long long pairs = (long long)p->S * ((p->Cout + 1) / 2);
+    const int npairs = (p->Cout + 1) / 2;
     if (p->profiling) cudaEventRecord(p->ev[0], st);
-#define RTB_OLS_LAUNCH(N) fft_kernel_launch<N>(ols_fdl_kernel<N>, prm, pairs, st)
+    if (p->tc_mono) {
+        const int rc = process_mono_tc(p, d_in, d_out, st);
+        if (rc != RTB_OK) return rc;
+        if (p->profiling) { cudaEventRecord(p->ev[1], st); p->ev_valid = true; }
+        p->par ^= 1;
+        RTB_CUDA(cudaGetLastError());
+        return RTB_OK;
+    }
+    // tile shape: mono-in / many-out (ARIR) shares both operands -> square tile; otherwise all
+    // transforms of a CTA take the same pair of consecutive streams
+#define RTB_OLS_LAUNCH(N)                                                                            \
+    {                                                                                                \
+        const int tpc = FftCfg<N>::TASKS;                                                            \
+        const bool mono = p->Cin == 1 && p->Cout > 1;                                                \
+        prm.TP = mono ? std::min(npairs, tpc >= 16 ? 4 : (tpc >= 4 ? 2 : 1)) : 1;                    \
+        prm.TS = tpc / prm.TP;                                                                       \
+        prm.tiles_s = (p->S + prm.TS - 1) / prm.TS;                                                  \
+        const long long tiles = (long long)prm.tiles_s * ((npairs + prm.TP - 1) / prm.TP);          \
+        fft_kernel_launch<N>(ols_fdl_kernel<N>, prm, tiles * tpc, st);                               \
+    }
     RTB_DISPATCH_N2(p->N2, RTB_OLS_LAUNCH)
 #undef RTB_OLS_LAUNCH
     if (p->profiling) { cudaEventRecord(p->ev[1], st); p->ev_valid = true; }
@@ -373,6 +689,9 @@ int rtb_ols_plan_destroy(rtb_ols_plan *p) {
     DeviceGuard guard(p->device);
     cudaFree(p->d_xstate); cudaFree(p->d_hist); cudaFree(p->d_hfd); cudaFree(p->d_incl); cudaFree(p->d_tw);
     cudaFree(p->d_in); cudaFree(p->d_out);
+    for (auto q : p->d_histT) cudaFree(q);
+    for (auto q : p->d_bmat) cudaFree(q);
+    for (auto q : p->d_Y) cudaFree(q);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     delete p;

@@ -43,6 +43,8 @@
 // chunk of a stage is requested by the loader group that fills the stage, completion is counted on
 // the stage's `full` mbarrier together with the loader warps' arrivals.
 #pragma once
+#include "rtb_common.cuh"
+#include "rtb_async.cuh"
 
 namespace rtb {
 
@@ -91,7 +93,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
 // -DRTB_TRACE_TC: CTA 0 logs clock64 stamps per role (tools/tc_trace.py): role 0 = loader warp 0
 // (indexed by chunk), role 2 = MMA issuer, role 3 = epilogue warp 8 (indexed by tile)
 #ifdef RTB_TRACE_TC
-__device__ long long g_tc_trace[4096];
+static __device__ long long g_tc_trace[4096];
 #define TC_STAMP(role, it, k) do { if (blockIdx.x == 0 && (it) < 100) g_tc_trace[(role) * 1000 + (it) * 8 + (k)] = clock64(); } while (0)
 #else
 #define TC_STAMP(role, it, k) do {} while (0)
@@ -115,7 +117,7 @@ __device__ long long g_tc_trace[4096];
 
 // 16 bytes of one channel row (4 consecutive samples), zero when the predicate is off (the
 // predicate is folded into the address).
-__device__ float4 g_tc_zero4;  // zero-initialised
+static __device__ float4 g_tc_zero4;  // zero-initialised
 __device__ __forceinline__ float4 ldg_nc_v4_pred(const float *p, bool pred) {
     return __ldg(reinterpret_cast<const float4 *>(pred ? p : reinterpret_cast<const float *>(&g_tc_zero4)));
 }
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(RTB_TC_THREADS, 1)
 sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                       const float *__restrict__ bsrc,  // [2][Kpad/4][Npad/8][8][4]: hi then lo
                       float *__restrict__ zcur,        // [S][J][B]
-                      int S, int C, int J, int B, int Kpad, int Npad, int acc_cols, int nst) {
+                      int S, int C, int J, int B, int Kpad, int Npad, int acc_cols, int nst,
+                      long long bmat_stride) {  // STREAM_B: floats between the matrices of consecutive streams (0: one matrix)
     constexpr int KC = RTB_TC_KC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *a_stage = reinterpret_cast<float *>(smem_raw);   // [nst stages][hi, lo][KC/4][16][8][4]
@@ -226,9 +229,10 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             if (STREAM_B && sub == 0 && lane == 0) {  // this chunk's rows of the split analysis matrix -> stage st
                 const unsigned bytes = (unsigned)(bchunk_floats * sizeof(float));
                 float *bst = b_hi + (size_t)st * 2 * bchunk_floats;
+                const float *bs = bsrc + (size_t)s * bmat_stride;  // lane 0: first row of the tile
                 mbar_expect_tx(&full_bar[st], 2 * bytes);
-                bulk_copy_g2s(bst, bsrc + (size_t)h * bchunk_floats, bytes, &full_bar[st]);
-                bulk_copy_g2s(bst + bchunk_floats, bsrc + (size_t)Kpad * Npad + (size_t)h * bchunk_floats, bytes,
+                bulk_copy_g2s(bst, bs + (size_t)h * bchunk_floats, bytes, &full_bar[st]);
+                bulk_copy_g2s(bst + bchunk_floats, bs + (size_t)Kpad * Npad + (size_t)h * bchunk_floats, bytes,
                               &full_bar[st]);
             }
 #pragma unroll

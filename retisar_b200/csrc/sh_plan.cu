@@ -135,7 +135,7 @@ void launch_analysis(const rtb_sh_plan *p, const float *d_in, float *zcur, int c
     {                                                                                                \
         kernel_attrs_once(sh_analysis_tc_kernel<SB>, 224 * 1024);                                    \
         sh_analysis_tc_kernel<SB><<<grid, RTB_TC_THREADS, p->tc_smem, st>>>(                         \
-            d_in, p->d_tc_b, zcur, count, p->C, p->J, p->B, p->tc_Kpad, p->tc_Npad, p->tc_cols, p->tc_nst); \
+            d_in, p->d_tc_b, zcur, count, p->C, p->J, p->B, p->tc_Kpad, p->tc_Npad, p->tc_cols, p->tc_nst, 0LL); \
     }
         if (p->tc_stream_b) RTB_TC_LAUNCH_T(true) else RTB_TC_LAUNCH_T(false)
 #undef RTB_TC_LAUNCH_T

@@ -77,3 +77,26 @@ def chain_flops_per_stream_block(C, K, B, E=2):
     F, N2 = B + 1, 2 * B
     fft = 2.5 * N2 * np.log2(N2)
     return C * fft + 8 * K * C * F + 6 * K * E * F + 2 * 8 * K * E * F + 2 * E * fft + 3 * E * B
+
+
+def make_c4_chain(tables, n_streams, arir_taps=4096, hpcf_taps=1024, device=None, seed=40):
+    """The three convolvers of BASELINE config c4 in the reference's production topology
+    (``JackRenderer`` chain pre-renderer -> renderer -> HPCF, ``_run.py:setup_*``): a mono source
+    through a 434-channel ARIR (``OverlapSaveConvolver``, mono input broadcast,
+    ``_convolver.py:588-591``), the SH renderer, and a 2-channel headphone compensation filter.
+
+    Returns (arir, renderer, hpcf, arir_irs [C; taps], hpcf_irs [2; taps]); SURVEY.md section 8d:
+    seeded decaying noise, 4096-tap ARIR (P = 64 at B = 64), 1024-tap HPCF (P = 16).
+    """
+    from ._convolver import Convolver
+    from ._filter_set import FilterSet
+
+    B, C = tables["B"], tables["C"]
+    arir_irs = syn.decaying_noise_irs((C, arir_taps), seed)
+    hpcf_irs = syn.decaying_noise_irs((2, hpcf_taps), seed + 1, scale=0.3)
+    convs = []
+    for irs in (arir_irs, hpcf_irs):
+        fs = FilterSet.create_instance_by_type(irs, "FIR_MULTICHANNEL")
+        fs.load(block_length=B, is_single_precision=True, is_prevent_logging=True)
+        convs.append(Convolver.create_instance_by_filter_set(fs, B, n_streams=n_streams, device=device))
+    return convs[0], make_renderer(tables, n_streams, device=device), convs[1], arir_irs, hpcf_irs
