@@ -288,7 +288,9 @@ struct OlsMonoIfftParams {
     int S, Spad, Jc, Cout, c0, nch, passthrough;  // chunk covers channels c0 .. c0 + nch - 1
 };
 
+#ifndef RTB_OLS_MONO_ST
 #define RTB_OLS_MONO_ST 32  // streams per CTA of the gather kernel
+#endif
 
 template <int N2>
 __global__ void __launch_bounds__(128)
@@ -307,14 +309,17 @@ ols_mono_ifft_kernel(const OlsMonoIfftParams prm) {
     const int cl0 = 2 * pair, cl1 = 2 * pair + 1;
     const bool has1 = cl1 < prm.nch;
     for (int i = threadIdx.x; i < N2; i += 128) s_tw[i] = prm.tw[i];
-    // coalesced gather: for every bin the four rows of the pair, ST consecutive streams each
-    for (int i = threadIdx.x; i < F * 4 * ST; i += 128) {
-        const int sl = i % ST, r = (i / ST) & 3, f = i / (4 * ST);
+    // coalesced gather: for every bin the four rows of the pair, ST consecutive streams each, as
+    // 16-byte loads (Spad is a multiple of ST); the scalar stores into the padded rows are
+    // conflict free (bank = 33 r + 4 sl4 + j)
+    for (int i = threadIdx.x; i < F * 4 * (ST / 4); i += 128) {
+        const int sl4 = i % (ST / 4), r = (i / (ST / 4)) & 3, f = i / ST;
         const int row = 2 * cl0 + r;  // rows of channel cl0 then cl1
-        float v = 0.f;
-        if ((r < 2 || has1) && s0 + sl < prm.Spad)
-            v = prm.Y[((size_t)f * prm.Jc + row) * prm.Spad + s0 + sl];
-        tile[(f * 4 + r) * (ST + 1) + sl] = v;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < 2 || has1)
+            v = __ldcs(reinterpret_cast<const float4 *>(prm.Y + ((size_t)f * prm.Jc + row) * prm.Spad + s0) + sl4);
+        float *d = tile + (f * 4 + r) * (ST + 1) + 4 * sl4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
     __syncthreads();
     float2 *buf = s_buf + (warp * GROUPS + grp) * Cfg::REGION;
