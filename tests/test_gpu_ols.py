@@ -74,3 +74,35 @@ def test_ols_batched_streams_long_filter():
         for c in range(C):
             ref = np.convolve(xs[s, c], irs[c].astype(np.float64))[: T * B]
             assert np.abs(y[s, c] - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("B,Cout,P,S", [(256, 33, 3, 5), (32, 40, 5, 130), (64, 120, 20, 3), (128, 32, 1, 2)])
+def test_mono_in_many_out_tensor_core_path(B, Cout, P, S):
+    """Mono input broadcast into >= 32 filter channels (the ARIR pre-renderer shape) runs as a
+    per-bin GEMM on the tensor cores: odd channel counts, partition counts that are not a multiple
+    of the K chunk, stream counts on both sides of one M = 128 tile, every block length of the path,
+    with passthrough blocks and a clear in between -- block by block against the pinned oracle."""
+    from oracle import sh_chain as oc
+    from retisar_b200.plans import OlsPlan
+
+    rng = np.random.default_rng(B + Cout)
+    T = 3 * P + 6
+    irs = (rng.standard_normal((Cout, P * B)) * 0.05 * np.exp(-np.arange(P * B) / (0.3 * P * B))).astype(np.float32)
+    H = oc.filter_blocks_fd(irs[None], B)  # [P, 1, Cout, F]
+    plan = OlsPlan(S, B, 1, Cout, P)
+    plan.set_filter(H[:, 0])
+    oracles = [oc.OlsOracle(H.copy(), B) for _ in range(S)]
+    x = (rng.standard_normal((T, S, 1, B)) * 0.3).astype(np.float32)
+    worst = 0.0
+    for t in range(T):
+        passthrough = t in (P + 1, P + 2)
+        plan.set_passthrough(passthrough)
+        if t == 2 * P + 3:
+            plan.reset()
+        y = plan.process_host(x[t])
+        for s, o in enumerate(oracles):
+            o.is_passthrough = passthrough
+            if t == 2 * P + 3:
+                o.clear()
+            worst = max(worst, float(np.abs(y[s] - o.filter_block(x[t, s])).max()))
+    assert worst <= TOL, worst
