@@ -16,8 +16,8 @@
 // the 4 KB A-operand fetch from shared memory).
 //
 // Warp-specialised, persistent (one CTA per SM, 13 warps):
-//   warps 0-7   loaders: one group of warps per operand stage (4 stages: pairs), groups run out of
-//               phase -- 16-byte row loads, TF32 split, conflict-free transposed stores,
+//   warps 0-7   loaders: four pairs of warps, each with its own full / empty mbarriers, running out
+//               of phase -- 16-byte row loads, TF32 split, conflict-free transposed stores,
 //               fence.proxy.async, arrive on the stage's `full` mbarrier
 //   warp 12     MMA issuer: warp-uniform loop, one elected lane issues the MMAs of a stage and
 //               commits the stage back (`empty`) / the accumulator to the epilogue (`tfull`)
@@ -154,8 +154,8 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
         }
     if (tid == 0) {
         for (int i = 0; i < RTB_TC_MAX_ST; ++i) {
-            // one arrival per warp of the stage's loader group (+ the expect_tx arrival of the B chunk)
-            mbar_init(&full_bar[i], 8 / nst + (STREAM_B ? 1 : 0));
+            // one arrival per warp of the loader group (+ the expect_tx arrival of the B chunk)
+            mbar_init(&full_bar[i], 2 + (STREAM_B ? 1 : 0));
             mbar_init(&empty_bar[i], 1);   // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
@@ -199,14 +199,17 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
         // step s stores row 4l + (s + rot) % 4 with rot = (l / 2) % 4, so that the eight lanes of a
         // 128-bit store phase hit eight different 16-byte bank groups (rows 4l + s for all lanes
         // would be a 4-way conflict).
-        // Loader groups = stages (2 or 4): group g fills stage g only, so it sees every phase of the
-        // stage's `empty` barrier (a group that skipped phases would misread the parity).  With 2
-        // stages a group is 4 warps of 8 channels, with 4 stages a pair of 16 channels.
-        const int wpg = 8 / nst, qpw = 8 / wpg;            // warps per group, channel quads per warp
-        const int pair = warp / wpg, sub = warp - pair * wpg;
+        // Four loader groups (pairs of warps, 16 channels per warp) whatever the number of physical
+        // stages: unit n (in MMA order) belongs to group n % 4 and lands in stage n % nst.  Every
+        // group has its own full / empty mbarrier pair (a barrier shared by two groups would be
+        // waited on every other phase and its parity misread): after unit n the MMA issuer commits
+        // to the `empty` barrier of group (n + nst) % 4, the next user of that stage.  With two
+        // stages (streamed B operand) four groups still keep 64 KB of loads in flight.
+        constexpr int qpw = 4;                             // channel quads per warp
+        const int pair = warp >> 1, sub = warp & 1;        // loader group, warp in the group
         const int rot = (lane >> 1) & 3;
         const bool r1 = rot & 1, r2 = rot & 2;
-        for (long long n = pair; n < my_units; n += nst) {
+        for (long long n = pair; n < my_units; n += 4) {
             const long long it = n / n_chunks;
             const int h = (int)(n - it * n_chunks);
             const long long g = ((long long)blockIdx.x + it * gridDim.x) * RTB_TC_M + 4 * lane;
@@ -222,18 +225,23 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[q][i] = ldg_nc_v4_pred(xp + (size_t)(4 * q + i) * B, 4 * q + i < cmax);
-            const int st = pair;
+            const int st = (int)(n % nst);
+            // k-th unit of this group: its stage was last used by unit n - nst, whose completion is
+            // commit number k (groups that start on a fresh stage) or k + 1 (the others) on this
+            // group's `empty` barrier
+            const unsigned k = (unsigned)(n >> 2);
+            const unsigned par = (pair < nst) ? ((k & 1) ^ 1) : (k & 1);
             if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 0);
-            mbar_wait(&empty_bar[st], (unsigned)(((n / nst) & 1) ^ 1));
+            mbar_wait(&empty_bar[pair], par);
             if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 1);
             if (STREAM_B && sub == 0 && lane == 0) {  // this chunk's rows of the split analysis matrix -> stage st
                 const unsigned bytes = (unsigned)(bchunk_floats * sizeof(float));
                 float *bst = b_hi + (size_t)st * 2 * bchunk_floats;
                 const float *bs = bsrc + (size_t)s * bmat_stride;  // lane 0: first row of the tile
-                mbar_expect_tx(&full_bar[st], 2 * bytes);
-                bulk_copy_g2s(bst, bs + (size_t)h * bchunk_floats, bytes, &full_bar[st]);
+                mbar_expect_tx(&full_bar[pair], 2 * bytes);
+                bulk_copy_g2s(bst, bs + (size_t)h * bchunk_floats, bytes, &full_bar[pair]);
                 bulk_copy_g2s(bst + bchunk_floats, bs + (size_t)Kpad * Npad + (size_t)h * bchunk_floats, bytes,
-                              &full_bar[st]);
+                              &full_bar[pair]);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -263,7 +271,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor core reads
 #endif
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[st]);
+            if (lane == 0) mbar_arrive(&full_bar[pair]);
             if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 2);
         }
     } else if (warp == 12) {
@@ -274,8 +282,8 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                                    ((uint32_t)(RTB_TC_M >> 4) << 24);  // D f32, A/B tf32, K-major, N, M
             const uint32_t lbo_a = (RTB_TC_M / 8) * 128, lbo_b = (Npad / 8) * 128, sbo = 128;
             const uint64_t step_a = (2 * lbo_a) >> 4, step_b = (2 * lbo_b) >> 4;
-            int st = 0;
-            unsigned ph = 0;
+            int st = 0;        // physical stage of the unit
+            long long mm = 0;  // unit counter: loader group mm % 4, its phase (mm / 4) % 2
             for (long long it = 0; it < my_tiles; ++it) {
                 const int acc = (int)(it & 1);
                 if (lane == 0) TC_STAMP(2, (int)it, 0);
@@ -286,7 +294,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                     const int ksteps = min(KC / 8, (C - h * KC + 7) / 8);  // the last chunk may be short
                     {
                         const uint32_t d_tmem = tmem + acc * acc_cols;
-                        mbar_wait(&full_bar[st], ph);
+                        mbar_wait(&full_bar[mm & 3], (unsigned)((mm >> 2) & 1));
                         if (h == 0 && lane == 0) TC_STAMP(2, (int)it, 2);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #if !RTB_TC_FENCE_WRITER
@@ -315,11 +323,13 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                                         umma_tf32(d_tmem, da0 + ks * step_a, db0 + ks * step_b, idesc,
                                                   (h | pass | ks) ? 1u : 0u);
                             }
-                            umma_commit(&empty_bar[st]);  // the stage is free once these MMAs have read it
+                            // the stage is free once these MMAs have read it: tell its next user
+                            umma_commit(&empty_bar[(mm + nst) & 3]);
                             if (h == n_chunks - 1) umma_commit(&tfull_bar[acc]);
                         }
                         __syncwarp();
-                        if (++st == nst) { st = 0; ph ^= 1; }
+                        ++mm;
+                        if (++st == nst) st = 0;
                     }
                 }
                 if (lane == 0) TC_STAMP(2, (int)it, 6);
