@@ -208,6 +208,124 @@ __device__ __forceinline__ void fft_exchange_c(float2 (&X)[Cfg::EPL], const floa
     sync();
 }
 
+// ---------------------------------------------------------------------------------------------
+// 512 points on one warp as 16 x 16 x 2 (RTB_FFT_R16): the kernels built on the warp transform are
+// bound by the L1 / shared-memory data pipe (render kernel: 78 % of its peak, 42 % of the wavefronts
+// are the two exchanges of the 8 x 8 x 8 schedule).  With radix 16 the lane's 16 elements are one
+// butterfly, so only ONE exchange goes through shared memory; the second one, in front of the final
+// radix-2 pass, is a swap of eight values with lane l ^ 16 (shuffles).  Same Stockham index algebra
+// as fft_pass_c: pass (R, NS) reads X[t] <-> element l + 32 t, multiplies by w^t with
+// w = exp(-+2 pi i k / (NS R)), k = l % NS, and leaves output t at position (l / NS) NS R + k + t NS.
+// ---------------------------------------------------------------------------------------------
+// Measured (render kernel, c2 10 240 streams / c5 8 192 streams): 230 vs 240 us, 517 vs 539 us.
+#ifndef RTB_FFT_R16
+#define RTB_FFT_R16 1
+#endif
+
+// exchange-buffer placement of the 16 x 16 schedule: writes 16 l + t (l = lane) and reads l + 32 u
+// are both conflict free per half warp (8-byte accesses)
+__host__ __device__ __forceinline__ constexpr int fft_swz16(int i) { return i ^ ((i >> 4) & 15); }
+
+template <bool INV>
+__device__ __forceinline__ float2 cmul_w16(float2 a, int p) {  // a * exp(-+2 pi i p / 16), p compile time
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    float2 w;
+    switch (p & 15) {
+        case 0: return a;
+        case 1: w = make_float2(c1, -s1); break;
+        case 2: w = make_float2(h, -h); break;
+        case 3: w = make_float2(s1, -c1); break;
+        case 4: return rot90<INV>(a);
+        case 5: w = make_float2(-s1, -c1); break;
+        case 6: w = make_float2(-h, -h); break;
+        case 7: w = make_float2(-c1, -s1); break;
+        case 8: return make_float2(-a.x, -a.y);
+        case 9: w = make_float2(-c1, s1); break;
+        case 10: w = make_float2(-h, h); break;
+        case 11: w = make_float2(-s1, c1); break;
+        case 12: { float2 r = rot90<INV>(a); return make_float2(-r.x, -r.y); }
+        case 13: w = make_float2(s1, c1); break;
+        case 14: w = make_float2(h, h); break;
+        default: w = make_float2(c1, s1); break;
+    }
+    if (INV) w.y = -w.y;
+    return cmul(a, w);
+}
+
+// 16-point DFT in place (4 x 4 decomposition): natural order in, output t in slot dft16_out(t)
+template <bool INV>
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dft4<INV>(v[q], v[q + 4], v[q + 8], v[q + 12]);  // v[q + 4 r] = a[q][r]
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+#pragma unroll
+        for (int r = 1; r < 4; ++r) v[q + 4 * r] = cmul_w16<INV>(v[q + 4 * r], q * r);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dft4<INV>(v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]);  // over q -> X[r + 4 s]
+    // v[4 r + s] now holds output r + 4 s: the callers index the result through dft16_out()
+}
+// register slot of output t of dft16
+__host__ __device__ __forceinline__ constexpr int dft16_out(int t) { return 4 * (t & 3) + (t >> 2); }
+
+template <bool INV, class Sync, class Hook>
+__device__ __forceinline__ void fft512_r16(float2 (&X)[16], float2 *buf, const float2 *tw, int l,
+                                           Sync &&sync, Hook &&after_last_exchange) {
+    // pass A: radix 16, NS = 1 (no twiddles); output t of lane l -> position 16 l + t
+    dft16<INV>(X);
+    // addresses as (lane part) ^ (immediate) + (immediate): the buffer is 128-byte aligned, the lane
+    // parts and the compile-time parts occupy disjoint bit fields
+    {
+        const unsigned pre = smem_addr32(buf) + 128u * (unsigned)l + 8u * (unsigned)(l & 15);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) sts64(pre ^ (8u * t), X[dft16_out(t)]);  // index 16 l + (t ^ l % 16)
+    }
+    sync();
+    {
+        const unsigned hi = (unsigned)l >> 4;
+        const unsigned pre = smem_addr32(buf) + 8u * (16u * hi + (((unsigned)l & 15u) ^ hi));
+#pragma unroll
+        for (int u = 0; u < 16; ++u)  // index (l + 32 u) ^ ((l / 16 + 2 u) % 16)
+            X[u] = lds64((pre ^ (8u * ((2 * u) & 15))) + 256u * u);
+    }
+    sync();
+    after_last_exchange();
+    // pass B: radix 16, NS = 16: k = l % 16, w = exp(-+2 pi i k / 256) = tw[2 k]
+    {
+        float2 w = tw[2 * (l & 15)];
+        if (INV) w.y = -w.y;
+        float2 wp = w;
+#pragma unroll
+        for (int t = 1; t < 16; ++t) {
+            X[t] = cmul(X[t], wp);
+            if (t < 15) wp = cmul(wp, w);
+        }
+    }
+    dft16<INV>(X);
+    // output t of lane l sits at position p = (l / 16) 256 + l % 16 + 16 t.  The final radix-2 pass
+    // (NS = 256) of lane l needs elements j = l + 32 b and j + 256, b < 8: both have t = l / 16 + 2 b
+    // and live in lanes l % 16 and l % 16 + 16 -- one of them is this lane, the other lane l ^ 16.
+    const bool upper = l >= 16;
+    float2 wl = tw[l];  // exp(-2 pi i l / 512); times exp(-2 pi i b / 16) per butterfly
+    if (INV) wl.y = -wl.y;
+    float2 Y[16];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const float2 even = X[dft16_out(2 * b)], odd = X[dft16_out(2 * b + 1)];
+        const float2 send = upper ? even : odd;
+        float2 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+        float2 v0 = upper ? recv : even;
+        float2 v1 = upper ? odd : recv;
+        v1 = cmul(v1, cmul_w16<INV>(wl, b));
+        Y[b] = cadd(v0, v1);
+        Y[b + 8] = csub(v0, v1);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) X[u] = Y[u];
+}
+
 // In-register transform of the group's points.  `buf` = this group's REGION of shared memory,
 // `tw` = exp(-2*pi*i*q/LEN), q < LEN (shared or global memory), l = lane index inside the group.
 // All lanes of the group must call it together.  `after_last_exchange()` runs once the exchange
@@ -217,6 +335,10 @@ __device__ __forceinline__ void fft_run_c(float2 (&X)[Cfg::EPL], float2 *buf, co
                                           Sync &&sync, Hook &&after_last_exchange) {
     constexpr int NP = Cfg::NPASS8;
     constexpr bool TAIL = Cfg::R_LAST != 0;
+    if constexpr (RTB_FFT_R16 && Cfg::LEN == 512 && Cfg::G == 32 && Cfg::EPL == 16) {
+        fft512_r16<INV>(X, buf, tw, l, sync, after_last_exchange);
+        return;
+    }
     fft_pass_c<Cfg, 8, 1, INV, true, AL>(X, buf, tw, l);
     fft_exchange_c<Cfg, AL>(X, buf, l, sync);
     if constexpr (NP == 2 && !TAIL) after_last_exchange();
