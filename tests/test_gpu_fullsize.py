@@ -55,3 +55,23 @@ def test_stream_independence_and_linearity_at_full_size():
         yb = b.filter_block(2.0 * x, yaw)        # scaling by 2 is exact in binary floating point
         assert np.array_equal(ya[777], ya[5])
         assert np.array_equal(yb, 2.0 * ya)
+
+
+@pytest.mark.parametrize("workload,S", [("c2", 4100), ("c5", 2051), ("c4", 1030)])
+def test_every_stream_of_a_large_batch_equals_the_first(workload, S):
+    """All streams get the same input and yaw: every output must equal stream 0 bit for bit (each
+    row of every tile of the persistent tensor-core kernel, through many mbarrier phases per CTA
+    and a ragged last tile), and stream 0 must match the oracle."""
+    from retisar_b200 import workloads as wl
+
+    tb = wl.sh_tables(workload, hrir_dirs=200)
+    conv = wl.make_renderer(tb, S)
+    o = _oracle_for(tb)
+    rng = np.random.default_rng(7)
+    C, B = tb["C"], tb["B"]
+    for t in range(3):
+        x1 = (rng.standard_normal((C, B)) * 0.1).astype(np.float32)
+        yaw1 = np.float32(rng.uniform(0, 360))
+        y = conv.filter_block(np.broadcast_to(x1, (S, C, B)).copy(), np.full(S, yaw1, np.float32))
+        assert np.array_equal(y, np.broadcast_to(y[0], y.shape)), (workload, t)
+        assert np.abs(y[0] - o.filter_block(x1, yaw1)).max() <= TOL, (workload, t)
