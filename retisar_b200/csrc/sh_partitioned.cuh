@@ -226,8 +226,11 @@ sh_partition_mac_kernel(const ShPartParams prm) {
 // Second version of the partition MAC: the H rows of the CTA's 32 bins are staged through shared
 // memory (cp.async, double buffered over chunks of RTB_MAC_SC steps) and shared by 8 warps = 16
 // streams, instead of every warp pulling them through L1/L2 (first version: 5.1 long-scoreboard
-// stall cycles per issue, FMA pipe 33 %, profiles/).  Spectra are read two steps ahead.
+// stall cycles per issue, FMA pipe 33 %, profiles/).  Spectra are read in batches (see the loop).
 #define RTB_MAC_SC 8        // steps per staged chunk
+#ifndef RTB_MAC_ZB
+#define RTB_MAC_ZB 2        // steps per batch of spectrum loads (measured c3: 2 -> 2479 us, 4 -> 2503 us, per-step prefetch 2639 us)
+#endif
 #define RTB_MAC_WARPS 8     // warps per CTA, 2 streams each
 #define RTB_MAC_MAX_STEPS 192
 
@@ -297,8 +300,13 @@ sh_partition_mac2_kernel(const ShPartParams prm) {
                 for (int c = 0; c < 2; ++c) acc[a][e][c][0] = acc[a][e][c][1] = make_float2(0.f, 0.f);
         if (nchunks > 0) stage_h(0, 0);
         cp_async_commit();
-        // spectra two steps ahead
-        float2 za[2], zb[2];
+        // Spectra: loaded in batches of RTB_MAC_ZB steps into two register rings.  ptxas tracks every
+        // LDG of this loop on one scoreboard, so the first use of ANY loaded value waits for ALL
+        // loads in flight: a per-step prefetch ("two steps ahead") in fact waited for the load issued
+        // in the same step (long-scoreboard 4.3 stall cycles per issue, FMA pipe 40 %).  With a batch
+        // issued every RTB_MAC_ZB steps the wait comes RTB_MAC_ZB steps of arithmetic later.
+        static_assert(RTB_MAC_SC % (2 * RTB_MAC_ZB) == 0, "chunk = whole pairs of spectrum batches");
+        float2 zr[2][RTB_MAC_ZB][2];  // [ring][step in batch][stream]
         auto load_z = [&](int j, float2 (&z)[2]) {
             if (j < nsteps && wactive) {
                 const ShStep st_ = s_steps[j];
@@ -309,43 +317,48 @@ sh_partition_mac2_kernel(const ShPartParams prm) {
                 z[0] = z[1] = make_float2(0.f, 0.f);
             }
         };
-        load_z(0, za);
-        load_z(1, zb);
+#pragma unroll
+        for (int i = 0; i < RTB_MAC_ZB; ++i) load_z(i, zr[0][i]);
         for (int c = 0; c < nchunks; ++c) {
             cp_async_wait_all();
             __syncthreads();  // chunk c has landed; everyone has left chunk c-1 (its buffer is free)
             if (c + 1 < nchunks) stage_h(c + 1, (c + 1) & 1);
             cp_async_commit();
             if (!wactive) continue;
-#pragma unroll 2
+#pragma unroll
             for (int jj = 0; jj < RTB_MAC_SC; ++jj) {
                 const int j = c * RTB_MAC_SC + jj;
-                if (j >= nsteps) break;
-                const ShStep stp = s_steps[j];
-                float2 zz[2] = {za[0], za[1]};
-                za[0] = zb[0]; za[1] = zb[1];
-                load_z(j + 2, zb);
-                const bool in_cur = j < prm.nsteps_cur, in_last = j < prm.nsteps_last;
-                float2 A[2][2];  // [cur/last][stream]
+                constexpr int ZB = RTB_MAC_ZB;
+                const int ring = (jj / ZB) & 1, slot = jj % ZB;
+                const float2 zz[2] = {zr[ring][slot][0], zr[ring][slot][1]};
+                if (slot == 0) {  // first use of this batch (the wait): now request the next one
 #pragma unroll
-                for (int st = 0; st < 2; ++st) {
-                    float2 z = zz[st];
-                    if (stp.term) z.y = -z.y;
-                    const float2 pc = in_cur ? phase_of(s_cs[warp][st][0], stp.m) : make_float2(0.f, 0.f);
-                    const float2 pl = in_last ? phase_of(s_cs[warp][st][1], stp.m) : make_float2(0.f, 0.f);
-                    A[0][st] = cmul(pc, z);
-                    A[1][st] = cmul(pl, z);
+                    for (int i = 0; i < ZB; ++i) load_z(j + ZB + i, zr[ring ^ 1][i]);
                 }
+                if (j < nsteps) {
+                    const ShStep stp = s_steps[j];
+                    const bool in_cur = j < prm.nsteps_cur, in_last = j < prm.nsteps_last;
+                    float2 A[2][2];  // [cur/last][stream]
 #pragma unroll
-                for (int a = 0; a < RTB_QC; ++a) {
-                    const float4 h = s_h[c & 1][jj][a][lane];
+                    for (int st = 0; st < 2; ++st) {
+                        float2 z = zz[st];
+                        if (stp.term) z.y = -z.y;
+                        const float2 pc = in_cur ? phase_of(s_cs[warp][st][0], stp.m) : make_float2(0.f, 0.f);
+                        const float2 pl = in_last ? phase_of(s_cs[warp][st][1], stp.m) : make_float2(0.f, 0.f);
+                        A[0][st] = cmul(pc, z);
+                        A[1][st] = cmul(pl, z);
+                    }
 #pragma unroll
-                    for (int cl = 0; cl < 2; ++cl)
+                    for (int a = 0; a < RTB_QC; ++a) {
+                        const float4 h = s_h[c & 1][jj][a][lane];
 #pragma unroll
-                        for (int st = 0; st < 2; ++st) {
-                            cfma(acc[a][0][cl][st], make_float2(h.x, h.y), A[cl][st]);
-                            cfma(acc[a][1][cl][st], make_float2(h.z, h.w), A[cl][st]);
-                        }
+                        for (int cl = 0; cl < 2; ++cl)
+#pragma unroll
+                            for (int st = 0; st < 2; ++st) {
+                                cfma(acc[a][0][cl][st], make_float2(h.x, h.y), A[cl][st]);
+                                cfma(acc[a][1][cl][st], make_float2(h.z, h.w), A[cl][st]);
+                            }
+                    }
                 }
             }
         }
