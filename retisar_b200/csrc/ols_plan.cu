@@ -514,9 +514,13 @@ int rtb_ols_plan_create(rtb_ols_plan **out, int device, int n_streams, int block
                         err = cudaMalloc(&p->d_Y[ch], sizeof(float) * (size_t)p->F * p->tc_Jc[ch] * spad);
                 }
                 if (err != cudaSuccess) {
-                    rtb_ols_plan_destroy(p);
-                    return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
-                                "plan allocation failed: %s", cudaGetErrorString(err));
+                    // the spectra buffers of very large batches may not fit: keep the SIMT kernel
+                    for (auto &q : p->d_histT) { cudaFree(q); q = nullptr; }
+                    for (auto &q : p->d_bmat) { cudaFree(q); q = nullptr; }
+                    for (auto &q : p->d_Y) { cudaFree(q); q = nullptr; }
+                    p->tc_mono = false;
+                    (void)cudaGetLastError();
+                    err = cudaSuccess;
                 }
             }
         }
