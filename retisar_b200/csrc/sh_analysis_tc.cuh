@@ -15,8 +15,8 @@
 // (tools/tc_rate.cu: a K = 8 TF32 MMA takes max(48, N/2) cycles, i.e. for N <= 96 it is bound by
 // the 4 KB A-operand fetch from shared memory).
 //
-// Warp-specialised, persistent (one CTA per SM, 13 warps):
-//   warps 0-7   loaders: four pairs of warps, each with its own full / empty mbarriers, running out
+// Warp-specialised, persistent (one CTA per SM, 2 * RTB_TC_LG + 5 = 13 warps):
+//   warps 0-7   loaders: RTB_TC_LG = four pairs of warps, each with its own full / empty mbarriers, running out
 //               of phase -- 16-byte row loads, TF32 split, conflict-free transposed stores,
 //               fence.proxy.async, arrive on the stage's `full` mbarrier
 //   warp 12     MMA issuer: warp-uniform loop, one elected lane issues the MMAs of a stage and
@@ -101,7 +101,13 @@ static __device__ long long g_tc_trace[4096];
 
 #define RTB_TC_M 128
 #define RTB_TC_KC 32       // channels per pipeline chunk (operand stage): 16 per warp of a loader pair
-#define RTB_TC_THREADS 416
+#ifndef RTB_TC_LG
+// loader groups (pairs of warps), each with 16 KB of loads in flight.  Measured with 6 groups (17 warps,
+// 96 KB in flight): c5 343 vs 356 us, c2 10 240 streams 99 vs 106 us, but c2 1 024 streams 22.3 vs
+// 21.8 us and c4 61.3 vs 59.9 us; 8 groups (80 registers, spills): slower everywhere.
+#define RTB_TC_LG 4
+#endif
+#define RTB_TC_THREADS (32 * (2 * RTB_TC_LG + 5))   // loaders, 4 epilogue warps, MMA issuer
 #define RTB_TC_MAX_ST 4    // operand stages (ring)
 // Where the generic-proxy -> async-proxy fence between the loaders' st.shared and the tensor core's
 // operand reads sits.  nvcc lowers fence.proxy.async to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the
@@ -138,7 +144,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
     float *b_hi = a_stage + (size_t)nst * 2 * KC * RTB_TC_M;
     float *b_lo = b_hi + (size_t)Kres * Npad;
     const size_t bchunk_floats = (size_t)KC * Npad;         // one K-chunk of hi (or lo)
-    __shared__ __align__(8) uint64_t full_bar[RTB_TC_MAX_ST], empty_bar[RTB_TC_MAX_ST], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[RTB_TC_LG], empty_bar[RTB_TC_LG], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     // warp index through a shuffle: provably warp-uniform, so that the role branches are uniform and
     // the MMA issuer's descriptors live in uniform registers (with `tid >> 5` and an `if (lane == 0)`
@@ -153,7 +159,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             reinterpret_cast<float4 *>(b_lo)[i] = __ldg(reinterpret_cast<const float4 *>(bsrc + (size_t)Kpad * Npad) + i);
         }
     if (tid == 0) {
-        for (int i = 0; i < RTB_TC_MAX_ST; ++i) {
+        for (int i = 0; i < RTB_TC_LG; ++i) {
             // one arrival per warp of the loader group (+ the expect_tx arrival of the B chunk)
             mbar_init(&full_bar[i], 2 + (STREAM_B ? 1 : 0));
             mbar_init(&empty_bar[i], 1);   // tcgen05.commit
@@ -185,7 +191,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
     const size_t stage_floats = (size_t)2 * KC * RTB_TC_M;
     const int log2B = 31 - __clz(B);  // block lengths are powers of two
 
-    if (warp < 8) {
+    if (warp < 2 * RTB_TC_LG) {
         // ===== loaders.  A stage (32 channels x 128 rows) is filled by a group of warps (a PAIR with 16
         // channels each when there are four stages); group p takes the units n = p, p + nst, ...  Lane l owns rows 4l .. 4l+3 of the stage (one
         // 16-byte load per channel: a warp request covers the 512 contiguous bytes of a channel row).
@@ -209,7 +215,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
         const int pair = warp >> 1, sub = warp & 1;        // loader group, warp in the group
         const int rot = (lane >> 1) & 3;
         const bool r1 = rot & 1, r2 = rot & 2;
-        for (long long n = pair; n < my_units; n += 4) {
+        for (long long n = pair; n < my_units; n += RTB_TC_LG) {
             const long long it = n / n_chunks;
             const int h = (int)(n - it * n_chunks);
             const long long g = ((long long)blockIdx.x + it * gridDim.x) * RTB_TC_M + 4 * lane;
@@ -229,7 +235,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             // k-th unit of this group: its stage was last used by unit n - nst, whose completion is
             // commit number k (groups that start on a fresh stage) or k + 1 (the others) on this
             // group's `empty` barrier
-            const unsigned k = (unsigned)(n >> 2);
+            const unsigned k = (unsigned)(n / RTB_TC_LG);
             const unsigned par = (pair < nst) ? ((k & 1) ^ 1) : (k & 1);
             if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 0);
             mbar_wait(&empty_bar[pair], par);
@@ -274,7 +280,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             if (lane == 0) mbar_arrive(&full_bar[pair]);
             if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 2);
         }
-    } else if (warp == 12) {
+    } else if (warp == 2 * RTB_TC_LG + 4) {
         // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues
         // hi*hi + lo*hi + hi*lo per stage, accumulating in TMEM
         {
@@ -294,7 +300,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                     const int ksteps = min(KC / 8, (C - h * KC + 7) / 8);  // the last chunk may be short
                     {
                         const uint32_t d_tmem = tmem + acc * acc_cols;
-                        mbar_wait(&full_bar[mm & 3], (unsigned)((mm >> 2) & 1));
+                        mbar_wait(&full_bar[mm % RTB_TC_LG], (unsigned)((mm / RTB_TC_LG) & 1));
                         if (h == 0 && lane == 0) TC_STAMP(2, (int)it, 2);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #if !RTB_TC_FENCE_WRITER
@@ -324,7 +330,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                                                   (h | pass | ks) ? 1u : 0u);
                             }
                             // the stage is free once these MMAs have read it: tell its next user
-                            umma_commit(&empty_bar[(mm + nst) & 3]);
+                            umma_commit(&empty_bar[(mm + nst) % RTB_TC_LG]);
                             if (h == n_chunks - 1) umma_commit(&tfull_bar[acc]);
                         }
                         __syncwarp();
