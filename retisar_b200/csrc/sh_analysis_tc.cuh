@@ -104,10 +104,13 @@ static __device__ long long g_tc_trace[4096];
 #ifndef RTB_TC_LG
 // loader groups (pairs of warps), each with 16 KB of loads in flight.  Measured with 6 groups (17 warps,
 // 96 KB in flight): c5 343 vs 356 us, c2 10 240 streams 99 vs 106 us, but c2 1 024 streams 22.3 vs
-// 21.8 us and c4 61.3 vs 59.9 us; 8 groups (80 registers, spills): slower everywhere.
+// 21.8 us and c4 61.3 vs 59.9 us; 8 groups (80 registers, spills): slower everywhere.  The launch
+// picks RTB_TC_LG_BIG groups when every CTA has many tiles (sh_plan.cu: launch_analysis).
 #define RTB_TC_LG 4
 #endif
-#define RTB_TC_THREADS (32 * (2 * RTB_TC_LG + 5))   // loaders, 4 epilogue warps, MMA issuer
+#define RTB_TC_LG_BIG 6     // for launches with many tiles per CTA (chosen at launch)
+#define RTB_TC_THREADS_OF(LG) (32 * (2 * (LG) + 5))   // loaders, 4 epilogue warps, MMA issuer
+#define RTB_TC_THREADS RTB_TC_THREADS_OF(RTB_TC_LG)
 #define RTB_TC_MAX_ST 4    // operand stages (ring)
 // Where the generic-proxy -> async-proxy fence between the loaders' st.shared and the tensor core's
 // operand reads sits.  nvcc lowers fence.proxy.async to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the
@@ -128,8 +131,8 @@ __device__ __forceinline__ float4 ldg_nc_v4_pred(const float *p, bool pred) {
     return __ldg(reinterpret_cast<const float4 *>(pred ? p : reinterpret_cast<const float *>(&g_tc_zero4)));
 }
 
-template <bool STREAM_B>
-__global__ void __launch_bounds__(RTB_TC_THREADS, 1)
+template <bool STREAM_B, int LG = RTB_TC_LG>
+__global__ void __launch_bounds__(RTB_TC_THREADS_OF(LG), 1)
 sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                       const float *__restrict__ bsrc,  // [2][Kpad/4][Npad/8][8][4]: hi then lo
                       float *__restrict__ zcur,        // [S][J][B]
@@ -144,7 +147,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
     float *b_hi = a_stage + (size_t)nst * 2 * KC * RTB_TC_M;
     float *b_lo = b_hi + (size_t)Kres * Npad;
     const size_t bchunk_floats = (size_t)KC * Npad;         // one K-chunk of hi (or lo)
-    __shared__ __align__(8) uint64_t full_bar[RTB_TC_LG], empty_bar[RTB_TC_LG], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[LG], empty_bar[LG], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     // warp index through a shuffle: provably warp-uniform, so that the role branches are uniform and
     // the MMA issuer's descriptors live in uniform registers (with `tid >> 5` and an `if (lane == 0)`
@@ -154,12 +157,12 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
     if (!STREAM_B)
-        for (int i = tid; i < Kres * Npad / 4; i += RTB_TC_THREADS) {
+        for (int i = tid; i < Kres * Npad / 4; i += RTB_TC_THREADS_OF(LG)) {
             reinterpret_cast<float4 *>(b_hi)[i] = __ldg(reinterpret_cast<const float4 *>(bsrc) + i);
             reinterpret_cast<float4 *>(b_lo)[i] = __ldg(reinterpret_cast<const float4 *>(bsrc + (size_t)Kpad * Npad) + i);
         }
     if (tid == 0) {
-        for (int i = 0; i < RTB_TC_LG; ++i) {
+        for (int i = 0; i < LG; ++i) {
             // one arrival per warp of the loader group (+ the expect_tx arrival of the B chunk)
             mbar_init(&full_bar[i], 2 + (STREAM_B ? 1 : 0));
             mbar_init(&empty_bar[i], 1);   // tcgen05.commit
@@ -191,7 +194,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
     const size_t stage_floats = (size_t)2 * KC * RTB_TC_M;
     const int log2B = 31 - __clz(B);  // block lengths are powers of two
 
-    if (warp < 2 * RTB_TC_LG) {
+    if (warp < 2 * LG) {
         // ===== loaders.  A stage (32 channels x 128 rows) is filled by a group of warps (a PAIR with 16
         // channels each when there are four stages); group p takes the units n = p, p + nst, ...  Lane l owns rows 4l .. 4l+3 of the stage (one
         // 16-byte load per channel: a warp request covers the 512 contiguous bytes of a channel row).
@@ -215,7 +218,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
         const int pair = warp >> 1, sub = warp & 1;        // loader group, warp in the group
         const int rot = (lane >> 1) & 3;
         const bool r1 = rot & 1, r2 = rot & 2;
-        for (long long n = pair; n < my_units; n += RTB_TC_LG) {
+        for (long long n = pair; n < my_units; n += LG) {
             const long long it = n / n_chunks;
             const int h = (int)(n - it * n_chunks);
             const long long g = ((long long)blockIdx.x + it * gridDim.x) * RTB_TC_M + 4 * lane;
@@ -235,7 +238,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             // k-th unit of this group: its stage was last used by unit n - nst, whose completion is
             // commit number k (groups that start on a fresh stage) or k + 1 (the others) on this
             // group's `empty` barrier
-            const unsigned k = (unsigned)(n / RTB_TC_LG);
+            const unsigned k = (unsigned)(n / LG);
             const unsigned par = (pair < nst) ? ((k & 1) ^ 1) : (k & 1);
             if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 0);
             mbar_wait(&empty_bar[pair], par);
@@ -280,7 +283,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             if (lane == 0) mbar_arrive(&full_bar[pair]);
             if (lane == 0 && sub == 0) TC_STAMP(0, (int)n, 2);
         }
-    } else if (warp == 2 * RTB_TC_LG + 4) {
+    } else if (warp == 2 * LG + 4) {
         // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues
         // hi*hi + lo*hi + hi*lo per stage, accumulating in TMEM
         {
@@ -300,7 +303,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                     const int ksteps = min(KC / 8, (C - h * KC + 7) / 8);  // the last chunk may be short
                     {
                         const uint32_t d_tmem = tmem + acc * acc_cols;
-                        mbar_wait(&full_bar[mm % RTB_TC_LG], (unsigned)((mm / RTB_TC_LG) & 1));
+                        mbar_wait(&full_bar[mm % LG], (unsigned)((mm / LG) & 1));
                         if (h == 0 && lane == 0) TC_STAMP(2, (int)it, 2);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #if !RTB_TC_FENCE_WRITER
@@ -330,7 +333,7 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                                                   (h | pass | ks) ? 1u : 0u);
                             }
                             // the stage is free once these MMAs have read it: tell its next user
-                            umma_commit(&empty_bar[(mm + nst) % RTB_TC_LG]);
+                            umma_commit(&empty_bar[(mm + nst) % LG]);
                             if (h == n_chunks - 1) umma_commit(&tfull_bar[acc]);
                         }
                         __syncwarp();
