@@ -326,6 +326,63 @@ __device__ __forceinline__ void fft512_r16(float2 (&X)[16], float2 *buf, const f
     for (int u = 0; u < 16; ++u) X[u] = Y[u];
 }
 
+// The same idea for 128 points on half a warp (64-sample blocks: 16 lanes x 8 elements) as 8 x 8 x 2:
+// one exchange through shared memory (placement i ^ (i / 8) % 16: writes 8 l + t and reads l + 16 u
+// are conflict free per group), then a swap of four values with lane l ^ 8 and the radix-2 pass.
+#ifndef RTB_FFT_R8X2
+#define RTB_FFT_R8X2 1
+#endif
+template <bool INV, class Sync, class Hook>
+__device__ __forceinline__ void fft128_r8(float2 (&X)[8], float2 *buf, const float2 *tw, int l,
+                                          Sync &&sync, Hook &&after_last_exchange) {
+    dft8<INV>(X);  // pass A: radix 8, NS = 1; output t of lane l -> position 8 l + t
+    {
+        const unsigned pre = smem_addr32(buf) + 8u * (unsigned)((8 * l) ^ l);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sts64(pre ^ (8u * t), X[t]);
+    }
+    sync();
+    {
+        const unsigned pre = smem_addr32(buf) + 8u * (unsigned)(l ^ (l >> 3));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) X[u] = lds64((pre ^ (8u * ((2 * u) & 15))) + 128u * u);
+    }
+    sync();
+    after_last_exchange();
+    {   // pass B: radix 8, NS = 8: k = l % 8, w = exp(-+2 pi i k / 64) = tw[2 k]
+        float2 w = tw[2 * (l & 7)];
+        if (INV) w.y = -w.y;
+        float2 wp = w;
+#pragma unroll
+        for (int t = 1; t < 8; ++t) {
+            X[t] = cmul(X[t], wp);
+            if (t < 7) wp = cmul(wp, w);
+        }
+    }
+    dft8<INV>(X);
+    // output t of lane l sits at position (l / 8) 64 + l % 8 + 8 t; the radix-2 pass (NS = 64) of lane l
+    // needs elements l + 16 b and l + 16 b + 64, b < 4: t = l / 8 + 2 b in lanes l % 8 and l % 8 + 8
+    const bool upper = l >= 8;
+    float2 wl = tw[l];
+    if (INV) wl.y = -wl.y;
+    float2 Y[8];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const float2 even = X[2 * b], odd = X[2 * b + 1];
+        const float2 send = upper ? even : odd;
+        float2 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 8);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 8);
+        const float2 v0 = upper ? recv : even;
+        float2 v1 = upper ? odd : recv;
+        v1 = cmul(v1, cmul_w16<INV>(wl, 2 * b));
+        Y[b] = cadd(v0, v1);
+        Y[b + 4] = csub(v0, v1);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) X[u] = Y[u];
+}
+
 // In-register transform of the group's points.  `buf` = this group's REGION of shared memory,
 // `tw` = exp(-2*pi*i*q/LEN), q < LEN (shared or global memory), l = lane index inside the group.
 // All lanes of the group must call it together.  `after_last_exchange()` runs once the exchange
@@ -337,6 +394,10 @@ __device__ __forceinline__ void fft_run_c(float2 (&X)[Cfg::EPL], float2 *buf, co
     constexpr bool TAIL = Cfg::R_LAST != 0;
     if constexpr (RTB_FFT_R16 && Cfg::LEN == 512 && Cfg::G == 32 && Cfg::EPL == 16) {
         fft512_r16<INV>(X, buf, tw, l, sync, after_last_exchange);
+        return;
+    }
+    if constexpr (RTB_FFT_R8X2 && Cfg::LEN == 128 && Cfg::G == 16 && Cfg::EPL == 8) {
+        fft128_r8<INV>(X, buf, tw, l, sync, after_last_exchange);
         return;
     }
     fft_pass_c<Cfg, 8, 1, INV, true, AL>(X, buf, tw, l);
