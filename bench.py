@@ -2,19 +2,26 @@
 """Benchmark of the per-block binaural rendering chain (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|c5|c4] [--streams S]
+                    [--workload c2|c5|c3|c4|c1] [--streams S] [--no-extras]
 
 A "step" is one block (256 samples at 48 kHz for c2) of S batched, independent render streams
 with their own head yaw.  One JSON line is printed by rank 0:
 
   value      real-time streams sustained = stream-blocks per second / (fs / B), whole job,
-             inputs resident in HBM, K steps back to back (device time, max over ranks)
-  e2e        same metric through ``AdjustableShConvolver.filter_block`` with pinned HOST buffers:
-             H2D copy of the block, render, D2H copy of the ear signals inside the timed region
+             inputs resident in HBM, exactly K steps back to back (device time, max over ranks)
+  e2e        same metric through the public host-buffer API (`AdjustableShConvolver.submit_block`
+             / `.result()`, pinned HOST buffers): H2D copy of every block, render, D2H copy of the
+             ear signals inside the timed region; `e2e.sync` = plain `filter_block` per block
   roofline   dominant kernel (the render kernel), timed live with CUDA events on its stream
+  sweep      S in {1024, 4096, 10240}: ms per step and p99 block latency (>= 500 latency steps)
+  held       largest S whose p99 block latency stays below 1 ms / below the block period
+             (the reference's own criterion "no dropouts", `_run_benchmark.py:311-321`)
+  fdl        roofline of the FDL kernel `ols_fdl_kernel` (north-star target: >= 60 % of HBM)
+  scaling_c5 BASELINE config 5 (order 8, 8192 streams per GPU) measured in the same run
   cpu_baseline / --impl reference
-             the numpy oracle (a line-by-line restatement of the reference's numpy path, kind
-             "port": the reference is pure Python and cannot travel to the GPU box) on host cores
+             the UNMODIFIED reference's `AdjustableShConvolver.filter_block` (staged into
+             oracle/_ref by build(); kind "reference") on the host cores, one process per core;
+             falls back to the numpy oracle (kind "port") when no staged copy exists
 """
 import argparse
 import json
@@ -37,76 +44,127 @@ if ROOT not in sys.path:
 
 METRIC = "real-time binaural streams @48kHz/256-blk per GPU; p99 block latency"
 UNIT = "realtime_streams"
+HRIR_DIRS = 2702  # the reference's default HRIR set (`config.py:48`), both arms
+
+
+def workload_config(workload, streams):
+    """`config` of the JSON line -- identical for both arms (the driver compares them)."""
+    from retisar_b200 import workloads as wl
+
+    c = wl.CONFIGS[workload]
+    return {"workload": f"{workload}: {c['desc']}", "streams_per_gpu": streams,
+            "block_length": c["block"], "fs": wl.FS, "sh_order": c["order"],
+            "hrir_directions": HRIR_DIRS, "crossfade": True}
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference, one process per host core
+# CPU arm: the unmodified reference (or its numpy port), one process per host core
 # ------------------------------------------------------------------------------------------------
+def _reference_kind(workload):
+    """"reference" when the unmodified package is importable and supports the workload."""
+    from retisar_b200 import workloads as wl
+
+    try:
+        from oracle import ref_harness as rh
+    except ImportError:
+        return "port"
+    c = wl.CONFIGS[workload]
+    if not rh.reference_available() or c["hrir_taps"] > c["block"]:  # the reference refuses P > 1
+        return "port"
+    return "reference"
+
+
 def _cpu_worker(args):
-    """Render `n_blocks` blocks of one stream with the oracle; returns seconds per block."""
-    workload, n_blocks, warm, seed = args
-    from oracle import sh_chain as oc
+    """Render `n_blocks` blocks of one stream on one core; returns seconds per block."""
+    workload, n_blocks, warm, seed, kind = args
     from retisar_b200 import synthetic as syn
     from retisar_b200 import workloads as wl
 
-    tb = wl.sh_tables(workload, hrir_dirs=400)
-    cfg = tb["sh_config"]
-    tb["hrir_set"].calculate_filter_blocks_fd(tb["B"])
-    tb["hrir_set"].calculate_filter_blocks_nm()
-    hnm = tb["hrir_set"].get_filter_blocks_nm()
-    cls = oc.ShOracle if hnm.shape[0] == 1 else oc.ShPartitionedOracle
-    o = cls(cfg.sh_m, cfg.sh_bases_weighted, hnm, tb["B"], tb["order"])
-    x = syn.noise_blocks(8, tb["C"], tb["B"], seed)
+    c = wl.CONFIGS[workload]
+    B, order = c["block"], c["order"]
+    az, co, w = wl._grid(c["grid"])
+    haz, hco = syn.random_sphere_grid(HRIR_DIRS, 7)
+    hrir_td = syn.decaying_noise_irs((HRIR_DIRS, 2, c["hrir_taps"]), 8)
+    x = syn.noise_blocks(8, len(az), B, seed)
     yaw = syn.yaw_walk(warm + n_blocks, seed + 1)
+    if kind == "reference":
+        # the reference's own classes, imported unmodified (oracle/ref_harness.py)
+        from oracle import ref_harness as rh
+
+        ref = rh.import_reference()
+        arr = rh.make_miro_filter_set(np.zeros((1, len(az), B), np.float32), az, co, w, order,
+                                      is_hrir=False, block_length=B)
+        hrir = rh.make_miro_filter_set(hrir_td, haz, hco, None, order, is_hrir=True, block_length=B)
+        hrir.calculate_filter_blocks_fd(B)
+        tracker = rh.make_tracker()
+        conv = rh.make_sh_convolver(hrir, arr, B, tracker)
+        azim = ref.HeadTracker.DataIndex.AZIM
+
+        def block(i, y):
+            tracker[azim] = float(y)
+            return conv.filter_block(x[i % 8].copy())  # the JACK client hands over a fresh copy
+    else:
+        from oracle import sh_chain as oc
+
+        tb = wl.sh_tables(workload, hrir_dirs=HRIR_DIRS)
+        cfg = tb["sh_config"]
+        tb["hrir_set"].calculate_filter_blocks_fd(B)
+        tb["hrir_set"].calculate_filter_blocks_nm()
+        hnm = tb["hrir_set"].get_filter_blocks_nm()
+        cls = oc.ShOracle if hnm.shape[0] == 1 else oc.ShPartitionedOracle
+        o = cls(cfg.sh_m, cfg.sh_bases_weighted, hnm, B, order)
+
+        def block(i, y):
+            return o.filter_block(x[i % 8], y)
     for i in range(warm):
-        o.filter_block(x[i % 8], yaw[i])
+        block(i, yaw[i])
     t0 = time.perf_counter()
     for i in range(n_blocks):
-        o.filter_block(x[i % 8], yaw[warm + i])
+        block(i, yaw[warm + i])
     return (time.perf_counter() - t0) / n_blocks
 
 
 def cpu_arm(workload, cores, n_blocks, warm=50):
-    """Streams the host sustains in real time with `cores` independent oracle processes."""
+    """Streams the host sustains in real time with `cores` independent single-stream processes."""
     import multiprocessing as mp
 
     from retisar_b200 import workloads as wl
 
-    c = wl.CONFIGS[workload]
-    block_period = c["block"] / wl.FS
+    kind = _reference_kind(workload)
+    block_period = wl.CONFIGS[workload]["block"] / wl.FS
+    jobs = [(workload, n_blocks, warm, i, kind) for i in range(cores)]
     if cores == 1:
-        per_block = [_cpu_worker((workload, n_blocks, warm, 0))]
+        per_block = [_cpu_worker(jobs[0])]
     else:
         with mp.get_context("fork").Pool(cores) as pool:
-            per_block = pool.map(_cpu_worker, [(workload, n_blocks, warm, i) for i in range(cores)])
+            per_block = pool.map(_cpu_worker, jobs)
     streams = sum(block_period / t for t in per_block)
-    return streams, float(np.mean(per_block))
+    sec = float(np.mean(per_block))
+    what = ("the UNMODIFIED reference AdjustableShConvolver.filter_block (oracle/_ref, np.fft branch)"
+            if kind == "reference" else "the numpy oracle (port of the reference)")
+    sample = (f"{cores} processes x 1 stream x {n_blocks} blocks of {what}, BLAS threads = 1, "
+              f"{HRIR_DIRS} HRIR directions, {sec * 1e6:.0f} us/block/stream")
+    return streams, sec, kind, sample
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    from retisar_b200 import workloads as wl
-
-    cores = os.cpu_count() or 1
-    c = wl.CONFIGS[args.workload]
-    n_blocks = max(200, min(args.steps, 3000))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n_blocks = 4000  # bounded sample: about one second of rendering per core plus set-up
     t0 = time.perf_counter()
-    streams, sec_per_block = cpu_arm(args.workload, cores, n_blocks, warm=max(args.warmup, 3))
+    streams, sec, kind, sample = cpu_arm(args.workload, cores, n_blocks, warm=max(args.warmup, 3) * 10)
     wall = time.perf_counter() - t0
-    sample = (f"{cores} processes x 1 stream x {n_blocks} blocks of the numpy oracle "
-              f"(np.fft, BLAS threads = 1), {sec_per_block * 1e6:.0f} us/block/stream")
     line = {
         "impl": "reference", "metric": METRIC, "value": streams, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec_per_block * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {c['desc']}", "streams": cores,
-                   "block_length": c["block"], "fs": wl.FS},
-        "cpu_baseline": {"value": streams, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+        "config": workload_config(args.workload, args.streams),
+        "cpu_baseline": {"value": streams, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": streams, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "step_definition": f"one bounded sample = {n_blocks} blocks of one stream per core; "
+                           f"ms_per_step = mean time of one block of one stream",
         "wall_s": wall,
     }
     print(json.dumps(line), flush=True)
@@ -160,19 +218,133 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+class Rig:
+    """One renderer with S streams and its HBM-resident input ring (larger than L2)."""
+
+    def __init__(self, tb, S, dev, seed, min_ring_bytes=160e6):
+        import torch
+
+        from retisar_b200 import workloads as wl
+
+        self.tb, self.S, self.dev = tb, S, dev
+        self.B, self.C, self.E = tb["B"], tb["C"], 2
+        self.conv = wl.make_renderer(tb, S, device=dev.index)
+        self.plan = self.conv._plan
+        self.in_bytes = S * self.C * self.B * 4
+        self.ring = max(2, int(np.ceil(min_ring_bytes / self.in_bytes)) + 1)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        self.x_ring = torch.empty((self.ring, S, self.C, self.B), device=dev, dtype=torch.float32)
+        for r in range(self.ring):  # block by block: no second copy of a multi-GB ring
+            self.x_ring[r].normal_(0.0, 0.1, generator=gen)
+        yaw0 = torch.rand((S,), generator=gen, device=dev) * 360.0
+        self.yaw_ring = torch.stack([yaw0 + 1.5 * i for i in range(self.ring)]).contiguous()
+        self.out = torch.empty((S, self.E, self.B), device=dev, dtype=torch.float32)
+        self.stream = torch.cuda.current_stream(dev)
+        self.n_done = 0
+
+    def run(self, count):
+        """`count` consecutive blocks enqueued by ONE library call (no Python between the launches)."""
+        self.plan.process_blocks_device(self.x_ring, self.yaw_ring, self.out, self.n_done, count, self.stream)
+        self.n_done += count
+
+    def timed(self, count):
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        self.run(count)
+        e1.record(self.stream)
+        return e0, e1
+
+    def latencies(self, n, flush=None):
+        """Per-block device time of n blocks, one at a time; L2 is flushed before every block
+        unless a single input block already exceeds it."""
+        import torch
+
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(n)]
+        for a, b in evs:
+            if flush is not None:
+                flush.add_(1.0)
+            a.record(self.stream)
+            self.run(1)
+            b.record(self.stream)
+        torch.cuda.synchronize(self.dev)
+        return np.array([a.elapsed_time(b) for a, b in evs])
+
+    def close(self):
+        self.conv._plan.close()
+        del self.x_ring, self.yaw_ring, self.out
+
+
+def _percentiles(lat):
+    return {k: float(np.percentile(lat, q)) for k, q in (("p50", 50), ("p99", 99), ("max", 100))}
+
+
+def measure_fdl(dev, peaks, S, taps, B, n_ch=2, steps=100):
+    """Roofline of `ols_fdl_kernel` on the reference benchmark's own shape (2-in / 2-out FIR)."""
+    import torch
+
+    from retisar_b200 import _capi
+    from retisar_b200.plans import OlsPlan
+
+    P, F = -(-taps // B), B + 1
+    Fp = (F + 3) // 4 * 4
+    rng = np.random.default_rng(0)
+    irs = (rng.standard_normal((n_ch, P * B)) * 0.05 * np.exp(-np.arange(P * B) / (P * B / 6))).astype(np.float32)
+    H = np.stack([np.fft.rfft(irs[:, p * B:(p + 1) * B], 2 * B) for p in range(P)]).astype(np.complex64)
+    plan = OlsPlan(S, B, n_ch, n_ch, P, device=dev.index)
+    plan.set_filter(H)
+    ring = max(2, int(np.ceil(160e6 / (S * n_ch * B * 4))) + 1)
+    x = torch.randn((ring, S, n_ch, B), device=dev) * 0.1
+    out = torch.empty((S, n_ch, B), device=dev)
+    st = torch.cuda.current_stream(dev)
+    for i in range(P + 4):
+        plan.process_device(x[i % ring], out, st)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(steps):
+        plan.process_device(x[i % ring], out, st)
+    e1.record(st)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    plan.set_profiling(True)
+    ks = []
+    for i in range(30):
+        plan.process_device(x[i % ring], out, st)
+        ks.append(plan.query(_capi.RTB_Q_RENDER_NS))
+    plan.close()
+    us = float(np.mean(ks)) / 1e3
+    # input-side delay line: read P stored spectra, write one; previous + current input block in,
+    # state and output out (DESIGN.md K-C)
+    bytes_per = 8 * Fp * n_ch * P + 4 * B * (3 * n_ch + n_ch)
+    ach = S * bytes_per / (us * 1e-6) / 1e9
+    return {"kernel": "ols_fdl_kernel", "shape": f"{n_ch}-in/{n_ch}-out, {taps} taps, B = {B}, P = {P}",
+            "streams": S, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": ach / peaks["hbm"], "bytes_per_launch": S * bytes_per, "us_per_launch": us,
+            "ms_per_step": ms, "realtime_convolvers": S / (ms * 1e-3) / (48000 / B),
+            "traffic": peaks["traffic"].get(f"fdl:{taps}:{B}:{S}", {}).get("bytes")}
+
+
 def run_gpu_arm(args):
     import torch
 
     from retisar_b200 import _capi
     from retisar_b200 import workloads as wl
+    from retisar_b200.distributed import bind_to_gpu_numa_node, gather_streams, max_over_ranks as _max
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU path)")
+    orig_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host side of the e2e leg: this rank's feeder thread and its page-locked buffers next to its GPU
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"node": None}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -184,163 +356,250 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    from retisar_b200.distributed import gather_streams, max_over_ranks as _max
-
     def max_over_ranks(v):
         return _max(v, device=dev)
 
+    peaks_file = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks_file = json.load(f)
+    except OSError:
+        pass
+    traffic_tab = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic_tab = json.load(f)
+    except (OSError, ValueError):
+        pass
+    peaks = {"hbm": float(peaks_file.get("hbm_gbs", 6650.0)), "traffic": traffic_tab,
+             "source": "measured (MEASURED_PEAKS.json)" if peaks_file else "fallback (B200_PROFILING.md)"}
+
     S, K, W = args.streams, args.steps, max(args.warmup, 3)
-    tb = wl.sh_tables(args.workload)
+    tb = wl.sh_tables(args.workload, hrir_dirs=HRIR_DIRS)
     B, C, E = tb["B"], tb["C"], 2
-    conv = wl.make_renderer(tb, S, device=local_rank)
-    plan = conv._plan
     block_rate = wl.FS / B  # blocks per second of one real-time stream
-
-    # inputs resident in HBM: a ring of distinct blocks larger than L2 (126 MB), so every timed
-    # step reads its block from DRAM without an explicit flush
-    in_bytes = S * C * B * 4
-    ring = max(4, int(np.ceil(160e6 / in_bytes)) + 1)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    x_ring = torch.randn((ring, S, C, B), generator=gen, device=dev, dtype=torch.float32) * 0.1
-    yaw0 = torch.rand((S,), generator=gen, device=dev) * 360.0
-    yaw_ring = torch.stack([yaw0 + 1.5 * i for i in range(ring)]).contiguous()
-    out = torch.empty((S, E, B), device=dev, dtype=torch.float32)
-    stream = torch.cuda.current_stream(dev)
-
-    def step(i):
-        plan.process_device(x_ring[i % ring], yaw_ring[i % ring], out, stream)
+    flush = torch.empty(int(256e6) // 4, device=dev, dtype=torch.float32)
+    rig = Rig(tb, S, dev, 1234 + rank)
+    plan, conv = rig.plan, rig.conv
 
     # ---- device-resident throughput: W warm-up, then exactly K steps between barriers
-    for i in range(W):
-        step(i)
+    rig.run(W)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = plan.query(_capi.RTB_Q_LAUNCHES)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(K):
-        step(W + i)
-    e1.record(stream)
+    e0, e1 = rig.timed(K)
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = plan.query(_capi.RTB_Q_LAUNCHES) - launches0
     value = world * S * K / (dev_ms * 1e-3) / block_rate
 
     # ---- block latency: per-step events, L2 flushed before every step
-    n_lat = min(K, 2000)
-    flush = torch.empty(int(256e6) // 4, device=dev, dtype=torch.float32)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(n_lat)]
-    for i, (a, b) in enumerate(evs):
-        flush.add_(1.0)
-        a.record(stream)
-        step(i)
-        b.record(stream)
-    torch.cuda.synchronize()
-    lat = np.array([a.elapsed_time(b) for a, b in evs])
-    lat_p50, lat_p99, lat_max = (float(np.percentile(lat, q)) for q in (50, 99, 100))
-    lat_p99 = max_over_ranks(lat_p99)
+    n_lat = max(500, min(K, 2000))
+    lat = rig.latencies(n_lat, flush)
+    pct = _percentiles(lat)
+    lat_p99 = max_over_ranks(pct["p99"])
 
-    # ---- per-kernel device time (CUDA events inside the library, on the launching stream)
+    # ---- per-kernel device time (CUDA events inside the library, on the launching stream); blocks
+    # one at a time from the same > L2 input ring as the timed loop, no flush in between
     plan.set_profiling(True)
     k_an, k_re = [], []
-    for i in range(min(K, 200)):
-        flush.add_(1.0)
-        step(i)
+    for i in range(100):
+        rig.run(1)
         k_an.append(plan.query(_capi.RTB_Q_ANALYSIS_NS))
         k_re.append(plan.query(_capi.RTB_Q_RENDER_NS))
     plan.set_profiling(False)
     an_us, re_us = float(np.mean(k_an)) / 1e3, float(np.mean(k_re)) / 1e3
 
     # ---- end to end through the public API with pinned host buffers
-    K_e2e = max(10, min(K, 200))
+    K_e2e = max(K, 50)
     hx = torch.randn((4, S, C, B), dtype=torch.float32).mul_(0.1).pin_memory()
     hyaw = (torch.rand((4, S)) * 360.0).pin_memory()
     hx_np, hyaw_np = hx.numpy(), hyaw.numpy()
-    for i in range(3):
+    for i in range(4):
         conv.filter_block(hx_np[i % 4], hyaw_np[i % 4])
     barrier()
     t0 = time.perf_counter()
     acc = 0.0
-    for i in range(K_e2e):
+    for i in range(K_e2e):  # the reference-shaped synchronous call, one block at a time
         y = conv.filter_block(hx_np[i % 4], hyaw_np[i % 4])
         acc += float(y[0, 0, 0])
+    barrier()
+    e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    t0 = time.perf_counter()
+    pending = conv.submit_block(hx_np[0], hyaw_np[0])
+    for i in range(1, K_e2e + 1):  # feeder shape: block t+1 is handed over before block t is collected
+        nxt = conv.submit_block(hx_np[i % 4], hyaw_np[i % 4]) if i < K_e2e else None
+        y = pending.result()
+        acc += float(y[0, 0, 0])
+        pending = nxt
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * S * K_e2e / e2e_s / block_rate
     clocks = sampler.stop() if sampler else None
 
     # ---- gather one output block from every rank (the only collective; off the timed path)
-    gathered = gather_streams(out, dst=0)
+    gathered = gather_streams(rig.out, dst=0)
     if rank == 0 and dist is not None:
         assert gathered.shape[0] == world * S and bool(torch.isfinite(gathered).all())
 
+    J = plan.query(_capi.RTB_Q_ROWS)
+    render_name = _capi.RENDER_KERNEL_NAMES.get(plan.query(_capi.RTB_Q_RENDER_KERNEL), "sh_render_kernel")
+    analysis_name = "sh_analysis_tc_kernel" if plan.query(_capi.RTB_Q_TENSOR_CORE) else "sh_analysis_kernel"
+    in_ring_desc = (f"inputs cycle through a {rig.ring * rig.in_bytes / 1e6:.0f} MB ring of {rig.ring} blocks "
+                    f"(> 126 MB L2); latency steps flush L2 with a 256 MB write")
+    rig.close()
+
+    # ---- extras measured in the same run --------------------------------------------------
+    extras = {}
+    if not args.no_extras:
+        def quick(workload, S_x, n_steps, n_lat_x, seed):
+            tbx = tb if workload == args.workload else wl.sh_tables(workload, hrir_dirs=HRIR_DIRS)
+            r = Rig(tbx, S_x, dev, seed)
+            r.run(max(5, W))
+            torch.cuda.synchronize(dev)
+            a, b = r.timed(n_steps)
+            torch.cuda.synchronize(dev)
+            ms = a.elapsed_time(b) / n_steps
+            fl = flush if r.in_bytes < 256e6 else None
+            p = _percentiles(r.latencies(n_lat_x, fl)) if n_lat_x else None
+            period = 1e3 * tbx["B"] / wl.FS
+            r.close()
+            return ms, p, period
+
+        # BASELINE config 5 beside the headline, at every N (weak scaling: 8192 streams per GPU)
+        barrier()
+        ms5, p5, period5 = quick("c5", 8192, 30, 100, 77 + rank)
+        ms5 = max_over_ranks(ms5)
+        extras["scaling_c5"] = {
+            "workload": "c5: " + wl.CONFIGS["c5"]["desc"], "streams_per_gpu": 8192,
+            "value": world * 8192 / (ms5 * 1e-3) / (wl.FS / 256), "unit": UNIT, "ms_per_step": ms5,
+            "p99_block_latency_ms": max_over_ranks(p5["p99"]), "steps": 30, "latency_steps": 100}
+        if world == 1 and args.workload == "c2":
+            sweep = {}
+            for S_x in (1024, 4096, 10240):
+                ms, p, period = quick("c2", S_x, 200, 500, 5 + S_x)
+                sweep[str(S_x)] = {"ms_per_step": ms, "p99_ms": p["p99"], "p50_ms": p["p50"],
+                                   "max_ms": p["max"], "latency_steps": 500,
+                                   "streams_sustained": S_x / (ms * 1e-3) / block_rate}
+            extras["sweep"] = sweep
+
+            def holds(S_x, limit_ms, n):
+                _, p, _ = quick("c2", S_x, 20, n, 11 + S_x)
+                return p["p99"] < limit_ms, p
+
+            def search(limit_ms, start, step, cap):
+                """Largest S (multiple of `step`) whose p99 over 300 blocks stays below the limit,
+                then confirmed over 2000 consecutive blocks (stepping down while it fails)."""
+                lo, hi = 0, None
+                s = start
+                while hi is None and s <= cap:
+                    ok, _ = holds(s, limit_ms, 300)
+                    if ok:
+                        lo, s = s, int(s * 1.5) // step * step
+                    else:
+                        hi = s
+                if hi is None:
+                    hi = cap + step
+                while hi - lo > step:
+                    mid = (lo + hi) // 2 // step * step
+                    if mid <= lo:
+                        break
+                    ok, _ = holds(mid, limit_ms, 300)
+                    lo, hi = (mid, hi) if ok else (lo, mid)
+                while lo > 0:
+                    ok, p = holds(lo, limit_ms, 2000)
+                    if ok:
+                        return {"streams": lo, "p99_ms": p["p99"], "p50_ms": p["p50"], "max_ms": p["max"],
+                                "limit_ms": limit_ms, "confirmed_blocks": 2000}
+                    lo -= step
+                return {"streams": 0, "limit_ms": limit_ms}
+
+            extras["held"] = {
+                "criterion": "largest S with p99(block device time) below the limit over 2000 consecutive "
+                             "blocks, one block per launch pair, L2 flushed (or input block > L2) "
+                             "between blocks; search in steps of 512 (1 ms) / 4096 (block period)",
+                "p99_below_1ms": search(1.0, 10240, 512, 200000),
+                "p99_below_block_period": search(1e3 / block_rate, 98304, 4096, 400000)}
+            # BASELINE config 1: ONE em32 / order-4 stream, the case the reference runs on a CPU core
+            ms1, p1, _ = quick("c1", 1, 200, 500, 3)
+            one = wl.make_renderer(tb, 1, device=dev.index)
+            xb = (np.random.default_rng(0).standard_normal((C, B)) * 0.1).astype(np.float32)
+            for i in range(20):
+                one.filter_block(xb, [10.0 + i])
+            host_lat = []
+            for i in range(300):
+                t1 = time.perf_counter()
+                one.filter_block(xb, [30.0 + i])
+                host_lat.append((time.perf_counter() - t1) * 1e3)
+            one._plan.close()
+            extras["c1_single_stream"] = {
+                "device_ms_per_block": ms1, "device_p99_ms": p1["p99"],
+                "filter_block_host_p50_ms": float(np.percentile(host_lat, 50)),
+                "filter_block_host_p99_ms": float(np.percentile(host_lat, 99)),
+                "note": "one stream, block latency; filter_block_host = wall time of the synchronous "
+                        "reference-shaped call with a [32,256] numpy block (H2D + 2 kernels + D2H)"}
+            extras["fdl"] = {
+                "target": ">= 60 % of the measured HBM peak on the FDL kernel (north star)",
+                "taps4096_b256": measure_fdl(dev, peaks, 16384, 4096, 256),
+                "hpcf_1024taps_b64": measure_fdl(dev, peaks, 16384, 1024, 64)}
+
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except OSError:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        J = plan.query(_capi.RTB_Q_ROWS)
-        render_name = _capi.RENDER_KERNEL_NAMES.get(plan.query(_capi.RTB_Q_RENDER_KERNEL), "sh_render_kernel")
-        analysis_name = "sh_analysis_tc_kernel" if plan.query(_capi.RTB_Q_TENSOR_CORE) else "sh_analysis_kernel"
         render_bytes = S * (4 * B * (2 * J + E) + 12)  # z rows of 2 blocks in, ear blocks out, yaw
         P = -(-wl.CONFIGS[args.workload]["hrir_taps"] // B)
-        if P > 1:  # a-X: plus both output-side queues [P][E][Fp] c64, read and written once per block
-            render_bytes += S * 2 * 2 * 8 * P * E * ((B + 1 + 3) // 4 * 4)
+        if P > 1:  # a-X: plus both output-side queues [P][E][F] c64, read and written once per block
+            render_bytes += S * 2 * 2 * 8 * P * E * (B + 1)
         analysis_bytes = S * 4 * B * (C + J)
         chain_bytes = S * wl.chain_bytes_per_stream_block(C, B, E)
         chain_flops = S * wl.chain_flops_per_stream_block(C, tb["K"], B, E)
         achieved = render_bytes / (re_us * 1e-6) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(f"{args.workload}:{S}", {}).get("bytes")
-        except (OSError, ValueError):
-            pass
+        traffic = traffic_tab.get(f"{args.workload}:{S}", {}).get("bytes")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {tb['desc']}", "streams_per_gpu": S,
-                       "block_length": B, "fs": wl.FS, "sh_order": tb["order"], "channels": C,
-                       "crossfade": True, "input_ring_blocks": ring,
-                       "l2_policy": f"inputs cycle through a {ring * in_bytes / 1e6:.0f} MB ring "
-                                    f"(> 126 MB L2); latency steps flush L2 with a 256 MB write"},
-            "p99_block_latency_ms": lat_p99, "p50_block_latency_ms": lat_p50,
-            "max_block_latency_ms": lat_max, "block_period_ms": 1e3 / block_rate,
+            "config": workload_config(args.workload, S),
+            "timing": {"input_ring_blocks": rig.ring, "l2_policy": in_ring_desc, "channels": C,
+                       "launch": "the K timed steps are enqueued by one rtb_sh_process_blocks call",
+                       "numa": numa},
+            "p99_block_latency_ms": lat_p99, "p50_block_latency_ms": pct["p50"],
+            "max_block_latency_ms": pct["max"], "block_period_ms": 1e3 / block_rate,
             "latency_steps": n_lat,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * C * B * 4 + S * 4,
                     "d2h_bytes_per_step": S * E * B * 4, "steps": K_e2e,
                     "ms_per_step": e2e_s / K_e2e * 1e3,
-                    "api": "AdjustableShConvolver.filter_block(numpy pinned [S,C,B], yaw[S])"},
+                    "api": "AdjustableShConvolver.submit_block(numpy pinned [S,C,B], yaw[S]) / ticket.result(): "
+                           "block t+1 submitted before block t is collected (feeder shape)",
+                    "sync": {"value": world * S * K_e2e / e2e_sync_s / block_rate,
+                             "ms_per_step": e2e_sync_s / K_e2e * 1e3,
+                             "api": "AdjustableShConvolver.filter_block(numpy pinned [S,C,B], yaw[S])"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": render_name, "achieved": achieved,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
+                         "traffic": traffic, "peak_source": peaks["source"],
                          "bytes_per_launch": render_bytes, "us_per_launch": re_us,
                          "note": "HBM figure as the contract asks; ncu (profiles/) shows this kernel bound by "
-                                 "the L1/shared-memory data pipe (66 %) and the FP32 pipe (47 %), not by HBM; "
-                                 "the HBM-bound kernels are the analysis GEMM ('kernels') and the FDL kernel "
-                                 "(tools/bench_fdl.py, 88 %)"},
+                                 "the L1/shared-memory data pipe and the FP32 pipe, not by HBM; the HBM-bound "
+                                 "kernels are the analysis GEMM ('kernels') and the FDL kernel ('fdl').  "
+                                 "us_per_launch: library events around single blocks read from the same > L2 "
+                                 "input ring as the timed loop (no extra flush)"},
             "kernels": {analysis_name: {"us": an_us, "bytes": analysis_bytes,
-                                        "GBps": analysis_bytes / (an_us * 1e-6) / 1e9},
+                                        "GBps": analysis_bytes / (an_us * 1e-6) / 1e9,
+                                        "frac_hbm": analysis_bytes / (an_us * 1e-6) / 1e9 / peaks["hbm"]},
                         render_name: {"us": re_us, "bytes": render_bytes, "GBps": achieved}},
             "chain": {"bytes_per_step": chain_bytes, "flops_per_step": chain_flops,
                       "GBps": chain_bytes / (dev_ms / K * 1e-3) / 1e9,
                       "TFLOPs_reference_formulation": chain_flops / (dev_ms / K * 1e-3) / 1e12},
         }
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
-            cb_streams, cb_sec = cpu_arm(args.workload, 1, 1500)
-            line["cpu_baseline"] = {
-                "value": cb_streams, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"1 stream x 1500 blocks of the numpy oracle on one host core "
-                          f"({cb_sec * 1e6:.0f} us/block); host has {os.cpu_count()} cores"}
+            if orig_affinity is not None:  # every core the process started with (undo the NUMA binding)
+                os.sched_setaffinity(0, orig_affinity)
+            cores = len(orig_affinity) if orig_affinity is not None else (os.cpu_count() or 1)
+            cb_streams, cb_sec, kind, sample = cpu_arm(args.workload, cores, 2000)
+            line["cpu_baseline"] = {"value": cb_streams, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": sample}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -353,9 +612,12 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5", "c4", "b4096"])
     ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip sweep / held / fdl / scaling_c5 (only the headline line)")
+    ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

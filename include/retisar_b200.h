@@ -42,7 +42,7 @@ int rtb_device_count(void);
 
 /* SH-domain renderer ------------------------------------------------------------------------- */
 /* AdjustableShConvolver.__init__ (_convolver.py:1010-1049) for S batched streams.
- * block_length B in {32, 64, 128, 256}; n_ears must be 2; n_partitions = number of B-sample
+ * block_length B: a power of two, 32 ... 4096 (32 ... 256 when n_partitions > 1); n_ears must be 2; n_partitions = number of B-sample
  * partitions of the HRIR.  1 is the reference's only supported case (_filter_set.py:1136-1140);
  * > 1 is an EXTENSION defined by composition with the reference's partition-queue semantics
  * (_convolver.py:802-836, :645-665), see DESIGN.md row a-X. */
@@ -82,10 +82,24 @@ int rtb_sh_plan_reset(rtb_sh_plan *plan);
  *   Asynchronous on `cuda_stream` (a cudaStream_t, NULL = default). */
 int rtb_sh_process_block(rtb_sh_plan *plan, const float *d_in, const float *d_yaw_deg,
                          float *d_out, void *cuda_stream);
+/* `count` consecutive blocks in one call: block i (first <= i < first + count) reads
+ * d_in_ring + (i % n_ring) * S*C*B and d_yaw_ring + (i % n_ring) * S; every block writes d_out. */
+int rtb_sh_process_blocks(rtb_sh_plan *plan, const float *d_in_ring, const float *d_yaw_ring,
+                          float *d_out, int n_ring, long long first, int count, void *cuda_stream);
 /* Same with host buffers: H2D copy, render, D2H copy, synchronise (the JACK-callback shape of
  * JackRenderer._process, _jack_renderer.py:296-315). */
 int rtb_sh_process_block_host(rtb_sh_plan *plan, const float *h_in, const float *h_yaw_deg,
                               float *h_out);
+/* The same block split into an asynchronous submit and a wait, for callers that feed blocks
+ * back to back (the reference's real-time feeder hands a block to JackRenderer._process every
+ * period, _jack_client.py:713-867): up to three submitted blocks are in flight, the input copy of
+ * block t+1 overlapping the kernels and the result copy of block t.  h_in / h_yaw_deg must stay
+ * valid until the block's wait returns (page-locked memory, rtb_host_alloc, makes the copies
+ * direct DMA); h_out is complete when rtb_sh_wait_block_host(plan, *ticket) returns.  Blocks are
+ * processed in submission order. */
+int rtb_sh_submit_block_host(rtb_sh_plan *plan, const float *h_in, const float *h_yaw_deg,
+                             float *h_out, long long *ticket);
+int rtb_sh_wait_block_host(rtb_sh_plan *plan, long long ticket);
 
 /* introspection: what = RTB_Q_* */
 #define RTB_Q_SYMMETRIC 1   /* 1 if Y_w has the (n,-m) conjugate symmetry (real analysis path) */
@@ -158,7 +172,8 @@ int rtb_host_free(void *ptr);
  * tools.py:1117-1169).  In place: d_out[s][c][:] *= d_gain[c] (output volume x per-channel
  * relative volume); d_rms / d_peak [n_streams][n_channels] receive the level of the scaled block
  * (dB with zeros reported as -200 when as_level != 0; either may be NULL); *d_clip_count is
- * incremented once per channel block whose peak exceeds 1 (the reference logs a warning). */
+ * incremented once per channel block whose peak exceeds 1 (the reference logs a warning);
+ * d_clip_count may be NULL when clipping detection is off. */
 int rtb_output_stage(float *d_out, const float *d_gain, float *d_rms, float *d_peak,
                      unsigned int *d_clip_count, long long n_streams, int n_channels,
                      int block_length, int as_level, void *cuda_stream);

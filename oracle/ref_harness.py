@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- stub-import harness around the UNMODIFIED reference.
 
-Imports ``/root/reference/ReTiSAR`` (read-only, exists only in the build container, never on
-the GPU box) with the third-party modules that are missing here replaced by mocks, so that the
+Imports ``/root/reference/ReTiSAR`` (read-only, exists only in the build container) -- or, on the
+GPU box, the unmodified copy ``oracle/stage_ref.py`` staged into the git-ignored ``oracle/_ref`` --
+with the third-party modules that are missing here replaced by mocks, so that the
 reference's own ``OverlapSaveConvolver`` / ``AdjustableFdConvolver`` / ``AdjustableShConvolver``
 (``ReTiSAR/_convolver.py``) and ``FilterSet*`` (``ReTiSAR/_filter_set.py``) can be executed on
 seeded synthetic inputs.  ``oracle/make_golden.py`` uses it to write ``tests/golden/*.npz``;
@@ -27,11 +28,30 @@ from unittest.mock import MagicMock
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
+
+def _find_reference_root():
+    """The reference itself in the build container, else the unmodified copy that
+    ``oracle/stage_ref.py`` staged into ``oracle/_ref`` (what the GPU box sees)."""
+    env = os.environ.get("RTB_REFERENCE_ROOT")  # tests: force the staged copy
+    if env:
+        return env
+    if os.path.isdir("/root/reference/ReTiSAR"):
+        return "/root/reference"
+    from oracle import stage_ref
+
+    return stage_ref.staged_root() or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "ReTiSAR"))
+
+
+def reference_is_original():
+    """True when the package is read from /root/reference (build container), False for the staged copy."""
+    return REFERENCE_ROOT == "/root/reference"
 
 
 # --------------------------------------------------------------------------------------------
@@ -102,10 +122,13 @@ def import_reference():
     for name in (
         "pythonosc", "pythonosc.dispatcher", "pythonosc.osc_server", "pythonosc.udp_client",
         "pysofaconventions", "samplerate", "soundfile", "serial", "serial.tools",
-        "serial.tools.list_ports", "pyfftw", "pyfftw.builders", "jack",
+        "serial.tools.list_ports", "pyfftw", "pyfftw.builders",
         "matplotlib", "matplotlib.pyplot", "matplotlib.ticker", "natsort",
     ):
         sys.modules.setdefault(name, MagicMock())
+    from oracle import fake_jack
+
+    sys.modules.setdefault("jack", fake_jack.build_module())
     sfa = _build_sfa_module()
     sys.modules["sound_field_analysis"] = sfa
     for sub in ("process", "sph", "io", "gen", "utils", "plot"):

@@ -34,7 +34,10 @@ SIGNATURES = {
     "rtb_sh_plan_set_crossfade": (_i, [_vp, _i]),
     "rtb_sh_plan_reset": (_i, [_vp]),
     "rtb_sh_process_block": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "rtb_sh_process_blocks": (_i, [_vp, _vp, _vp, _vp, _i, ctypes.c_longlong, _i, _vp]),
     "rtb_sh_process_block_host": (_i, [_vp, _vp, _vp, _vp]),
+    "rtb_sh_submit_block_host": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_longlong)]),
+    "rtb_sh_wait_block_host": (_i, [_vp, ctypes.c_longlong]),
     "rtb_sh_plan_query": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
     "rtb_sh_plan_set_profiling": (_i, [_vp, _i]),
     "rtb_sh_plan_destroy": (_i, [_vp]),

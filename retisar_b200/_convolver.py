@@ -197,6 +197,7 @@ class OverlapSaveConvolver(Convolver):
         self._device = config.CUDA_DEVICE if device is None else device
         self._filter.calculate_filter_blocks_fd(self._block_length)
         self._plan = None
+        self._blocks_seen = 0  # blocks processed by the current plan (mono / full-width choice)
         if type(self) is OverlapSaveConvolver:
             # rows of `_input_block_td` = filter channels (`_convolver.py:477-480`); a mono input
             # is broadcast into all of them (`:588-591`), for which the plan has a cheaper form
@@ -208,6 +209,7 @@ class OverlapSaveConvolver(Convolver):
                              device=self._device)
         self._plan.set_filter(hfd[:, 0])
         self._plan.set_passthrough(self._is_passthrough)
+        self._blocks_seen = 0
 
     def __copy__(self):
         """Independent clone for ``JackRendererBenchmark.add_convolver`` (``_convolver.py:482-491``);
@@ -240,9 +242,26 @@ class OverlapSaveConvolver(Convolver):
             return Convolver.filter_block(self, None)
         n_rows = input_block_td.shape[-2]
         if n_rows != self._plan.n_in:
-            if n_rows != 1:
-                raise ValueError(f"expected {self._plan.n_out} (or 1) input channels, got {n_rows}")
-            self._make_plan(1)  # first mono block: switch to the mono-input delay line
+            # The reference accepts a mono or a full-width block on every call and broadcasts mono
+            # into the same buffers (`_convolver.py:588-591`).  Here the mono form has its own,
+            # much cheaper plan (one input spectrum per block): it is selected by the FIRST block.
+            # A mono block after full-width ones is broadcast on the way in (state kept, exactly
+            # the reference's arithmetic); a full-width block on a mono plan cannot be honoured
+            # without dropping the delay line and is refused.
+            if n_rows == 1 and self._blocks_seen == 0:
+                self._make_plan(1)
+            elif n_rows == 1:
+                if _is_torch_tensor(input_block_td):
+                    input_block_td = input_block_td.expand(
+                        *input_block_td.shape[:-2], self._plan.n_in, input_block_td.shape[-1]).contiguous()
+                else:
+                    input_block_td = np.ascontiguousarray(np.broadcast_to(
+                        input_block_td, input_block_td.shape[:-2] + (self._plan.n_in, input_block_td.shape[-1])))
+            else:
+                raise ValueError(
+                    f"expected {self._plan.n_in} input channel(s) (the convolver was started with "
+                    f"{'a mono' if self._plan.n_in == 1 else 'a full-width'} block), got {n_rows}")
+        self._blocks_seen += 1
         plan = self._plan
         if _is_torch_tensor(input_block_td):
             import torch
@@ -493,3 +512,24 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         x = np.asarray(input_block_td, dtype=np.float32)
         out = plan.process_host(x.reshape(plan.S, plan.C, plan.B), yaw_deg)
         return out if x.ndim == 3 else out[0]
+
+    def submit_block(self, input_block_td, yaw_deg=None):
+        """Extension: asynchronous ``filter_block`` for host blocks.  Returns a ticket whose
+        ``result()`` yields what ``filter_block`` would have returned.  Blocks are rendered in
+        submission order; up to three may be in flight, so a feeder that submits block t+1 before
+        it collects block t overlaps the input copy with the rendering and the result copy (a
+        real-time feeder does exactly that: the reference's JACK thread hands over one block per
+        period, ``_jack_client.py:713-867``).  The input array must not be modified before
+        ``result()`` returns."""
+        if self._plan is None:
+            raise RuntimeError(self._filter._ERROR_MSG_NM)
+        plan = self._plan
+        if yaw_deg is None:
+            azim = self._tracker_deg[HeadTracker.DataIndex.AZIM] if self._tracker_deg is not None else 0.0
+            yaw_deg = np.full(plan.S, azim, dtype=np.float32)
+        x = np.asarray(input_block_td, dtype=np.float32)
+        ticket = plan.submit_host(x.reshape(plan.S, plan.C, plan.B), yaw_deg)
+        if x.ndim != 3:
+            ticket._out = ticket._out[0]
+        return ticket
+

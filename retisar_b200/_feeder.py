@@ -79,6 +79,7 @@ class BlockFeeder(object):
         self.last_peak = None
         self.last_block_seconds = 0.0
         self._d_gain = self._d_levels = self._d_clip = None
+        self._d_clip_seen = 0  # device clip count already added to `_counter_clipping`
 
     # ---- configuration (names of `_jack_client.py:560-711`) ----------------------------------
     def init_input_buffer(self, max_length_sec, channel_count, n_streams=None, device=None):
@@ -155,6 +156,7 @@ class BlockFeeder(object):
             self._d_gain = torch.empty(n_ch, device=y.device, dtype=torch.float32)
             self._d_levels = torch.empty((2, rows), device=y.device, dtype=torch.float32)
             self._d_clip = torch.zeros(1, device=y.device, dtype=torch.int32)
+            self._d_clip_seen = 0
             self._gain_host = None
         gain = (self._output_volume * self._output_volume_relative[:, 0]).astype(np.float32)
         if self._gain_host is None or not np.array_equal(gain, self._gain_host):
@@ -164,18 +166,31 @@ class BlockFeeder(object):
         check(lib.rtb_output_stage(_dev_ptr(y), _dev_ptr(self._d_gain),
                                    _dev_ptr(self._d_levels[0]) if measure else None,
                                    _dev_ptr(self._d_levels[1]) if measure else None,
-                                   _dev_ptr_int(self._d_clip), rows // n_ch, n_ch, B, 1,
+                                   _dev_ptr_int(self._d_clip) if self._is_detect_clipping else None,
+                                   rows // n_ch, n_ch, B, 1,
                                    _stream_ptr(torch.cuda.current_stream(y.device))))
         if measure:
             lv = self._d_levels.cpu().numpy().reshape((2,) + tuple(y.shape[:-1]))
             self.last_rms, self.last_peak = lv[0], lv[1]
-        if self._is_detect_clipping and measure:  # the count is read back with the levels
-            self._counter_clipping = int(self._d_clip.item())
+            if self._is_detect_clipping:  # the count is read back together with the levels
+                self._refresh_device_clipping()
         return y
 
+    def _refresh_device_clipping(self):
+        """Add what the device counted since the last read to the host counter (the host path adds
+        to the same counter) and warn like ``_jack_client.py:853-862``."""
+        if self._d_clip is None:
+            return
+        total = int(self._d_clip.item())
+        delta = total - self._d_clip_seen
+        self._d_clip_seen = total
+        if delta > 0:
+            self._counter_clipping += delta
+            if self._logger:
+                self._logger.warning(f"output clipping detected ({delta} channel blocks).")
+
     def get_clipping_counter(self):
-        if self._d_clip is not None:
-            self._counter_clipping = int(self._d_clip.item())
+        self._refresh_device_clipping()
         return self._counter_clipping
 
     def process_block(self, input_td, yaw_deg=None):

@@ -228,6 +228,12 @@ int rtb_fd_plan_create(rtb_fd_plan **out, int device, int n_streams, int block_l
     if (!out) return fail(RTB_ERR_INVALID, "plan output pointer is NULL");
     *out = nullptr;
     if (n_streams < 1 || n_dirs < 1 || n_partitions < 1) return fail(RTB_ERR_INVALID, "sizes must be >= 1");
+    // the direction index is int(-azimuth) on the integer-degree SSR grid (_convolver.py:913-945,
+    // _filter_set.py:883-899): 0 or n_dirs - k with k = 1 .. 359.  With fewer directions the
+    // reference fails with an IndexError at run time; refuse the plan instead of reading out of bounds.
+    if (n_dirs < 360)
+        return fail(RTB_ERR_INVALID, "the direction-switching renderer indexes filters by whole degrees of "
+                    "azimuth and needs at least 360 directions (got %d)", n_dirs);
     if (n_sources < 1)
         return fail(RTB_ERR_INVALID, "no virtual source positions (according to playback file channel count) given.");
     if (!block_length_supported(block_length))
@@ -293,6 +299,7 @@ int rtb_fd_plan_set_filter(rtb_fd_plan *p, const float *hfd, const float *win_in
     RTB_CUDA(cudaMemcpy(p->d_hfd, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_win_in, wi.data(), sizeof(float) * p->B, cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_win_out, wo.data(), sizeof(float) * p->B, cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaDeviceSynchronize());  // uploads and creation-time memsets done before a non-blocking stream runs
     p->filter_set = true;
     return RTB_OK;
 }
@@ -321,6 +328,7 @@ int rtb_fd_plan_set_crossfade(rtb_fd_plan *p, int on) {
         DeviceGuard guard(p->device);
         RTB_CUDA(cudaDeviceSynchronize());
         RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * fd_queue_elems(p)));
+        RTB_CUDA(cudaDeviceSynchronize());
         p->last_valid = false;
     }
     return RTB_OK;
@@ -329,9 +337,11 @@ int rtb_fd_plan_set_crossfade(rtb_fd_plan *p, int on) {
 int rtb_fd_plan_reset(rtb_fd_plan *p) {
     if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
     DeviceGuard guard(p->device);
+    RTB_CUDA(cudaDeviceSynchronize());  // blocks in flight on non-blocking streams (see rtb_ols_plan_reset)
     RTB_CUDA(cudaMemset(p->d_xstate, 0, sizeof(float) * 2 * fd_state_elems(p)));
     RTB_CUDA(cudaMemset(p->d_qcur, 0, sizeof(float2) * fd_queue_elems(p)));
     RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * fd_queue_elems(p)));
+    RTB_CUDA(cudaDeviceSynchronize());
     return RTB_OK;
 }
 

@@ -578,6 +578,7 @@ int rtb_ols_plan_set_filter(rtb_ols_plan *p, const float *hfd) {
             RTB_CUDA(cudaMemcpy(p->d_bmat[ch], bm.data(), sizeof(float) * bm.size(), cudaMemcpyHostToDevice));
         }
     }
+    RTB_CUDA(cudaDeviceSynchronize());  // uploads and creation-time memsets done before a non-blocking stream runs
     p->filter_set = true;
     return RTB_OK;
 }
@@ -591,13 +592,17 @@ int rtb_ols_plan_set_passthrough(rtb_ols_plan *p, int on) {
 int rtb_ols_plan_reset(rtb_ols_plan *p) {
     if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
     DeviceGuard guard(p->device);
-    // _input_block_td.fill(0); _blocks_fd.fill(0)  (_convolver.py:500-505)
+    // _input_block_td.fill(0); _blocks_fd.fill(0)  (_convolver.py:500-505).  The memsets run on the legacy
+    // default stream, which does not order against the plan's (non-blocking) streams or a caller's:
+    // wait for the blocks in flight first and for the memsets afterwards.
+    RTB_CUDA(cudaDeviceSynchronize());
     RTB_CUDA(cudaMemset(p->d_xstate, 0, sizeof(float) * 2 * state_elems(p)));
     RTB_CUDA(cudaMemset(p->d_hist, 0, sizeof(float2) * hist_elems(p)));
     RTB_CUDA(cudaMemset(p->d_incl, 0, p->P));
     if (p->tc_mono)
         for (int i = 0; i < 2; ++i)
             RTB_CUDA(cudaMemset(p->d_histT[i], 0, sizeof(float) * (size_t)p->F * p->tc_Kpad * p->tc_Spad));
+    RTB_CUDA(cudaDeviceSynchronize());
     return RTB_OK;
 }
 

@@ -31,7 +31,7 @@ output_stage_kernel(float *__restrict__ y, const float *__restrict__ gain, float
     }
     if (lane == 0) {
         float r = sqrtf(ss / (float)B), pk = mx;
-        if (mx > 1.0f) atomicAdd(clip_count, 1u);  // `_is_detect_clipping`: peak > 1 (:856)
+        if (clip_count && mx > 1.0f) atomicAdd(clip_count, 1u);  // `_is_detect_clipping`: peak > 1 (:856)
         if (as_level) {  // 20 log10, zeros reported as -200 dB (tools.py:1141-1145, :1165-1169)
             r = r == 0.f ? -200.f : 20.f * log10f(r);
             pk = pk == 0.f ? -200.f : 20.f * log10f(pk);
@@ -46,7 +46,7 @@ output_stage_kernel(float *__restrict__ y, const float *__restrict__ gain, float
 extern "C" int rtb_output_stage(float *d_out, const float *d_gain, float *d_rms, float *d_peak,
                                 unsigned int *d_clip_count, long long n_streams, int n_channels,
                                 int block_length, int as_level, void *cuda_stream) {
-    if (!d_out || !d_gain || !d_clip_count) return rtb::fail(RTB_ERR_INVALID, "NULL argument");
+    if (!d_out || !d_gain) return rtb::fail(RTB_ERR_INVALID, "NULL argument");  // d_clip_count NULL: detection off
     if (n_streams < 1 || n_channels < 1 || block_length < 4 || block_length % 4)
         return rtb::fail(RTB_ERR_INVALID, "bad sizes (block length must be a multiple of 4)");
     const long long rows = n_streams * n_channels;

@@ -215,8 +215,6 @@ __device__ __forceinline__ float2 phase_of(const float2 *cs, int m) {
 #include "sh_analysis_mma.cuh"
 #include "sh_render.cuh"
 #include "sh_render_mg.cuh"
-#include "sh_render_split.cuh"
-#include "sh_render_eo.cuh"
 #include "sh_partitioned.cuh"
 
 namespace rtb {

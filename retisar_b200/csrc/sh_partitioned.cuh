@@ -106,124 +106,7 @@ sh_spectra_kernel(const ShPartParams prm) {
 
 #define RTB_QC 4  // partitions per register tile
 
-template <int N2>
-__global__ void __launch_bounds__(128)
-sh_partition_mac_kernel(const ShPartParams prm) {
-    constexpr int B = N2 / 2;
-    __shared__ float2 s_cs[4][2][2][RTB_MAX_ORDER + 1];  // [warp][stream][cur/last][m] = (cos, sin)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = blockIdx.x * 32 + lane;
-    const bool fvalid = f <= B;
-    const int fc = fvalid ? f : 0;                 // clamped: out-of-range lanes read bin 0
-    const int fm = (N2 - fc) & (N2 - 1);           // mirrored bin
-    const int sbase = (blockIdx.y * 4 + warp) * 2;
-    if (sbase >= prm.S) return;
-    const bool has_s1 = sbase + 1 < prm.S;
-    // rotation phases of both streams, current and previous yaw (a4)
-    for (int i = lane; i < 4 * (prm.order_max + 1); i += 32) {
-        const int m = i % (prm.order_max + 1), which = i / (prm.order_max + 1);
-        const int st = which >> 1, cl = which & 1;
-        const int s = min(sbase + st, prm.S - 1);
-        const float rad = cl ? prm.rad_last_in[s]
-                             : yaw_deg_to_rad16(prm.yaw_deg[s], prm.tracker_dir, prm.src_azim16);
-        float sn, cs;
-        sincosf((float)m * rad, &sn, &cs);
-        s_cs[warp][st][cl][m] = make_float2(cs, sn);
-    }
-    __syncwarp();
-    const int nsteps = max(prm.nsteps_cur, prm.nsteps_last);
-    const float2 *z0 = prm.zspec + (size_t)sbase * prm.NPT * N2;
-    const float2 *z1 = prm.zspec + (size_t)(has_s1 ? sbase + 1 : sbase) * prm.NPT * N2;
-    const size_t hq = (size_t)prm.NPT * 2 * prm.Fp;  // H stride between partitions
-
-    for (int q0 = 0; q0 < prm.P; q0 += RTB_QC) {
-        float2 acc[RTB_QC][2][2][2];  // [partition][ear][cur/last][stream]
-#pragma unroll
-        for (int a = 0; a < RTB_QC; ++a)
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) acc[a][e][c][0] = acc[a][e][c][1] = make_float2(0.f, 0.f);
-        const float4 *hbase = prm.htab + (size_t)q0 * hq + fc;
-        // software pipeline: the loads of step j+1 are in flight while step j is computed
-        ShStep stp = nsteps > 0 ? prm.steps[0] : ShStep{0, 0, 0, 0};
-        float4 h[RTB_QC];
-        float2 zz[2];
-        auto load = [&](const ShStep &st_, float4 (&hh)[RTB_QC], float2 (&z)[2]) {
-            const size_t zo = (size_t)st_.p * N2 + (st_.term ? fm : fc);
-            z[0] = __ldg(z0 + zo);
-            z[1] = __ldg(z1 + zo);
-            const float4 *hp = hbase + ((size_t)st_.p * 2 + st_.term) * prm.Fp;
-#pragma unroll
-            for (int a = 0; a < RTB_QC; ++a)
-                hh[a] = (q0 + a < prm.P) ? __ldg(hp + (size_t)a * hq) : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        if (nsteps > 0) load(stp, h, zz);
-        for (int j = 0; j < nsteps; ++j) {
-            ShStep nxt = stp;
-            float4 hn[RTB_QC];
-            float2 zn[2];
-            if (j + 1 < nsteps) {
-                nxt = prm.steps[j + 1];
-                load(nxt, hn, zn);
-            }
-            const bool in_cur = j < prm.nsteps_cur, in_last = j < prm.nsteps_last;
-            float2 A[2][2];  // [cur/last][stream]
-#pragma unroll
-            for (int st = 0; st < 2; ++st) {
-                float2 z = zz[st];
-                if (stp.term) z.y = -z.y;
-                const float2 pc = in_cur ? phase_of(s_cs[warp][st][0], stp.m) : make_float2(0.f, 0.f);
-                const float2 pl = in_last ? phase_of(s_cs[warp][st][1], stp.m) : make_float2(0.f, 0.f);
-                A[0][st] = cmul(pc, z);
-                A[1][st] = cmul(pl, z);
-            }
-#pragma unroll
-            for (int a = 0; a < RTB_QC; ++a)
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int st = 0; st < 2; ++st) {
-                        cfma(acc[a][0][c][st], make_float2(h[a].x, h[a].y), A[c][st]);
-                        cfma(acc[a][1][c][st], make_float2(h[a].z, h[a].w), A[c][st]);
-                    }
-            stp = nxt;
-#pragma unroll
-            for (int a = 0; a < RTB_QC; ++a) h[a] = hn[a];
-            zz[0] = zn[0];
-            zz[1] = zn[1];
-        }
-        if (fvalid) {
-#pragma unroll
-            for (int a = 0; a < RTB_QC; ++a) {
-                if (q0 + a < prm.P) {
-                    const int sc = (prm.head_cur + q0 + a) % prm.P, sl = (prm.head_last + q0 + a) % prm.P;
-#pragma unroll
-                    for (int st = 0; st < 2; ++st) {
-                        if (st == 0 || has_s1) {
-                            const size_t sq = (size_t)(sbase + st) * prm.P;
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                float2 *qc = prm.qcur + ((sq + sc) * 2 + e) * prm.Fp + f;
-                                float2 v = *qc;
-                                v.x += acc[a][e][0][st].x; v.y += acc[a][e][0][st].y;
-                                *qc = v;
-                                if (prm.crossfade) {
-                                    float2 *ql = prm.qlast + ((sq + sl) * 2 + e) * prm.Fp + f;
-                                    float2 w = *ql;
-                                    w.x += acc[a][e][1][st].x; w.y += acc[a][e][1][st].y;
-                                    *ql = w;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-}
-
-// Second version of the partition MAC: the H rows of the CTA's 32 bins are staged through shared
+// The partition MAC (SIMT form): the H rows of the CTA's 32 bins are staged through shared
 // memory (cp.async, double buffered over chunks of RTB_MAC_SC steps) and shared by 8 warps = 16
 // streams, instead of every warp pulling them through L1/L2 (first version: 5.1 long-scoreboard
 // stall cycles per issue, FMA pipe 33 %, profiles/).  Spectra are read in batches (see the loop).

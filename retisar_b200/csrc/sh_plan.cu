@@ -13,6 +13,7 @@
 using namespace rtb;
 
 #define RTB_MAX_CHUNKS 4
+#define RTB_HOST_SLOTS 3
 
 struct rtb_sh_plan {
     int device = 0;
@@ -42,12 +43,9 @@ struct rtb_sh_plan {
     // programmatic dependent launch of the chain's kernels: RTB_PDL=1 enables.  Measured on B200:
     // 1 024 streams 55.4 -> 62.8 us per block (worse), 10 240 streams 385 -> 380 us: off by default
     bool pdl = false;
-    bool mg_enabled = false, split_enabled = false;  // split: RTB_RENDER_SPLIT=1 (measured: no gain)
+    bool mg_enabled = false;
     int mg_order = -1, mg_np = 0;
     float4 *d_mg_htab = nullptr;
-    float4 *d_eo_htab = nullptr;   // the same tables decimated into even / odd bins (sh_render_eo.cuh)
-    bool eo_enabled = false;       // RTB_RENDER_EO=1: two warps per stream; measured: equal at 1 024
-                                   // streams (39.2 vs 38.6 us), slower at 10 240 (284 vs 252 us)
     ShMgSignal *d_mg_signals = nullptr;
     std::vector<ShSignal> h_sig;       // host copy of the signal list
     std::vector<float> h_hnm;          // host copy of H_nm [K][2][F] complex (P == 1)
@@ -62,15 +60,16 @@ struct rtb_sh_plan {
     float2 *d_zspec = nullptr;    // [S][NP][N2]
     float2 *d_qcur = nullptr, *d_qlast = nullptr;  // [S][P][2][Fp]
     int head_cur = 0, head_last = 0;
-    // staging for the host-buffer entry point
-    float *d_in = nullptr, *d_yaw = nullptr, *d_out = nullptr;
+    // staging for the host-buffer entry points: RTB_HOST_SLOTS device copies of (input block, yaw,
+    // output block) so that the input copy of block t+1 overlaps the kernels and the result copy
+    // of block t (rtb_sh_submit_block_host / rtb_sh_wait_block_host)
+    struct HostSlot {
+        float *d_in = nullptr, *d_yaw = nullptr, *d_out = nullptr;
+        cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+    } hslot[RTB_HOST_SLOTS];
+    bool hslots_ready = false;
+    long long submitted = 0;      // blocks submitted through the host entry points (ticket counter)
     cudaStream_t own_stream = nullptr, d2h_stream = nullptr, k_stream = nullptr;
-    cudaEvent_t chunk_ev[2 * RTB_MAX_CHUNKS] = {};
-    // device entry point, large batches: analysis of chunk c+1 runs next to the render kernel of
-    // chunk c on two internal streams (the kernels stress different units: HBM / FP32 latency)
-    int ov_chunks = 0;            // 0 = not decided yet
-    cudaStream_t ov_a = nullptr, ov_r = nullptr;
-    cudaEvent_t ov_ev[RTB_MAX_CHUNKS + 2] = {};
     // control state (reference attribute it mirrors)
     int slot = 0;                 // which half of d_zring receives the current block
     int rad_idx = 0;              // which half of d_radlast holds the previous yaw
@@ -169,22 +168,8 @@ void launch_render_mg_t(const ShRenderMgParams &prm, cudaStream_t st, bool pdl) 
 }
 
 void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStream_t st) {
-    if (p->N2 == 512 && p->eo_enabled && p->d_eo_htab) {  // two warps per stream: even / odd bins
-        constexpr int NST = RTB_EO_STREAMS;
-        const size_t smem = sizeof(float2) * (2 * NST) * (4 * 4 * 32) + sizeof(float) * NST * 4 * 256 +
-                            sizeof(float2) * (2 * NST) * 256;
-        kernel_attrs_once(sh_render_eo_kernel<NST>, (int)smem, true);
-        ShRenderMgParams q = prm;
-        q.htab = p->d_eo_htab;
-        sh_render_eo_kernel<NST><<<(unsigned)((prm.S + NST - 1) / NST), 64 * NST, smem, st>>>(q);
-        return;
-    }
     if (p->N2 == 256) launch_render_mg_t<256>(prm, st, p->pdl);
-    else if (p->split_enabled) {  // two warps per stream
-        kernel_attrs_once(sh_render_split_kernel<RTB_SPLIT_STREAMS>, 48 * 1024, true);
-        sh_render_split_kernel<RTB_SPLIT_STREAMS>
-            <<<(unsigned)((prm.S + RTB_SPLIT_STREAMS - 1) / RTB_SPLIT_STREAMS), 64 * RTB_SPLIT_STREAMS, 0, st>>>(prm);
-    } else launch_render_mg_t<512>(prm, st, p->pdl);
+    else launch_render_mg_t<512>(prm, st, p->pdl);
 }
 
 // Tables of the steady-state render kernel for SH order `order`: signals sorted by m (one group
@@ -264,23 +249,6 @@ int build_mg_tables(rtb_sh_plan *p, int order) {
     RTB_CUDA(cudaMalloc(&p->d_mg_signals, sizeof(ShMgSignal) * sig.size()));
     RTB_CUDA(cudaMemcpy(p->d_mg_htab, htab.data(), sizeof(float4) * htab.size(), cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_mg_signals, sig.data(), sizeof(ShMgSignal) * sig.size(), cudaMemcpyHostToDevice));
-    cudaFree(p->d_eo_htab); p->d_eo_htab = nullptr;
-    if (p->N2 == 512) {  // [signal][role: even, odd][term][RTB_EO_HE]
-        const int HE = RTB_EO_HE;
-        std::vector<float4> eo(sig.size() * 4 * (size_t)HE, make_float4(0.f, 0.f, 0.f, 0.f));
-        for (size_t q = 0; q < sig.size(); ++q) {
-            const float4 *src = htab.data() + q * 2 * (size_t)F;
-            auto h1 = [&](int f) { return src[f]; };
-            auto h2 = [&](int f) { return src[F + (B - f)]; };  // term 2 at bin f (stored mirrored above)
-            float4 *dst = eo.data() + q * 4 * (size_t)HE;
-            for (int j = 0; j <= 128; ++j) dst[j] = h1(2 * j);                 // even, U: bin 2j
-            for (int i = 0; i <= 128; ++i) dst[HE + i] = h2(2 * (128 - i));    // even, V: mirror position i
-            for (int j = 0; j < 128; ++j) dst[2 * HE + j] = h1(2 * j + 1);     // odd, U: bin 2j+1
-            for (int i = 0; i < 128; ++i) dst[3 * HE + i] = h2(255 - 2 * i);   // odd, V
-        }
-        RTB_CUDA(cudaMalloc(&p->d_eo_htab, sizeof(float4) * eo.size()));
-        RTB_CUDA(cudaMemcpy(p->d_eo_htab, eo.data(), sizeof(float4) * eo.size(), cudaMemcpyHostToDevice));
-    }
     p->mg_np = (int)sig.size();
     p->mg_order = order;
     if (p->mg_np > RTB_MG_MAX_SIGNALS) {  // beyond the kernel's shared-memory signal list
@@ -325,7 +293,6 @@ void free_tables(rtb_sh_plan *p) {
     cudaFree(p->d_signals); p->d_signals = nullptr;
     cudaFree(p->d_mg_htab); p->d_mg_htab = nullptr;
     cudaFree(p->d_mg_signals); p->d_mg_signals = nullptr;
-    cudaFree(p->d_eo_htab); p->d_eo_htab = nullptr;
     p->mg_order = -1;
     cudaFree(p->d_steps); p->d_steps = nullptr;
     cudaFree(p->d_tc_b); p->d_tc_b = nullptr;
@@ -524,6 +491,15 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     RTB_CUDA(cudaMemcpy(p->d_rmT, rmT.data(), sizeof(float) * rmT.size(), cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_htab, htab.data(), sizeof(float4) * htab.size(), cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_signals, sig.data(), sizeof(ShSignal) * NP, cudaMemcpyHostToDevice));
+    if (p->P > 1) {
+        int n_steps = 0;
+        for (int q = 0; q < NP; ++q) n_steps += sig[q].m2 != RTB_NO_TERM ? 2 : 1;
+        if (n_steps > RTB_MAC_MAX_STEPS) {
+            free_tables(p);
+            return fail(RTB_ERR_UNSUPPORTED, "the partitioned SH-domain HRIR extension supports up to %d "
+                        "(signal, term) steps (SH order 12); this configuration has %d", RTB_MAC_MAX_STEPS, n_steps);
+        }
+    }
     {
         std::vector<ShStep> steps;
         p->steps_prefix.assign(NP + 1, 0);
@@ -545,9 +521,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     p->h_shm.assign(sh_m, sh_m + K);
     p->mg_enabled = p->P == 1 && (p->N2 == 256 || p->N2 == 512);
     if (const char *env = getenv("RTB_RENDER_MG")) p->mg_enabled = p->mg_enabled && env[0] != '0';
-    if (const char *env = getenv("RTB_RENDER_SPLIT")) p->split_enabled = env[0] != '0';
     if (const char *env = getenv("RTB_PDL")) p->pdl = env[0] != '0';
-    if (const char *env = getenv("RTB_RENDER_EO")) p->eo_enabled = env[0] != '0';
     if (p->mg_enabled) {
         p->h_hnm.assign(hnm, hnm + 2 * (size_t)K * 2 * F);
         const int rc = build_mg_tables(p, p->order);
@@ -669,6 +643,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     p->cur_order = p->last_order = p->order;
     p->last_valid = false;
     p->tables_set = true;
+    RTB_CUDA(cudaDeviceSynchronize());  // table uploads / state memsets done before a non-blocking stream runs
     return RTB_OK;
 }
 
@@ -720,6 +695,7 @@ int rtb_sh_plan_set_crossfade(rtb_sh_plan *p, int on) {
             DeviceGuard guard(p->device);
             RTB_CUDA(cudaDeviceSynchronize());
             RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * queue_elems(p)));
+            RTB_CUDA(cudaDeviceSynchronize());
         }
     }
     return RTB_OK;
@@ -739,12 +715,15 @@ int rtb_sh_plan_reset(rtb_sh_plan *p) {
     if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
     if (!p->tables_set) return RTB_OK;
     DeviceGuard guard(p->device);
-    // _input_block_td.fill(0); the P == 1 spectra buffers are rewritten every block anyway
+    // _input_block_td.fill(0); the P == 1 spectra buffers are rewritten every block anyway.  Legacy-stream
+    // memsets do not order against non-blocking streams: drain the blocks in flight, then the memsets.
+    RTB_CUDA(cudaDeviceSynchronize());
     RTB_CUDA(cudaMemset(p->d_zring, 0, sizeof(float) * 2 * (size_t)p->S * p->J * p->B));
     if (p->P > 1) {  // _blocks_fd.fill(0); _last_blocks_fd.fill(0)
         RTB_CUDA(cudaMemset(p->d_qcur, 0, sizeof(float2) * queue_elems(p)));
         RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * queue_elems(p)));
     }
+    RTB_CUDA(cudaDeviceSynchronize());
     return RTB_OK;
 }
 
@@ -752,18 +731,13 @@ namespace {
 
 // kernels for streams [s0, s0 + count) of the current block; in/yaw/out point at stream s0
 void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const float *d_yaw_deg,
-                  float *d_out, cudaStream_t st, cudaStream_t st_render = nullptr, cudaEvent_t ev_mid = nullptr) {
+                  float *d_out, cudaStream_t st) {
     const size_t zhalf = (size_t)p->S * p->J * p->B, zo = (size_t)s0 * p->J * p->B;
     float *zcur = p->d_zring + (size_t)p->slot * zhalf + zo;
     const float *zprev = p->d_zring + (size_t)(p->slot ^ 1) * zhalf + zo;
     launch_analysis(p, d_in, zcur, count, st);  // a1/a2: the overlap-save state advances in every mode
     p->launches++;
     if (p->profiling && s0 == 0) cudaEventRecord(p->ev[1], st);
-    if (st_render) {  // the render kernel of this range goes to its own stream, behind the analysis
-        cudaEventRecord(ev_mid, st);
-        cudaStreamWaitEvent(st_render, ev_mid, 0);
-        st = st_render;
-    }
     if (p->passthrough) {
         p->last_render_kernel = 4;
         const long long total = (long long)count * p->E * p->B;
@@ -798,15 +772,11 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         prm.nsteps_last = p->steps_prefix[prm.np_last];
         prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
         const unsigned gw = (unsigned)((count + 3) / 4);
-        const dim3 gmac((unsigned)((p->F + 31) / 32), (unsigned)((count + 7) / 8));
         const dim3 gmac2((unsigned)((p->F + 31) / 32), (unsigned)((count + 2 * RTB_MAC_WARPS - 1) / (2 * RTB_MAC_WARPS)));
-        static const bool mac_v1 = getenv("RTB_MAC_V1") && getenv("RTB_MAC_V1")[0] != '0';
-        const bool mac2 = !mac_v1 && (int)p->steps_prefix.back() <= RTB_MAC_MAX_STEPS;
 #define RTB_PART_LAUNCH(N)                                                                  \
     case N:                                                                                 \
         sh_spectra_kernel<N><<<gw, 128, 0, st>>>(prm);                                      \
-        if (mac2) sh_partition_mac2_kernel<N><<<gmac2, 32 * RTB_MAC_WARPS, 0, st>>>(prm);   \
-        else sh_partition_mac_kernel<N><<<gmac, 128, 0, st>>>(prm);                         \
+        sh_partition_mac2_kernel<N><<<gmac2, 32 * RTB_MAC_WARPS, 0, st>>>(prm);             \
         sh_partition_tail_kernel<N><<<gw, 128, 0, st>>>(prm);                               \
         break;
         switch (p->N2) {
@@ -825,7 +795,7 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
             cudaStreamSynchronize(st);
             use_mg = build_mg_tables(p, p->cur_order) == RTB_OK && p->mg_enabled;
         }
-        p->last_render_kernel = use_mg ? ((p->N2 == 512 && p->eo_enabled && p->d_eo_htab) ? 5 : ((p->split_enabled && p->N2 == 512) ? 2 : 1)) : 0;
+        p->last_render_kernel = use_mg ? 1 : 0;
         if (use_mg) {
             ShRenderMgParams prm;
             prm.zprev = zprev; prm.zcur = zcur;
@@ -887,38 +857,6 @@ int rtb_sh_process_block(rtb_sh_plan *p, const float *d_in, const float *d_yaw_d
     if (!d_yaw_deg && !p->passthrough) return fail(RTB_ERR_INVALID, "NULL yaw pointer");
     DeviceGuard guard(p->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (p->ov_chunks == 0) {  // decide once.  Off by default: measured on B200 (RTB_OVERLAP_CHUNKS=2/4,
-        // c2) 4096 streams 0.168 -> 0.195 ms, 10 240 streams 0.386 -> 0.392 / 0.401 ms, 16 384 equal:
-        // the persistent analysis CTAs hold the shared memory the render CTAs would need
-        int n = 1;
-        if (const char *env = getenv("RTB_OVERLAP_CHUNKS")) n = atoi(env);
-        p->ov_chunks = std::max(1, std::min(RTB_MAX_CHUNKS, n));
-        if (p->ov_chunks > 1) {
-            cudaError_t err = cudaStreamCreateWithFlags(&p->ov_a, cudaStreamNonBlocking);
-            if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&p->ov_r, cudaStreamNonBlocking);
-            for (auto &e : p->ov_ev)
-                if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-            if (err != cudaSuccess) p->ov_chunks = 1;
-        }
-    }
-    if (p->ov_chunks > 1 && !p->profiling && !p->passthrough && p->P == 1) {
-        // fork from the caller's stream, chunks of streams through (analysis | render), join back
-        const size_t in_per = (size_t)p->C * p->B, out_per = (size_t)p->E * p->B;
-        const int per = ((p->S + p->ov_chunks - 1) / p->ov_chunks + 3) / 4 * 4;
-        RTB_CUDA(cudaEventRecord(p->ov_ev[RTB_MAX_CHUNKS], st));
-        RTB_CUDA(cudaStreamWaitEvent(p->ov_a, p->ov_ev[RTB_MAX_CHUNKS], 0));
-        RTB_CUDA(cudaStreamWaitEvent(p->ov_r, p->ov_ev[RTB_MAX_CHUNKS], 0));
-        for (int c = 0, s0 = 0; s0 < p->S; ++c, s0 += per) {
-            const int count = std::min(per, p->S - s0);
-            launch_range(p, s0, count, d_in + s0 * in_per, d_yaw_deg + s0, d_out + s0 * out_per, p->ov_a,
-                         p->ov_r, p->ov_ev[c]);
-        }
-        RTB_CUDA(cudaEventRecord(p->ov_ev[RTB_MAX_CHUNKS + 1], p->ov_r));
-        RTB_CUDA(cudaStreamWaitEvent(st, p->ov_ev[RTB_MAX_CHUNKS + 1], 0));
-        advance_block(p);
-        RTB_CUDA(cudaGetLastError());
-        return RTB_OK;
-    }
     if (p->profiling) cudaEventRecord(p->ev[0], st);
     launch_range(p, 0, p->S, d_in, d_yaw_deg, d_out, st);
     if (p->profiling) { cudaEventRecord(p->ev[2], st); p->ev_valid = true; }
@@ -927,52 +865,101 @@ int rtb_sh_process_block(rtb_sh_plan *p, const float *d_in, const float *d_yaw_d
     return RTB_OK;
 }
 
-int rtb_sh_process_block_host(rtb_sh_plan *p, const float *h_in, const float *h_yaw_deg, float *h_out) {
+// A run of consecutive blocks in one call (offline rendering of a recorded session, benchmarks):
+// block i reads d_in_ring + (i % n_ring) * S*C*B and d_yaw_ring + (i % n_ring) * S, every block
+// writes d_out.  Same kernels and state updates as `count` calls of rtb_sh_process_block.
+int rtb_sh_process_blocks(rtb_sh_plan *p, const float *d_in_ring, const float *d_yaw_ring, float *d_out,
+                          int n_ring, long long first, int count, void *cuda_stream) {
+    if (!p || !d_in_ring || !d_out || n_ring < 1 || count < 0 || first < 0)
+        return fail(RTB_ERR_INVALID, "bad argument");
+    const size_t in_blk = (size_t)p->S * p->C * p->B;
+    for (long long i = first; i < first + count; ++i) {
+        const int r = (int)(i % n_ring);
+        const int rc = rtb_sh_process_block(p, d_in_ring + (size_t)r * in_blk,
+                                            d_yaw_ring ? d_yaw_ring + (size_t)r * p->S : nullptr, d_out, cuda_stream);
+        if (rc != RTB_OK) return rc;
+    }
+    return RTB_OK;
+}
+
+namespace {
+
+int host_slots_init(rtb_sh_plan *p) {
+    if (p->hslots_ready) return RTB_OK;
+    const size_t in_per = (size_t)p->C * p->B, out_per = (size_t)p->E * p->B;
+    cudaError_t err = cudaSuccess;
+    for (auto &h : p->hslot) {
+        if (err == cudaSuccess) err = cudaMalloc(&h.d_in, sizeof(float) * p->S * in_per);
+        if (err == cudaSuccess) err = cudaMalloc(&h.d_out, sizeof(float) * p->S * out_per);
+        if (err == cudaSuccess) err = cudaMalloc(&h.d_yaw, sizeof(float) * p->S);
+        if (err == cudaSuccess) err = cudaMemset(h.d_yaw, 0, sizeof(float) * p->S);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h.in_done, cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h.k_done, cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h.out_done, cudaEventDisableTiming);
+    }
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&p->k_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) return fail(RTB_ERR_NOMEM, "staging allocation failed: %s", cudaGetErrorString(err));
+    p->hslots_ready = true;
+    return RTB_OK;
+}
+
+}  // namespace
+
+// Host-buffer entry points.  A block travels through three streams -- input copy, kernels, result
+// copy -- and RTB_HOST_SLOTS staging slots, so that consecutive submitted blocks form a software
+// pipeline over the full-duplex link: while block t renders and its ear signals go back, the
+// input of block t+1 is already on its way (the input copy is ~95 % of a step at PCIe Gen5 rates).
+// The kernels of consecutive blocks stay ordered on one stream (they share the per-stream state).
+int rtb_sh_submit_block_host(rtb_sh_plan *p, const float *h_in, const float *h_yaw_deg, float *h_out,
+                             long long *ticket) {
     if (!p || !h_in || !h_out) return fail(RTB_ERR_INVALID, "NULL argument");
     if (!p->tables_set)
         return fail(RTB_ERR_STATE, "blocks in spherical harmonics domain have not been calculated yet.");
     if (!h_yaw_deg && !p->passthrough) return fail(RTB_ERR_INVALID, "NULL yaw pointer");
     DeviceGuard guard(p->device);
+    if (int rc = host_slots_init(p)) return rc;
     const size_t in_per = (size_t)p->C * p->B, out_per = (size_t)p->E * p->B;
-    if (!p->d_in) {
-        cudaError_t err = cudaMalloc(&p->d_in, sizeof(float) * p->S * in_per);
-        if (err == cudaSuccess) err = cudaMalloc(&p->d_out, sizeof(float) * p->S * out_per);
-        if (err == cudaSuccess) err = cudaMalloc(&p->d_yaw, sizeof(float) * p->S);
-        if (err == cudaSuccess) err = cudaMemset(p->d_yaw, 0, sizeof(float) * p->S);
-        if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking);
-        if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&p->k_stream, cudaStreamNonBlocking);
-        for (auto &e : p->chunk_ev)
-            if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-        if (err != cudaSuccess) return fail(RTB_ERR_NOMEM, "staging allocation failed: %s", cudaGetErrorString(err));
-    }
-    // Software pipeline over chunks of streams on three streams: input copies run back to back,
-    // the kernels of chunk i overlap the copy of chunk i+1, and result copies go the other way
-    // over the full-duplex link.
+    rtb_sh_plan::HostSlot &h = p->hslot[p->submitted % RTB_HOST_SLOTS];
+    const bool reused = p->submitted >= RTB_HOST_SLOTS;
     cudaStream_t st_in = p->own_stream, st_k = p->k_stream, st_out = p->d2h_stream;
-    if (h_yaw_deg)
-        RTB_CUDA(cudaMemcpyAsync(p->d_yaw, h_yaw_deg, sizeof(float) * p->S, cudaMemcpyHostToDevice, st_in));
-    // Measured on B200 (PCIe Gen5 x16): the input copy is ~97 % of the step and runs at 42-45 GB/s
-    // either way, so chunking buys nothing and costs event overhead; default is a single chunk.
-    int n_chunks = 1;
-    if (const char *env = getenv("RTB_HOST_CHUNKS")) n_chunks = std::max(1, std::min(RTB_MAX_CHUNKS, atoi(env)));
-    n_chunks = std::min(n_chunks, std::max(1, p->S / 256));
-    const int per = (p->S + n_chunks - 1) / n_chunks;
-    for (int c = 0, s0 = 0; s0 < p->S; ++c, s0 += per) {
-        const int count = std::min(per, p->S - s0);
-        RTB_CUDA(cudaMemcpyAsync(p->d_in + s0 * in_per, h_in + s0 * in_per, sizeof(float) * count * in_per,
-                                 cudaMemcpyHostToDevice, st_in));
-        RTB_CUDA(cudaEventRecord(p->chunk_ev[2 * c], st_in));
-        RTB_CUDA(cudaStreamWaitEvent(st_k, p->chunk_ev[2 * c], 0));
-        launch_range(p, s0, count, p->d_in + s0 * in_per, p->d_yaw + s0, p->d_out + s0 * out_per, st_k);
-        RTB_CUDA(cudaEventRecord(p->chunk_ev[2 * c + 1], st_k));
-        RTB_CUDA(cudaStreamWaitEvent(st_out, p->chunk_ev[2 * c + 1], 0));
-        RTB_CUDA(cudaMemcpyAsync(h_out + s0 * out_per, p->d_out + s0 * out_per, sizeof(float) * count * out_per,
-                                 cudaMemcpyDeviceToHost, st_out));
+    if (reused) {
+        // the slot's previous block: its kernels have read d_in, its result copy has read d_out
+        RTB_CUDA(cudaStreamWaitEvent(st_in, h.k_done, 0));
+        RTB_CUDA(cudaStreamWaitEvent(st_k, h.out_done, 0));
     }
+    if (h_yaw_deg)
+        RTB_CUDA(cudaMemcpyAsync(h.d_yaw, h_yaw_deg, sizeof(float) * p->S, cudaMemcpyHostToDevice, st_in));
+    RTB_CUDA(cudaMemcpyAsync(h.d_in, h_in, sizeof(float) * p->S * in_per, cudaMemcpyHostToDevice, st_in));
+    RTB_CUDA(cudaEventRecord(h.in_done, st_in));
+    RTB_CUDA(cudaStreamWaitEvent(st_k, h.in_done, 0));
+    launch_range(p, 0, p->S, h.d_in, h.d_yaw, h.d_out, st_k);
+    RTB_CUDA(cudaEventRecord(h.k_done, st_k));
+    RTB_CUDA(cudaStreamWaitEvent(st_out, h.k_done, 0));
+    RTB_CUDA(cudaMemcpyAsync(h_out, h.d_out, sizeof(float) * p->S * out_per, cudaMemcpyDeviceToHost, st_out));
+    RTB_CUDA(cudaEventRecord(h.out_done, st_out));
     advance_block(p);
-    RTB_CUDA(cudaStreamSynchronize(p->d2h_stream));
+    if (ticket) *ticket = p->submitted;
+    p->submitted++;
     RTB_CUDA(cudaGetLastError());
     return RTB_OK;
+}
+
+int rtb_sh_wait_block_host(rtb_sh_plan *p, long long ticket) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    if (ticket < 0 || ticket >= p->submitted) return fail(RTB_ERR_INVALID, "unknown ticket %lld", ticket);
+    // (a slot that has been reused since carries a later block's event: the result stream is in
+    // order, so waiting for it covers this block too)
+    DeviceGuard guard(p->device);
+    RTB_CUDA(cudaEventSynchronize(p->hslot[ticket % RTB_HOST_SLOTS].out_done));
+    return RTB_OK;
+}
+
+int rtb_sh_process_block_host(rtb_sh_plan *p, const float *h_in, const float *h_yaw_deg, float *h_out) {
+    long long ticket = 0;
+    if (int rc = rtb_sh_submit_block_host(p, h_in, h_yaw_deg, h_out, &ticket)) return rc;
+    return rtb_sh_wait_block_host(p, ticket);
 }
 
 int rtb_sh_plan_query(rtb_sh_plan *p, int what, int64_t *value) {
@@ -1006,25 +993,20 @@ int rtb_debug_tc_trace(long long *h_out, int n) {  // trace builds only (not par
     return cudaMemcpyFromSymbol(h_out, rtb::g_tc_trace, sizeof(long long) * n) == cudaSuccess ? RTB_OK : RTB_ERR_CUDA;
 }
 #endif
-#ifdef RTB_TRACE
-int rtb_debug_eo_trace(long long *h_out, int n) {  // trace builds only (not part of the public ABI)
-    return cudaMemcpyFromSymbol(h_out, rtb::g_eo_trace, sizeof(long long) * n) == cudaSuccess ? RTB_OK : RTB_ERR_CUDA;
-}
-#endif
-
 int rtb_sh_plan_destroy(rtb_sh_plan *p) {
     if (!p) return RTB_OK;
     DeviceGuard guard(p->device);
     free_tables(p);
     cudaFree(p->d_tw); cudaFree(p->d_win_in); cudaFree(p->d_win_out); cudaFree(p->d_radlast);
-    cudaFree(p->d_in); cudaFree(p->d_yaw); cudaFree(p->d_out);
+    for (auto &h : p->hslot) {
+        cudaFree(h.d_in); cudaFree(h.d_yaw); cudaFree(h.d_out);
+        if (h.in_done) cudaEventDestroy(h.in_done);
+        if (h.k_done) cudaEventDestroy(h.k_done);
+        if (h.out_done) cudaEventDestroy(h.out_done);
+    }
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
     if (p->k_stream) cudaStreamDestroy(p->k_stream);
-    if (p->ov_a) cudaStreamDestroy(p->ov_a);
-    if (p->ov_r) cudaStreamDestroy(p->ov_r);
-    for (auto &e : p->ov_ev) if (e) cudaEventDestroy(e);
-    for (auto &e : p->chunk_ev) if (e) cudaEventDestroy(e);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
     return RTB_OK;

@@ -46,3 +46,58 @@ def gather_streams(block, dst=0):
     if rank != dst:
         return None
     return torch.cat([p[: int(c.item())] for p, c in zip(parts, counts)], dim=0)
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPUs of the NUMA node the GPU is attached to, so that the
+    page-locked buffers it allocates afterwards (first touch) and the thread that feeds them sit
+    next to the GPU's PCIe root port.  With one process per GPU this keeps every rank's host-side
+    block traffic on its own socket instead of all ranks sharing node 0.
+
+    Returns a dict describing what was done (``node`` is None when the platform exposes no
+    topology, e.g. inside a VM: nothing is changed then).
+    """
+    import os
+
+    info = {"node": None, "cpus": None, "bdf": None}
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    except Exception:  # older torch: ask the driver
+        try:
+            import subprocess
+
+            bdf = subprocess.run(
+                ["nvidia-smi", f"--id={device_index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                stdout=subprocess.PIPE, text=True, timeout=10).stdout.strip().lower()
+            if len(bdf.split(":")[0]) == 8:  # nvidia-smi prints an 8-digit domain
+                bdf = bdf[4:]
+        except Exception:
+            return info
+    info["bdf"] = bdf
+    try:
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(node=node, cpus=len(cpus))
+    except (OSError, ValueError):
+        pass
+    return info

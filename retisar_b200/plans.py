@@ -98,21 +98,59 @@ class ShPlan:
     def set_profiling(self, on):
         check(lib.rtb_sh_plan_set_profiling(self._h, int(bool(on))))
 
-    def process_host(self, x, yaw_deg, out=None):
-        """x [S,C,B] float32 host, yaw_deg [S] float32 host -> out [S,E,B] float32 host."""
+    def _host_args(self, x, yaw_deg, out):
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.shape != (self.S, self.C, self.B):
             raise ValueError(f"input shape {x.shape} != {(self.S, self.C, self.B)}")
         yaw = None if yaw_deg is None else np.ascontiguousarray(yaw_deg, dtype=np.float32).reshape(self.S)
         if out is None:
-            out = np.empty((self.S, self.E, self.B), dtype=np.float32)
+            out = _OUT_POOL.take((self.S, self.E, self.B))
+        return x, yaw, out
+
+    def process_host(self, x, yaw_deg, out=None):
+        """x [S,C,B] float32 host, yaw_deg [S] float32 host -> out [S,E,B] float32 host (a fresh,
+        writable, page-locked array the caller may keep or modify in place)."""
+        x, yaw, out = self._host_args(x, yaw_deg, out)
         check(lib.rtb_sh_process_block_host(self._h, np_ptr(x), np_ptr(yaw), np_ptr(out)))
         return out
+
+    def submit_host(self, x, yaw_deg, out=None):
+        """Asynchronous form of `process_host`: returns a ticket object whose ``result()`` blocks
+        until the ear signals have arrived.  Up to three blocks may be in flight; the input copy
+        of a block overlaps the kernels and the result copy of the one before it."""
+        x, yaw, out = self._host_args(x, yaw_deg, out)
+        ticket = ctypes.c_longlong()
+        check(lib.rtb_sh_submit_block_host(self._h, np_ptr(x), np_ptr(yaw), np_ptr(out),
+                                           ctypes.byref(ticket)))
+        return HostTicket(self, ticket.value, out, (x, yaw))
 
     def process_device(self, d_x, d_yaw, d_out, stream=None):
         """Asynchronous: device tensors / pointers [S,C,B], [S] -> [S,E,B]."""
         check(lib.rtb_sh_process_block(self._h, _dev_ptr(d_x), _dev_ptr(d_yaw), _dev_ptr(d_out),
                                        _stream_ptr(stream)))
+
+
+    def process_blocks_device(self, d_x_ring, d_yaw_ring, d_out, first, count, stream=None):
+        """`count` consecutive blocks enqueued by one library call: block i reads ring slot
+        i % len(ring) of d_x_ring [R,S,C,B] / d_yaw_ring [R,S]; every block writes d_out."""
+        n_ring = int(d_x_ring.shape[0])
+        check(lib.rtb_sh_process_blocks(self._h, _dev_ptr(d_x_ring), _dev_ptr(d_yaw_ring),
+                                        _dev_ptr(d_out), n_ring, int(first), int(count),
+                                        _stream_ptr(stream)))
+
+
+class HostTicket:
+    """A block submitted through `ShPlan.submit_host`; keeps the input arrays alive until the
+    result has been fetched (the library reads them asynchronously)."""
+
+    def __init__(self, plan, ticket, out, keep):
+        self._plan, self._ticket, self._out, self._keep = plan, ticket, out, keep
+
+    def result(self):
+        if self._keep is not None:
+            check(lib.rtb_sh_wait_block_host(self._plan._h, self._ticket))
+            self._keep = None
+        return self._out
 
 
 class OlsPlan:
@@ -158,7 +196,7 @@ class OlsPlan:
         if x.shape != (self.S, self.n_in, self.B):
             raise ValueError(f"input shape {x.shape} != {(self.S, self.n_in, self.B)}")
         if out is None:
-            out = np.empty((self.S, self.n_out, self.B), dtype=np.float32)
+            out = _OUT_POOL.take((self.S, self.n_out, self.B))
         check(lib.rtb_ols_process_block_host(self._h, np_ptr(x), np_ptr(out)))
         return out
 
@@ -216,7 +254,7 @@ class FdPlan:
             raise ValueError(f"input shape {x.shape} != {(self.S, self.NS, self.B)}")
         yaw = None if yaw_deg is None else np.ascontiguousarray(yaw_deg, dtype=np.float32).reshape(self.S)
         if out is None:
-            out = np.empty((self.S, 2, self.B), dtype=np.float32)
+            out = _OUT_POOL.take((self.S, 2, self.B))
         check(lib.rtb_fd_process_block_host(self._h, np_ptr(x), np_ptr(yaw), np_ptr(out)))
         return out
 
@@ -245,3 +283,52 @@ class PinnedBuffer:
             self._ptr = ctypes.c_void_p()
 
     __del__ = close
+
+
+class PinnedPool:
+    """Page-locked result buffers for the host entry points.
+
+    `filter_block` must return a fresh, writable array that does not alias internal state (the
+    reference's callers scale it in place, ``_jack_client.py:795``).  A new pageable ``np.empty`` per
+    block costs an mmap / page-fault / munmap cycle and a staged (not direct) device-to-host copy.
+    The pool hands out views of page-locked buffers instead and takes a buffer back once the
+    caller has dropped every reference to it (``sys.getrefcount`` of the buffer's root array: views
+    handed out -- and views of those views -- keep the root alive and counted).  A caller that
+    keeps many results simply makes the pool grow, up to `max_bytes`; beyond that, and for tiny
+    blocks, plain ``np.empty`` arrays are returned.
+    """
+
+    def __init__(self, max_bytes=1 << 30, min_bytes=1 << 16):
+        self._roots = {}  # nbytes -> [root arrays (1-D uint8 views of page-locked memory)]
+        self._bufs = []   # PinnedBuffer owners
+        self._bytes = 0
+        self.max_bytes, self.min_bytes = max_bytes, min_bytes
+
+    def take(self, shape, dtype=np.float32):
+        import sys
+
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        if n < self.min_bytes:
+            return np.empty(shape, dtype=dtype)
+        roots = self._roots.setdefault(n, [])
+        for root in roots:
+            if sys.getrefcount(root) == 3:  # the list, the loop variable, getrefcount's argument
+                return root.view(dtype).reshape(shape)
+        if self._bytes + n > self.max_bytes:
+            return np.empty(shape, dtype=dtype)
+        try:
+            buf = PinnedBuffer((n,), np.uint8)
+        except (MemoryError, RuntimeError):
+            return np.empty(shape, dtype=dtype)
+        self._bufs.append(buf)
+        self._bytes += n
+        root = buf.array
+        while isinstance(root.base, np.ndarray):  # numpy parents every view to the array over the raw buffer
+            root = root.base
+        buf.array = None  # the pool's list holds the only long-lived reference to the root
+        roots.append(root)
+        return root.view(dtype).reshape(shape)
+
+
+_OUT_POOL = PinnedPool()

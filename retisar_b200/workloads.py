@@ -9,9 +9,12 @@ FS = 48000
 
 # name -> (array grid, SH order, block length, HRIR taps, description)
 CONFIGS = {
-    "c1": dict(grid="em32", order=4, block=4096, hrir_taps=128,
-               desc="Eigenmike em32 (32 ch), SH order 4, 4096-sample block (the reference's default "
-                    "block length, config.py:9), 128-tap HRIR"),
+    "c1": dict(grid="em32", order=4, block=256, hrir_taps=128,
+               desc="Eigenmike em32 (32 ch), SH order 4, 256-sample block, 128-tap KU100-shaped HRIR, "
+                    "ONE stream (BASELINE config 1: the reference's own CPU-runnable case)"),
+    "b4096": dict(grid="em32", order=4, block=4096, hrir_taps=128,
+                  desc="Eigenmike em32 (32 ch), SH order 4, 4096-sample block (the reference's default "
+                       "block length, config.py:9), 128-tap HRIR"),
     "c2": dict(grid="em32", order=4, block=256, hrir_taps=128,
                desc="Eigenmike em32 (32 ch), SH order 4, 256-sample block, 128-tap KU100-shaped HRIR"),
     "c3": dict(grid="le110", order=8, block=256, hrir_taps=4096,

@@ -86,3 +86,26 @@ def test_feeder_device_output_stage_and_renderer():
             assert np.allclose(f.last_rms[s], rms, atol=1e-3) and np.allclose(f.last_peak[s], peak, atol=1e-3)
     assert f.get_clipping_counter() >= 1
     assert f.last_rms.shape == (S, 2)
+
+
+@pytest.mark.gpu
+def test_feeder_device_clipping_accounting():
+    """Device path: nothing is counted while detection is off; with detection on and level
+    metering off the count is still delivered by `get_clipping_counter`, and it ADDS to what the
+    host path counted before."""
+    import torch
+
+    from retisar_b200._feeder import BlockFeeder
+
+    B = 64
+    f = BlockFeeder(None, B, 48000, is_measure_levels=False, is_detect_clipping=False)
+    loud = torch.full((5, 2, B), 3.0, device="cuda")
+    f.process_block(loud.clone())
+    assert f.get_clipping_counter() == 0
+    f._is_detect_clipping = True
+    f.process_block(np.full((2, B), 2.0, np.float32))      # host path: 2 clipped channel blocks
+    assert f.get_clipping_counter() == 2
+    f.process_block(loud.clone())                           # device path: 10 more
+    assert f.get_clipping_counter() == 12
+    f.process_block(loud.clone() * 0.1)                     # no clipping
+    assert f.get_clipping_counter() == 12

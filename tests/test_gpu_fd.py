@@ -67,3 +67,12 @@ def test_fd_batched_streams_vs_oracle():
         y = conv.filter_block(x, yaw)
         ref = np.stack([o.filter_block(x[s], yaw[s]) for s, o in enumerate(oracles)])
         assert np.abs(y - ref).max() <= TOL, t
+
+
+def test_fd_plan_refuses_fewer_than_360_directions():
+    """The direction index is int(-azimuth) on a whole-degree grid: fewer than 360 directions would
+    index out of bounds on the device (the reference raises IndexError at run time)."""
+    from retisar_b200.plans import FdPlan
+
+    with pytest.raises(ValueError, match="360 directions"):
+        FdPlan(2, 64, 1, 72, 2)

@@ -17,7 +17,7 @@ def _oracle_for(tb):
                        tb["B"], tb["order"])
 
 
-@pytest.mark.parametrize("workload,S,T", [("c2", 1024, 4), ("c5", 200, 3), ("c4", 301, 3), ("c1", 24, 3)])
+@pytest.mark.parametrize("workload,S,T", [("c2", 1024, 4), ("c5", 200, 3), ("c4", 301, 3), ("b4096", 24, 3)])
 def test_spot_streams_match_oracle_at_scale(workload, S, T):
     from retisar_b200 import workloads as wl
 

@@ -106,3 +106,39 @@ def test_mono_in_many_out_tensor_core_path(B, Cout, P, S):
                 o.clear()
             worst = max(worst, float(np.abs(y[s] - o.filter_block(x[t, s])).max()))
     assert worst <= TOL, worst
+
+
+def test_reset_is_ordered_against_blocks_in_flight_and_mono_after_full_width():
+    """`filter_block(None)` / `_clear_buffers` right behind a device block on a non-blocking stream
+    must clear the state that block wrote (the reset drains the device first), and a mono block
+    after full-width ones is broadcast into the same state like `_convolver.py:588-591`."""
+    import torch
+
+    from oracle import sh_chain as oc
+    from retisar_b200 import Convolver, FilterSet
+    from retisar_b200 import synthetic as syn
+
+    B, taps, n_ch, S = 128, 1000, 3, 64
+    irs = syn.decaying_noise_irs((n_ch, taps), 3)
+    fs = FilterSet.create_instance_by_type(irs, "FIR_MULTICHANNEL")
+    fs.load(block_length=B, is_single_precision=True, is_prevent_logging=True)
+    conv = Convolver.create_instance_by_filter_set(fs, B, n_streams=S)
+    side = torch.cuda.Stream()
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal((6, S, n_ch, B)) * 0.1).astype(np.float32)
+    with torch.cuda.stream(side):
+        for t in range(3):
+            conv.filter_block(torch.from_numpy(x[t]).cuda())
+        conv._clear_buffers()  # must wait for the three blocks above, then clear
+        y = conv.filter_block(torch.from_numpy(x[3]).cuda())
+    side.synchronize()
+    o = oc.OlsOracle(fs.get_filter_blocks_fd(), B)
+    ref = o.filter_block(x[3, 7])
+    assert np.abs(y[7].cpu().numpy() - ref).max() <= 1e-5
+    # mono block after a full-width one: broadcast, state kept
+    xm = x[4][:, :1]
+    ym = conv.filter_block(xm)
+    refm = o.filter_block(xm[7])
+    assert ym.shape == (S, n_ch, B) and np.abs(ym[7] - refm).max() <= 1e-5
+    with pytest.raises(ValueError, match="input channel"):
+        conv.filter_block(x[5][:, :2])

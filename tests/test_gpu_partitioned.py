@@ -105,3 +105,120 @@ def test_partitioned_equals_long_convolution_property():
         y = np.concatenate([conv.filter_block(x[t][:, i * 64:(i + 1) * 64], [33.0]) for i in range(4)], axis=-1)
         ref = o.filter_block(x[t], 33.0)
         assert np.abs(y - ref).max() <= TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config c3 at its real size: Lebedev-110, order 8, 4096-tap HRIR = 16 partitions, B = 256
+# ------------------------------------------------------------------------------------------------
+def _c3_tables(hrir_dirs=150):
+    from retisar_b200 import workloads as wl
+
+    return wl.sh_tables("c3", hrir_dirs=hrir_dirs)
+
+
+def test_c3_full_size_events_match_composition_oracle():
+    """le110 / N = 8 / P = 16 / B = 256 with S = 2051 streams (ragged last tile of every kernel of
+    the partitioned path), 3P + 6 blocks with order / cross-fade / passthrough / clear events.
+    Reference semantics restated by the oracle: queue roll `_convolver.py:645-665`, time-varying
+    multiply `:838-866`, the TODO sketch `:1265-1269`.  Inputs live on the device; the probe
+    streams are copied back for the per-stream numpy oracle."""
+    import torch
+
+    from oracle import sh_chain as oc
+    from retisar_b200 import workloads as wl
+
+    S = 2051
+    tb = _c3_tables()
+    conv = wl.make_renderer(tb, S)
+    hnm = tb["hrir_set"].get_filter_blocks_nm()
+    cfg = tb["sh_config"]
+    B, C, order = tb["B"], tb["C"], tb["order"]
+    P = hnm.shape[0]
+    assert (P, B, C, order) == (16, 256, 110, 8) and conv._plan.P == 16
+    probes = [0, 1, 127, 128, 1023, 2047, 2048, S - 1]
+    oracles = {s: oc.ShPartitionedOracle(cfg.sh_m, cfg.sh_bases_weighted, hnm, B, order) for s in probes}
+    T = 3 * P + 6
+    events = {P + 1: ("order", 5), P + 3: ("order", order), P + 4: ("crossfade", 0),
+              2 * P + 2: ("crossfade", 1), 2 * P + 4: ("passthrough", 1), 2 * P + 5: ("passthrough", 0),
+              3 * P + 2: ("clear", 0)}
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(33)
+    yaw = torch.rand((S,), generator=gen, device=dev) * 360.0
+    worst, peak = 0.0, 0.0
+    idx = torch.as_tensor(probes, device=dev)
+    for t in range(T):
+        if t in events:
+            kind, val = events[t]
+            for o in oracles.values():
+                if kind == "order":
+                    o.set_order(val)
+                elif kind == "crossfade":
+                    o.set_crossfade(bool(val))
+                elif kind == "passthrough":
+                    o.is_passthrough = bool(val)
+                else:
+                    o.clear()
+            if kind == "order":
+                conv.update_sh_processing(val)
+            elif kind == "crossfade":
+                conv.set_crossfade(bool(val))
+            elif kind == "passthrough":
+                conv.set_passthrough(bool(val))
+            else:
+                conv._clear_buffers()
+        x = torch.randn((S, C, B), generator=gen, device=dev) * 0.1
+        yaw = yaw + (torch.rand((S,), generator=gen, device=dev) - 0.5) * 40.0
+        y = conv.filter_block(x, yaw)
+        xs, ys, yaws = x[idx].cpu().numpy(), y[idx].cpu().numpy(), yaw[idx].cpu().numpy()
+        assert bool(torch.isfinite(y).all())
+        for i, s in enumerate(probes):
+            ref = oracles[s].filter_block(xs[i], yaws[i])
+            err = float(np.abs(ys[i] - ref).max())
+            worst, peak = max(worst, err), max(peak, float(np.abs(ref).max()))
+            assert err <= TOL, (t, s, err, events.get(t))
+    print(f"c3 full size: S {S} P {P} max abs err {worst:.3g} (peak {peak:.3g}, rel {worst / peak:.3g})")
+    assert worst <= 2e-6, worst  # regression bar, well inside the 1e-5 contract
+
+
+def test_c3_p16_fixed_yaw_equals_reference_pinned_oracle_on_long_block():
+    """Pin that does not depend on the composition oracle: with a fixed yaw and the cross-fade off
+    the 16-partition renderer at B = 256 must equal the single-partition renderer at B = 4096 --
+    and that one is `ShOracle`, pinned bit for bit to the unmodified reference."""
+    from oracle import sh_chain as oc
+    from retisar_b200 import synthetic as syn
+    from retisar_b200 import workloads as wl
+    from retisar_b200._filter_set import FilterSetMiro
+
+    tb = _c3_tables()
+    S = 130  # more than one 128-row tile
+    conv = wl.make_renderer(tb, S)
+    conv.set_crossfade(False)
+    cfg, C, order = tb["sh_config"], tb["C"], tb["order"]
+    long_b = 4096
+    irs = tb["hrir_set"]._irs_td[:, :, :long_b]
+    grid = tb["hrir_set"]._irs_grid
+    hr2 = FilterSetMiro.from_arrays(irs, grid.azimuth, grid.colatitude, None, order, True)
+    hr2.load(long_b, True, is_prevent_logging=True)
+    hr2.calculate_filter_blocks_fd(long_b)
+    hr2.calculate_filter_blocks_nm()
+    assert hr2.get_filter_blocks_nm().shape[0] == 1
+    yaws = np.linspace(-170.0, 185.0, S).astype(np.float32)
+    probes = [0, 64, 128, S - 1]
+    oracles = {}
+    for s in probes:
+        o = oc.ShOracle(cfg.sh_m, cfg.sh_bases_weighted, hr2.get_filter_blocks_nm(), long_b, order)
+        o.set_crossfade(False)
+        oracles[s] = o
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for t in range(2):
+        x = (rng.standard_normal((S, C, long_b)) * 0.1).astype(np.float32)
+        y = np.concatenate([conv.filter_block(np.ascontiguousarray(x[:, :, i * 256:(i + 1) * 256]), yaws)
+                            for i in range(long_b // 256)], axis=-1)
+        for s, o in oracles.items():
+            ref = o.filter_block(x[s], yaws[s])
+            err = float(np.abs(y[s] - ref).max())
+            worst = max(worst, err)
+            assert err <= TOL, (t, s, err)
+    print("c3 P = 16 vs reference-pinned B = 4096 oracle: max abs err", worst)

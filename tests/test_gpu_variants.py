@@ -1,5 +1,5 @@
-"""The kernel variants that are off by default (measured without gain or superseded, kept as
-documented experiments / fallbacks) stay parity-green: each is switched on through its environment variable before the
+"""The kernel variants that are off by default (fallbacks selected by geometry or environment) stay
+parity-green: each is switched on through its environment variable before the
 plan is created and run against a reference golden with control events."""
 import numpy as np
 import pytest
@@ -12,11 +12,8 @@ TOL = 1e-5
 
 
 @pytest.mark.parametrize("env", [
-    {"RTB_RENDER_EO": "1"},            # even / odd bins on two warps per stream
-    {"RTB_RENDER_SPLIT": "1"},         # two warps per transform, named barriers
     {"RTB_RENDER_MG": "0"},            # term-wise render kernel only
     {"RTB_PDL": "1"},                  # programmatic dependent launch
-    {"RTB_OVERLAP_CHUNKS": "3"},       # analysis | render on two streams
     {"RTB_ANALYSIS_TC": "0"},          # mma.sync (warp-level tensor core) analysis GEMM
     {"RTB_ANALYSIS_TC": "0", "RTB_ANALYSIS_MMA": "0"},  # FFMA2 SIMT analysis GEMM
     {"RTB_TC_NST": "2"},               # tcgen05 analysis with two operand stages (4-warp loader groups)
@@ -33,7 +30,7 @@ def test_variant_matches_reference_golden(env, monkeypatch):
         yaw = np.repeat(g["yaw"][t:t + 1], S)
         y = plan.process_host(x, yaw)
         assert np.abs(y - g["y"][t][None]).max() <= TOL, (env, t)
-    # device entry point (the overlap path lives there)
+    # device entry point
     import torch
 
     dev = torch.device("cuda", 0)
