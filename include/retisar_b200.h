@@ -111,9 +111,9 @@ int rtb_sh_wait_block_host(rtb_sh_plan *plan, long long ticket);
 #define RTB_Q_RENDER_NS 7   /* device time of the last block's render kernel   (profiling on)  */
 #define RTB_Q_TENSOR_CORE 8 /* 1 if the analysis GEMM runs on tcgen05 (wide arrays)             */
 #define RTB_Q_RENDER_KERNEL 9 /* render kernel of the last block: 0 sh_render_kernel (term-wise),
-                                 1 sh_render_mg_kernel (grouped by m), 2 sh_render_split_kernel,
-                                 3 partitioned (spectra + partition MAC + tail), 4 passthrough,
-                                 5 sh_render_eo_kernel (even / odd bins on two warps per stream)   */
+                                 1 sh_render_mg_kernel (grouped by m),
+                                 3 partitioned (spectra + SIMT partition MAC + tail), 4 passthrough,
+                                 6 partitioned on tensor cores (sh_partition_tc_kernel)            */
 int rtb_sh_plan_query(rtb_sh_plan *plan, int what, int64_t *value);
 /* record CUDA events around each kernel of process_block (measurement aid, no reference
  * counterpart; the reference reports load through JACK, _jack_client.py:869-895) */

@@ -38,12 +38,12 @@ def extract_grids():
     np.savez_compressed(os.path.join(DATA, "array_grids.npz"), **out)
 
 
-def _array_and_hrir(grid, order, B, hrir_dirs, hrir_taps, seed, enforce_pinv=False):
+def _array_and_hrir(grid, order, B, hrir_dirs, hrir_taps, seed, enforce_pinv=False, array_radius=0.042):
     """Reference FilterSetMiro pair: (array set for Y_w, HRIR set for H_nm)."""
     az, co, w = grid
     arr = rh.make_miro_filter_set(
         np.zeros((1, len(az), B), dtype=np.float32), az, co, w, order, is_hrir=False,
-        block_length=B, enforce_pinv=enforce_pinv)
+        block_length=B, enforce_pinv=enforce_pinv, array_radius=array_radius)
     haz, hco = syn.random_sphere_grid(hrir_dirs, seed + 1)
     hrir = rh.make_miro_filter_set(
         syn.decaying_noise_irs((hrir_dirs, 2, hrir_taps), seed + 2), haz, hco, None, order,
@@ -263,6 +263,42 @@ def golden_levels(name, seed=402):
     print(name, "rms", rms[0])
 
 
+def golden_compensation(name="compensation_em32_le110"):
+    """The reference's own `Compensation.generate_by_type` (`_compensation.py:182-505`) with the
+    third-party design functions bound to the restatements (`ref_harness.inject_compensation_backend`):
+    pins the bookkeeping of `retisar_b200/_compensation.py` -- type lists and "+"-joined strings,
+    once-only application, filter-length budget, per-degree repetition, the (-1)^m factor of the
+    radial filters (`:617-627`), SHF with / without tapering, SDS / EDS masks (`:734-833`), zero
+    padding to the block spectrum length."""
+    ref = rh.import_reference()
+    rh.inject_compensation_backend()
+    C = ref.Compensation
+    em32 = syn.load_array_grid("em32")
+    le110 = syn.load_array_grid("le110")
+    cases = [
+        ("sht_n4_b256", em32, 4, 256, 128, ["SHT"], 18, 0.042),
+        ("sds_n4_b256", em32, 4, 256, 128, ["SDS"], 18, 0.042),
+        ("eds_n8_b128", le110, 8, 128, 64, ["EDS"], 18, 0.0875),
+        ("mrf_n4_b256", em32, 4, 256, 128, ["MRF"], 18, 0.042),
+        ("shf_mrf_n4_b256", em32, 4, 256, 128, ["SHF", "MRF"], 18, 0.042),
+        ("sht_shf_mrf_n8_b256", le110, 8, 256, 100, ["SHT+SHF", "MRF"], 40, 0.0875),
+        ("sds_mrf_mrf_n3_b512", em32, 3, 512, 50, ["SDS", "MRF", "MRF"], 6, 0.042),
+    ]
+    out = {"names": np.array([c[0] for c in cases])}
+    for cname, grid, order, B, taps, types, limit_db, radius in cases:
+        arr, hrir = _array_and_hrir(grid, order, B, 60, taps, 500, array_radius=radius)
+        hrir.calculate_filter_blocks_nm()
+        cfg = arr.get_sh_configuration()
+        C.reset_config(is_plot=False)
+        comp = C.generate_by_type(types, filter_set=hrir, arir_config=cfg.arir_config,
+                                  amp_limit_db=limit_db, nfft=None, nfft_padded=2 * B)
+        out[cname] = np.asarray(comp)
+        out[cname + "_meta"] = np.array([order, B, taps, limit_db, radius], dtype=np.float64)
+        out[cname + "_types"] = np.array(types)
+        print(name, cname, comp.shape, comp.dtype, float(np.abs(comp).max()))
+    np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     extract_grids()
@@ -314,6 +350,8 @@ def main():
     # block delay line of the JACK clients (row f4)
     golden_delay("delay_3ch_b64")
     golden_levels("levels_4ch_b256")
+    # compensation bookkeeping (row f1)
+    golden_compensation()
 
 
 if __name__ == "__main__":

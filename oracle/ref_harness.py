@@ -243,3 +243,28 @@ def make_ssr_filter_set(irs_td, block_length, is_hrir=True, fs=48000):
     fset._dirac_td = np.zeros(fset._irs_td.shape[-2:], dtype=fset._irs_td.dtype)
     fset._dirac_td[:, 0] = 1.0
     return fset
+
+
+def inject_compensation_backend():
+    """Give the stub `sound_field_analysis` the design functions `ReTiSAR/_compensation.py` calls
+    (`gen.radial_filter_fullspec` :586, `process.rfi` :595, `gen.spherical_head_filter_spec` :659,
+    `gen.delay_fd` :670, `gen.tapering_window` :713, `utils.zero_pad_fd` :505), bound to the
+    restatements in `retisar_b200/_compensation.py` under the third-party package's call
+    signatures.  With them the reference's OWN `Compensation.generate_by_type` runs unmodified, so
+    its bookkeeping -- type parsing, once-only application, filter-length budget, per-degree
+    repetition, the (-1)^m factor of the radial filters, SDS / EDS masks, zero padding -- produces
+    goldens for this repository's `Compensation`.  The design VALUES stay restated (the package is
+    absent): those remain parity-unpinned."""
+    import_reference()
+    from retisar_b200 import _compensation as own
+
+    sfa = sys.modules["sound_field_analysis"]
+    sfa.gen.radial_filter_fullspec = lambda max_order, NFFT, fs, array_configuration, amp_maxdB=40: \
+        own.radial_filter_fullspec(max_order, NFFT, fs, array_configuration, amp_maxdB)
+    sfa.process.rfi = lambda FIR, kernelSize=512: own.rfi(FIR, kernelSize)
+    sfa.gen.spherical_head_filter_spec = lambda max_order, NFFT, fs, radius, is_tapering=False: \
+        own.spherical_head_filter_spec(max_order, NFFT, fs, radius, is_tapering)
+    sfa.gen.delay_fd = lambda target_length_fd, delay_samples: own.delay_fd(target_length_fd, delay_samples)
+    sfa.gen.tapering_window = lambda max_order: own.tapering_window(max_order)
+    sfa.utils.zero_pad_fd = lambda data_fd, target_length_td: own.zero_pad_fd(data_fd, target_length_td)
+

@@ -15,7 +15,7 @@ RTB_OK, RTB_ERR_INVALID, RTB_ERR_STATE, RTB_ERR_UNSUPPORTED, RTB_ERR_CUDA, RTB_E
 RTB_Q_SYMMETRIC, RTB_Q_ROWS, RTB_Q_SIGNALS, RTB_Q_LAUNCHES, RTB_Q_STATE_BYTES = 1, 2, 3, 4, 5
 RTB_Q_ANALYSIS_NS, RTB_Q_RENDER_NS, RTB_Q_TENSOR_CORE, RTB_Q_RENDER_KERNEL = 6, 7, 8, 9
 RENDER_KERNEL_NAMES = {0: "sh_render_kernel", 1: "sh_render_mg_kernel", 2: "sh_render_split_kernel",
-                       3: "sh_partition_mac_kernel", 4: "sh_passthrough_kernel", 5: "sh_render_eo_kernel"}
+                       3: "sh_partition_mac2_kernel", 4: "sh_passthrough_kernel", 6: "sh_partition_tc_kernel"}
 
 # every symbol include/retisar_b200.h declares: name -> (restype, argtypes)
 _c_float_p = ctypes.POINTER(ctypes.c_float)

@@ -216,6 +216,7 @@ __device__ __forceinline__ float2 phase_of(const float2 *cs, int m) {
 #include "sh_render.cuh"
 #include "sh_render_mg.cuh"
 #include "sh_partitioned.cuh"
+#include "sh_partitioned_tc.cuh"
 
 namespace rtb {
 

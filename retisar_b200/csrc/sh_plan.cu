@@ -59,6 +59,13 @@ struct rtb_sh_plan {
     int Fp = 0;
     float2 *d_zspec = nullptr;    // [S][NP][N2]
     float2 *d_qcur = nullptr, *d_qlast = nullptr;  // [S][P][2][Fp]
+    // tensor-core partition MAC (sh_partitioned_tc.cuh): stream-minor layout of the spectra
+    // [N2][NP][Spad] and of the queues [F][P][2][Spad], split H operand per bin and K-chunk
+    bool pt_enabled = false;
+    long long pt_Spad = 0;
+    int pt_Npad = 0, pt_acc_cols = 0, pt_chunks_max = 0, pt_smem = 0, pt_grid = 0;
+    float *d_pt_b = nullptr;
+    const float *pt_hnm_src = nullptr;
     int head_cur = 0, head_last = 0;
     // staging for the host-buffer entry points: RTB_HOST_SLOTS device copies of (input block, yaw,
     // output block) so that the input copy of block t+1 overlaps the kernels and the result copy
@@ -284,7 +291,50 @@ std::vector<float4> build_htab(const rtb_sh_plan *p, const float *hnm) {
     return htab;
 }
 
-size_t queue_elems(const rtb_sh_plan *p) { return (size_t)p->S * p->P * 2 * p->Fp; }
+size_t queue_elems(const rtb_sh_plan *p) {
+    if (p->pt_enabled) return (size_t)p->F * p->P * 2 * (size_t)p->pt_Spad;
+    return (size_t)p->S * p->P * 2 * p->Fp;
+}
+
+// Split H operand of the tensor-core partition MAC: per bin f and K-chunk the matrix
+// B[n = ((q*2 + ear)*2 + re/im)][k = 2*step + re/im] of the real embedding of the complex product,
+//   k even (a_re): (Hr, Hi);  k odd (a_im): (-Hi, Hr),
+// in the K-major core-matrix layout [k/4][n/8][n%8][k%4], TF32 hi block then lo block.
+std::vector<float> build_pt_b(const rtb_sh_plan *p, const float *hnm) {
+    const int F = p->F, K = p->K, P = p->P, Npad = p->pt_Npad, KC = RTB_PT_KC;
+    const int NP = (int)p->sig_k1.size();
+    struct Step { int k; float sg; };
+    std::vector<Step> steps;
+    for (int q = 0; q < NP; ++q) {
+        steps.push_back({p->sig_k1[q], 1.f});
+        if (p->sig_k2[q] >= 0) steps.push_back({p->sig_k2[q], p->sig_sign2[q]});
+    }
+    const size_t per_chunk = (size_t)2 * KC * Npad, per_bin = per_chunk * p->pt_chunks_max;
+    std::vector<float> b(per_bin * F, 0.f);
+    for (int f = 0; f < F; ++f)
+        for (size_t j = 0; j < steps.size(); ++j)
+            for (int part = 0; part < P; ++part)
+                for (int e = 0; e < 2; ++e) {
+                    const size_t hi_ = 2 * ((((size_t)part * K + steps[j].k) * 2 + e) * F + f);
+                    const float hr = steps[j].sg * hnm[hi_], him = steps[j].sg * hnm[hi_ + 1];
+                    for (int c = 0; c < 2; ++c)        // k = 2j + c
+                        for (int ri = 0; ri < 2; ++ri) {  // n = ((part*2 + e)*2 + ri)
+                            const float v = c == 0 ? (ri == 0 ? hr : him) : (ri == 0 ? -him : hr);
+                            const int k = 2 * (int)j + c, n = (part * 2 + e) * 2 + ri;
+                            const int h = k / KC, kl = k % KC;
+                            const size_t off = ((size_t)(kl / 4) * (Npad / 8) + n / 8) * 32 + (n % 8) * 4 + kl % 4;
+                            uint32_t u;
+                            memcpy(&u, &v, 4);
+                            u = (u + 0x1000u) & 0xffffe000u;  // round to nearest TF32
+                            float hi;
+                            memcpy(&hi, &u, 4);
+                            float *blk = b.data() + f * per_bin + h * per_chunk;
+                            blk[off] = hi;
+                            blk[(size_t)KC * Npad + off] = v - hi;
+                        }
+                }
+    return b;
+}
 
 void free_tables(rtb_sh_plan *p) {
     cudaFree(p->d_rmT); p->d_rmT = nullptr;
@@ -301,6 +351,7 @@ void free_tables(rtb_sh_plan *p) {
     cudaFree(p->d_zspec); p->d_zspec = nullptr;
     cudaFree(p->d_qcur); p->d_qcur = nullptr;
     cudaFree(p->d_qlast); p->d_qlast = nullptr;
+    cudaFree(p->d_pt_b); p->d_pt_b = nullptr;
     p->tables_set = false;
 }
 
@@ -477,7 +528,31 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     if (err == cudaSuccess) err = cudaMalloc(&p->d_htab, sizeof(float4) * htab.size());
     if (err == cudaSuccess) err = cudaMalloc(&p->d_signals, sizeof(ShSignal) * NP);
     if (p->P > 1) {
-        if (err == cudaSuccess) err = cudaMalloc(&p->d_zspec, sizeof(float2) * (size_t)p->S * NP * p->N2);
+        // tensor-core partition MAC: default from 64 streams up (RTB_PART_TC=0 / 1 forces); needs
+        // N = 4P <= 128 accumulator columns (two yaws, double buffered in 512 TMEM columns) and the
+        // two phase tables next to four operand stages in shared memory
+        p->pt_enabled = false;
+        const int Npad = (4 * p->P + 15) / 16 * 16;
+        const char *env = getenv("RTB_PART_TC");
+        const bool want = env ? env[0] != '0' : p->S >= 64;
+        const size_t stage_bytes = sizeof(float) * ((size_t)2 * 2 * RTB_PT_KC * 128 + (size_t)2 * RTB_PT_KC * Npad);
+        const size_t pt_smem = RTB_PT_LG * stage_bytes + sizeof(float2) * 2 * 2 * (size_t)(p->order + 1) * 128;
+        if (want && Npad <= 128 && pt_smem <= 220 * 1024) {
+            p->pt_enabled = true;
+            p->pt_Npad = Npad;
+            p->pt_acc_cols = Npad <= 32 ? 32 : (Npad <= 64 ? 64 : 128);
+            p->pt_Spad = ((long long)p->S + 127) / 128 * 128;
+            p->pt_smem = (int)pt_smem;
+            int n_steps = 0;
+            for (int q = 0; q < NP; ++q) n_steps += sig[q].m2 != RTB_NO_TERM ? 2 : 1;
+            p->pt_chunks_max = (2 * n_steps + RTB_PT_KC - 1) / RTB_PT_KC;
+            int n_sm = 148;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device);
+            p->pt_grid = n_sm;
+        }
+        const size_t zspec_elems = p->pt_enabled ? (size_t)p->N2 * NP * (size_t)p->pt_Spad : (size_t)p->S * NP * p->N2;
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_zspec, sizeof(float2) * zspec_elems);
+        if (err == cudaSuccess) err = cudaMemset(p->d_zspec, 0, sizeof(float2) * zspec_elems);  // padding rows stay finite
         if (err == cudaSuccess) err = cudaMalloc(&p->d_qcur, sizeof(float2) * queue_elems(p));
         if (err == cudaSuccess) err = cudaMalloc(&p->d_qlast, sizeof(float2) * queue_elems(p));
         if (err == cudaSuccess) err = cudaMemset(p->d_qcur, 0, sizeof(float2) * queue_elems(p));
@@ -491,6 +566,15 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     RTB_CUDA(cudaMemcpy(p->d_rmT, rmT.data(), sizeof(float) * rmT.size(), cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_htab, htab.data(), sizeof(float4) * htab.size(), cudaMemcpyHostToDevice));
     RTB_CUDA(cudaMemcpy(p->d_signals, sig.data(), sizeof(ShSignal) * NP, cudaMemcpyHostToDevice));
+    if (p->pt_enabled) {
+        const std::vector<float> b = build_pt_b(p, hnm);
+        cudaError_t e2 = cudaMalloc(&p->d_pt_b, sizeof(float) * b.size());
+        if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_pt_b, b.data(), sizeof(float) * b.size(), cudaMemcpyHostToDevice);
+        if (e2 != cudaSuccess) {
+            free_tables(p);
+            return fail(RTB_ERR_CUDA, "partition operand upload failed: %s", cudaGetErrorString(e2));
+        }
+    }
     if (p->P > 1) {
         int n_steps = 0;
         for (int q = 0; q < NP; ++q) n_steps += sig[q].m2 != RTB_NO_TERM ? 2 : 1;
@@ -657,6 +741,10 @@ int rtb_sh_plan_update_filter(rtb_sh_plan *p, const float *hnm) {
     // reference's in-place `_irs_blocks_nm *= comp_nm` under a cleared IS_RUNNING
     RTB_CUDA(cudaDeviceSynchronize());
     RTB_CUDA(cudaMemcpy(p->d_htab, htab.data(), sizeof(float4) * htab.size(), cudaMemcpyHostToDevice));
+    if (p->pt_enabled) {
+        const std::vector<float> b = build_pt_b(p, hnm);
+        RTB_CUDA(cudaMemcpy(p->d_pt_b, b.data(), sizeof(float) * b.size(), cudaMemcpyHostToDevice));
+    }
     if (p->mg_enabled) {
         p->h_hnm.assign(hnm, hnm + 2 * (size_t)p->K * 2 * p->F);
         return build_mg_tables(p, p->mg_order >= 0 ? p->mg_order : p->cur_order);
@@ -742,7 +830,12 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         p->last_render_kernel = 4;
         const long long total = (long long)count * p->E * p->B;
         sh_passthrough_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_in, d_out, count, p->C, p->E, p->B);
-        if (p->P > 1) {  // queue slot 0 is overwritten and leaves the queue (_convolver.py:558-562, :653-659)
+        if (p->P > 1 && p->pt_enabled) {
+            const long long n = (long long)p->F * 2 * count;
+            sh_queue_clear_head_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                p->d_qcur, count, p->F, p->P, p->pt_Spad, p->head_cur);
+            p->launches++;
+        } else if (p->P > 1) {  // queue slot 0 is overwritten and leaves the queue (_convolver.py:558-562, :653-659)
             const long long n = (long long)count * 2 * p->Fp;
             sh_queue_clear_head_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
                 p->d_qcur + (size_t)s0 * p->P * 2 * p->Fp, count, p->P, p->Fp, p->head_cur);
@@ -773,6 +866,60 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
         const unsigned gw = (unsigned)((count + 3) / 4);
         const dim3 gmac2((unsigned)((p->F + 31) / 32), (unsigned)((count + 2 * RTB_MAC_WARPS - 1) / (2 * RTB_MAC_WARPS)));
+        if (p->pt_enabled) {  // tensor-core partition MAC on the stream-minor layout (whole plan: s0 == 0)
+            p->last_render_kernel = 6;
+            const unsigned gs = (unsigned)((count + 7) / 8);
+#define RTB_PT_LAUNCH(N)                                                                                     \
+    {                                                                                                        \
+        const size_t sm = sizeof(float2) * (size_t)(FftCfg<N>::GROUPS * N) * 9;                              \
+        kernel_attrs_once(sh_spectra_soa_kernel<N>, 100 * 1024, true);                                       \
+        sh_spectra_soa_kernel<N><<<gs, 256, sm, st>>>(prm, p->d_zspec, p->pt_Spad);                          \
+    }
+            switch (p->N2) {
+                case 64: RTB_PT_LAUNCH(64) break;
+                case 128: RTB_PT_LAUNCH(128) break;
+                case 256: RTB_PT_LAUNCH(256) break;
+                default: RTB_PT_LAUNCH(512) break;
+            }
+#undef RTB_PT_LAUNCH
+            ShPartTcParams tp;
+            tp.zspecT = p->d_zspec; tp.bsrc = p->d_pt_b; tp.steps = p->d_steps;
+            tp.yaw_deg = d_yaw_deg; tp.rad_last_in = prm.rad_last_in;
+            tp.qcurT = p->d_qcur; tp.qlastT = p->d_qlast;
+            tp.Spad = p->pt_Spad; tp.S = count;
+            tp.F = p->F; tp.N2 = p->N2; tp.NPT = p->NP; tp.P = p->P; tp.Npad = p->pt_Npad; tp.acc_cols = p->pt_acc_cols;
+            tp.nsteps_cur = prm.nsteps_cur; tp.nsteps_last = prm.nsteps_last;
+            const int nsteps = std::max(prm.nsteps_cur, prm.nsteps_last);
+            tp.n_chunks = (2 * nsteps + RTB_PT_KC - 1) / RTB_PT_KC;
+            tp.n_chunks_max = p->pt_chunks_max;
+            tp.order_max = p->order; tp.do_last = p->crossfade ? 1 : 0;
+            tp.head_cur = p->head_cur; tp.head_last = p->head_last;
+            tp.tracker_dir = p->tracker_dir; tp.src_azim16 = p->src_azim16;
+            kernel_attrs_once(sh_partition_tc_kernel, 220 * 1024);  // + 3 KB static (barriers, step list)
+            const int n_stiles_total = (count + 127) / 128;
+            if (tp.n_chunks > 0)
+                // a launch covers at most as many stream tiles as there are CTAs, so that the contiguous
+                // run of tiles of a CTA (<= F tiles) meets at most two stream tiles
+                for (int st0 = 0, per = std::min(RTB_PT_MAX_STILES_PER_LAUNCH, p->pt_grid); st0 < n_stiles_total; st0 += per) {
+                    tp.s0 = st0 * 128;
+                    tp.n_stiles = std::min(per, n_stiles_total - st0);
+                    ShPartTcParams q = tp;
+                    q.zspecT = tp.zspecT + tp.s0; q.qcurT = tp.qcurT + tp.s0; q.qlastT = tp.qlastT + tp.s0;
+                    const long long n_tiles = (long long)q.n_stiles * p->F;
+                    const int grid = (int)std::min<long long>(n_tiles, p->pt_grid);
+                    sh_partition_tc_kernel<<<grid, RTB_PT_THREADS, p->pt_smem, st>>>(q);
+                    p->launches++;
+                }
+#define RTB_PT_TAIL(N) sh_partition_tail_soa_kernel<N><<<gw, 128, 0, st>>>(prm, p->d_qcur, p->d_qlast, p->pt_Spad);
+            switch (p->N2) {
+                case 64: RTB_PT_TAIL(64) break;
+                case 128: RTB_PT_TAIL(128) break;
+                case 256: RTB_PT_TAIL(256) break;
+                default: RTB_PT_TAIL(512) break;
+            }
+#undef RTB_PT_TAIL
+            p->launches++;
+        } else {
 #define RTB_PART_LAUNCH(N)                                                                  \
     case N:                                                                                 \
         sh_spectra_kernel<N><<<gw, 128, 0, st>>>(prm);                                      \
@@ -785,6 +932,7 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         }
 #undef RTB_PART_LAUNCH
         p->launches += 2;
+        }
     } else {
         const int np_cur = signals_for_order(p, p->cur_order);
         const int np_last = (p->crossfade && p->last_valid) ? signals_for_order(p, p->last_order) : 0;

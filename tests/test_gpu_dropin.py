@@ -102,9 +102,12 @@ def test_reference_renderer_client_fir_filter_and_controls(monkeypatch):
 def test_reference_renderer_client_sh_renderer(monkeypatch):
     """The binaural renderer behind the reference client: `JackRenderer._process`,
     `set_client_crossfade` (`:351-377`) and the tracker array read per block; the convolvers are
-    built from the same synthetic em32 / HRIR tables on both sides."""
+    built from the same synthetic em32 / HRIR tables on both sides.  The reference client runs
+    first, completely, with the reference's classes; then the module is patched and the same
+    session is replayed on this repository's classes."""
     rh, jr = _reference()
     import ReTiSAR
+    from retisar_b200 import Convolver
     from retisar_b200 import workloads as wl
 
     tb = wl.sh_tables("c2", hrir_dirs=240)
@@ -112,8 +115,25 @@ def test_reference_renderer_client_sh_renderer(monkeypatch):
     irs = np.zeros((2, B), np.float32)
     irs[:, 0] = 1
     kw = dict(name="sh", block_length=B, filter_name=irs, filter_type="FIR_MULTICHANNEL", **CLIENT_KW)
-    r_ref = _alive(jr.JackRenderer(**kw))
     tracker = rh.make_tracker()
+    azim = ReTiSAR.HeadTracker.DataIndex.AZIM
+    T = 12
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((T, C, B)) * 0.1).astype(np.float32)
+
+    def session(client):
+        client._is_passthrough = False
+        outs = []
+        for t in range(T):
+            if t == 5:
+                assert client.set_client_crossfade(False) is False
+            if t == 8:
+                assert client.set_client_crossfade(True) is True
+            tracker[azim] = float(37.5 * t - 100.0)
+            outs.append(client._process(x[t].copy()).copy())
+        return np.stack(outs)
+
+    r_ref = _alive(jr.JackRenderer(**kw))
     hr, ar = tb["hrir_set"], tb["array_set"]
     ref_arr = rh.make_miro_filter_set(np.zeros((1, C, B), np.float32), ar._irs_grid.azimuth,
                                       ar._irs_grid.colatitude, ar._irs_grid.weight, order, False, B)
@@ -121,27 +141,15 @@ def test_reference_renderer_client_sh_renderer(monkeypatch):
                                        hr._irs_grid.colatitude, None, order, True, B)
     ref_hrir.calculate_filter_blocks_fd(B)
     r_ref._convolver = rh.make_sh_convolver(ref_hrir, ref_arr, B, tracker)
+    y_ref = session(r_ref)
+
     _swap_in_repo_classes(monkeypatch, jr)
     r_new = _alive(jr.JackRenderer(**kw))
-    from retisar_b200 import Convolver
-
     conv = Convolver.create_instance_by_filter_set(hr, B, [(0, 0)], tracker)
     conv.prepare_sh_processing(tb["sh_config"], 0, None, comp_nm=tb["comp_nm"])
     r_new._convolver = conv
     assert type(r_new._convolver) is jr.AdjustableShConvolver  # the class identity callers test
-    for r in (r_ref, r_new):
-        r._is_passthrough = False
-    azim = ReTiSAR.HeadTracker.DataIndex.AZIM
-    rng = np.random.default_rng(3)
-    worst = 0.0
-    for t in range(12):
-        if t == 5:
-            assert r_ref.set_client_crossfade(False) is False and r_new.set_client_crossfade(False) is False
-        if t == 8:
-            r_ref.set_client_crossfade(True); r_new.set_client_crossfade(True)
-        tracker[azim] = float(37.5 * t - 100.0)
-        x = (rng.standard_normal((C, B)) * 0.1).astype(np.float32)
-        y_ref, y_new = r_ref._process(x.copy()), r_new._process(x.copy())
-        worst = max(worst, float(np.abs(y_new - y_ref).max()))
-        assert np.abs(y_new - y_ref).max() <= TOL, t
-    print("reference JackRenderer with the CUDA SH renderer: max abs err", worst)
+    y_new = session(r_new)
+    err = np.abs(y_new - y_ref).reshape(T, -1).max(axis=1)
+    assert err.max() <= TOL, err
+    print("reference JackRenderer with the CUDA SH renderer: max abs err", err.max(), "peak", np.abs(y_ref).max())

@@ -28,17 +28,20 @@ def build(grid_name, order, B, taps, n_dirs, seed):
     return arr, hrir, len(az)
 
 
+@pytest.mark.parametrize("tc", ["0", "1"])  # SIMT partition MAC / tensor-core partition MAC (forced)
 @pytest.mark.parametrize("grid_name,order,B,taps,S", [
     ("em32", 4, 64, 200, 3),     # P = 4
     ("rnd", 3, 32, 90, 5),       # P = 3 (not a multiple of the register tile)
     ("le110", 8, 128, 700, 2),   # P = 6, order 8
     ("em32", 4, 256, 1100, 2),   # P = 5 at the headline block length
+    ("em32", 4, 256, 1100, 131), # more than one 128-stream tile, ragged
 ])
-def test_partitioned_sh_matches_composition_oracle(grid_name, order, B, taps, S):
+def test_partitioned_sh_matches_composition_oracle(grid_name, order, B, taps, S, tc, monkeypatch):
     from oracle import sh_chain as oc
-    from retisar_b200 import Convolver
+    from retisar_b200 import Convolver, _capi
     from retisar_b200 import synthetic as syn
 
+    monkeypatch.setenv("RTB_PART_TC", tc)
     arr, hrir, C = build(grid_name, order, B, taps, 120, 31)
     conv = Convolver.create_instance_by_filter_set(hrir, B, [(0, 0)], None, n_streams=S)
     cfg = arr.get_sh_configuration()
@@ -47,7 +50,8 @@ def test_partitioned_sh_matches_composition_oracle(grid_name, order, B, taps, S)
     hnm = hrir.get_filter_blocks_nm()
     P = hnm.shape[0]
     assert P == -(-taps // B) and conv._plan.P == P
-    oracles = [oc.ShPartitionedOracle(cfg.sh_m, cfg.sh_bases_weighted, hnm, B, order) for _ in range(S)]
+    probes = list(range(S)) if S <= 8 else [0, 1, 63, 64, 127, 128, S - 1]
+    oracles = {s: oc.ShPartitionedOracle(cfg.sh_m, cfg.sh_bases_weighted, hnm, B, order) for s in probes}
     T = 3 * P + 6
     x = syn.noise_blocks(T, S * C, B, 7).reshape(T, S, C, B)
     yaw = np.stack([syn.yaw_walk(T, 50 + s, step=25.0) for s in range(S)], axis=1)
@@ -58,7 +62,7 @@ def test_partitioned_sh_matches_composition_oracle(grid_name, order, B, taps, S)
     for t in range(T):
         if t in events:
             kind, val = events[t]
-            for o in oracles:
+            for o in oracles.values():
                 if kind == "order":
                     o.set_order(val)
                 elif kind == "crossfade":
@@ -76,11 +80,14 @@ def test_partitioned_sh_matches_composition_oracle(grid_name, order, B, taps, S)
             else:
                 conv._clear_buffers()
         y = conv.filter_block(x[t], yaw[t])
-        ref = np.stack([o.filter_block(x[t, s], yaw[t, s]) for s, o in enumerate(oracles)])
-        err = np.abs(y - ref).max()
+        ref = np.stack([o.filter_block(x[t, s], yaw[t, s]) for s, o in oracles.items()])
+        err = np.abs(y[probes] - ref).max()
         worst = max(worst, err)
         assert err <= TOL, (t, err, events.get(t))
-    print(grid_name, order, B, "P", P, "max abs err", worst, "peak", np.abs(ref).max())
+        if not conv._is_passthrough:
+            want = _capi.RENDER_KERNEL_NAMES[6 if tc == "1" else 3]
+            assert _capi.RENDER_KERNEL_NAMES[conv._plan.query(_capi.RTB_Q_RENDER_KERNEL)] == want
+    print(grid_name, order, B, "P", P, "tc", tc, "max abs err", worst, "peak", np.abs(ref).max())
 
 
 def test_partitioned_equals_long_convolution_property():
