@@ -101,6 +101,15 @@ int rtb_sh_submit_block_host(rtb_sh_plan *plan, const float *h_in, const float *
                              float *h_out, long long *ticket);
 int rtb_sh_wait_block_host(rtb_sh_plan *plan, long long ticket);
 
+/* Optional headphone-compensation filter (HPCF) behind the renderer.  The reference chains it as a
+ * separate client after the renderer (_run.py:290-338): a 2-in / 2-out channel-wise
+ * OverlapSaveConvolver (_convolver.py:524-571) fed with the binaural block.  Here the warp that
+ * produced a stream's ear signals continues with the filter in the same launch (input-side delay
+ * line of n_partitions binaural spectra per stream).  hfd [n_partitions][2][F] complex =
+ * FilterSet.get_filter_blocks_fd() of the HPCF set (_filter_set.py:625-664); n_partitions == 0
+ * (hfd may be NULL) detaches the filter.  Attaching resets the filter's own state only. */
+int rtb_sh_plan_set_hpcf(rtb_sh_plan *plan, const float *hfd, int n_partitions);
+
 /* introspection: what = RTB_Q_* */
 #define RTB_Q_SYMMETRIC 1   /* 1 if Y_w has the (n,-m) conjugate symmetry (real analysis path) */
 #define RTB_Q_ROWS 2        /* J: real analysis rows per stream                                */

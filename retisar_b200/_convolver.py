@@ -365,6 +365,7 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         self._comp_arir_config = None
         self._comp_mrf_limit = None
         self._comp_nm_override = None
+        self._hpcf_filter = None
 
     def __copy__(self):
         """The reference raises here ("not tested", ``_convolver.py:1051-1060``); this returns an
@@ -424,6 +425,8 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         self._plan.set_source(float(self._sources_deg[0, 0]), 1 if self._filter._is_hrir else -1)
         self._plan.set_crossfade(self._is_crossfade)
         self._plan.set_passthrough(self._is_passthrough)
+        if self._hpcf_filter is not None:
+            self.set_hpcf(self._hpcf_filter)
 
     def update_sh_processing(self, sh_new_order, logger=None):
         """Change the rendering order at run time (``_convolver.py:1123-1168``)."""
@@ -512,6 +515,24 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         x = np.asarray(input_block_td, dtype=np.float32)
         out = plan.process_host(x.reshape(plan.S, plan.C, plan.B), yaw_deg)
         return out if x.ndim == 3 else out[0]
+
+    def set_hpcf(self, hpcf_filter_set):
+        """Extension: run a headphone-compensation filter behind the renderer inside the renderer's
+        own kernels.  The reference chains the HPCF as a separate client
+        (``_run.py:290-338`` -> ``OverlapSaveConvolver.filter_block``, ``_convolver.py:524-571``);
+        the result is the same, one launch and one HBM round trip of the binaural block less.
+        `hpcf_filter_set`: a loaded 2-channel ``FilterSetMultiChannel`` (``None`` detaches)."""
+        self._hpcf_filter = hpcf_filter_set
+        if self._plan is None:
+            return  # applied by `_install_tables` once the renderer is prepared
+        if hpcf_filter_set is None:
+            self._plan.set_hpcf(None)
+            return
+        hpcf_filter_set.calculate_filter_blocks_fd(self._block_length)
+        hfd = hpcf_filter_set.get_filter_blocks_fd()  # [P, 1, 2, F] ([P, 2, 1, F] for an "HPCF_FIR" set)
+        if hfd.shape[1] * hfd.shape[2] != 2:
+            raise ValueError(f"the headphone compensation filter must have 2 channels, got {hfd.shape[1:3]}")
+        self._plan.set_hpcf(hfd.reshape(hfd.shape[0], 2, hfd.shape[-1]))
 
     def submit_block(self, input_block_td, yaw_deg=None):
         """Extension: asynchronous ``filter_block`` for host blocks.  Returns a ticket whose

@@ -497,15 +497,15 @@ __device__ __forceinline__ void fft_hermitian_fill(float2 (&X)[FftCfg<N2>::EPL],
 
 // Launch of a kernel built on FftCfg<N2>: `tasks` transforms-in-flight (streams, channel pairs...),
 // TASKS per CTA; CTA-wide transforms get their exchange buffer as dynamic shared memory.
-template <int N2, class Kernel, class Params>
+template <int N2, class Kernel, class Params, class... Extra>
 inline void fft_kernel_launch(Kernel kernel, const Params &prm, long long tasks, cudaStream_t st,
-                              size_t extra_smem = 0, int small_tasks_per_cta = 0) {
+                              size_t extra_smem = 0, int small_tasks_per_cta = 0, Extra... extra) {
     using Cfg = FftCfg<N2>;
     const size_t smem = (Cfg::BIG ? sizeof(float2) * Cfg::REGION : 0) + extra_smem;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int per_cta = Cfg::BIG ? 1 : (small_tasks_per_cta ? small_tasks_per_cta : Cfg::TASKS);
     const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
-    kernel<<<grid, Cfg::THREADS, smem, st>>>(prm);
+    kernel<<<grid, Cfg::THREADS, smem, st>>>(prm, extra...);
 }
 
 // N2 = 2 * block length dispatch over every supported size

@@ -183,6 +183,10 @@ struct ShSignal {   // one complex FFT signal (see sh_plan.cu: build_signals)
 #define RTB_NO_TERM 0x7fffffff
 #define RTB_MAX_ORDER 31
 
+}  // namespace rtb
+#include "hpcf_stage.cuh"
+namespace rtb {
+
 struct ShRenderParams {
     const float *zprev;          // [S][J][B] analysis rows of the previous block
     const float *zcur;           // [S][J][B] analysis rows of the current block
@@ -201,6 +205,7 @@ struct ShRenderParams {
     int order_max;               // SH order (for the phase tables)
     int crossfade;
     float tracker_dir, src_azim16;
+    HpcfParams hp;               // optional HPCF stage behind the cross-fade (hp.P == 0: none)
 };
 
 // phase = exp(-i * m * alpha) from the (cos, sin)(|m| alpha) table

@@ -77,6 +77,12 @@ struct rtb_sh_plan {
     bool hslots_ready = false;
     long long submitted = 0;      // blocks submitted through the host entry points (ticket counter)
     cudaStream_t own_stream = nullptr, d2h_stream = nullptr, k_stream = nullptr;
+    // optional headphone-compensation filter behind the renderer (hpcf_stage.cuh): partitions,
+    // filter spectra [P][2][Fp], delay line of binaural spectra [S][P][2][Fp] (ring: hp_slot),
+    // binaural block state [2][S][2][B] (ping-pong: hp_xidx receives the current block)
+    int hp_P = 0, hp_slot = 0, hp_xidx = 0;
+    float2 *d_hp_hfd = nullptr, *d_hp_hist = nullptr;
+    float *d_hp_x = nullptr;
     // control state (reference attribute it mirrors)
     int slot = 0;                 // which half of d_zring receives the current block
     int rad_idx = 0;              // which half of d_radlast holds the previous yaw
@@ -811,7 +817,51 @@ int rtb_sh_plan_reset(rtb_sh_plan *p) {
         RTB_CUDA(cudaMemset(p->d_qcur, 0, sizeof(float2) * queue_elems(p)));
         RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * queue_elems(p)));
     }
+    if (p->hp_P > 0) {  // the HPCF client's own _clear_buffers (_convolver.py:500-505)
+        RTB_CUDA(cudaMemset(p->d_hp_x, 0, sizeof(float) * 2 * (size_t)p->S * 2 * p->B));
+        RTB_CUDA(cudaMemset(p->d_hp_hist, 0, sizeof(float2) * (size_t)p->S * p->hp_P * 2 * p->Fp));
+    }
     RTB_CUDA(cudaDeviceSynchronize());
+    return RTB_OK;
+}
+
+// Attach (or, with n_partitions == 0, remove) a 2-channel headphone-compensation filter behind the
+// renderer: hfd [P][2][F] complex = FilterSet.get_filter_blocks_fd() of the HPCF set
+// (_filter_set.py:625-664).  Same result as the reference's separate HPCF client
+// (OverlapSaveConvolver.filter_block, _convolver.py:524-571) fed with the renderer's output.
+int rtb_sh_plan_set_hpcf(rtb_sh_plan *p, const float *hfd, int n_partitions) {
+    if (!p) return fail(RTB_ERR_INVALID, "NULL plan");
+    if (n_partitions < 0 || (n_partitions > 0 && !hfd)) return fail(RTB_ERR_INVALID, "bad HPCF argument");
+    DeviceGuard guard(p->device);
+    RTB_CUDA(cudaDeviceSynchronize());
+    cudaFree(p->d_hp_hfd); cudaFree(p->d_hp_hist); cudaFree(p->d_hp_x);
+    p->d_hp_hfd = p->d_hp_hist = nullptr; p->d_hp_x = nullptr;
+    p->hp_P = 0; p->hp_slot = 0; p->hp_xidx = 0;
+    if (n_partitions == 0) return RTB_OK;
+    const int F = p->F, Fp = p->Fp, P = n_partitions;
+    std::vector<float2> h((size_t)P * 2 * Fp, make_float2(0.f, 0.f));
+    for (int q = 0; q < P; ++q)
+        for (int e = 0; e < 2; ++e)
+            for (int f = 0; f < F; ++f) {
+                const size_t i = 2 * (((size_t)q * 2 + e) * F + f);
+                h[((size_t)q * 2 + e) * Fp + f] = make_float2(hfd[i], hfd[i + 1]);
+            }
+    const size_t xbytes = sizeof(float) * 2 * (size_t)p->S * 2 * p->B;
+    const size_t hbytes = sizeof(float2) * (size_t)p->S * P * 2 * Fp;
+    cudaError_t err = cudaMalloc(&p->d_hp_hfd, sizeof(float2) * h.size());
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_hp_hist, hbytes);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_hp_x, xbytes);
+    if (err == cudaSuccess) err = cudaMemset(p->d_hp_hist, 0, hbytes);
+    if (err == cudaSuccess) err = cudaMemset(p->d_hp_x, 0, xbytes);
+    if (err == cudaSuccess) err = cudaMemcpy(p->d_hp_hfd, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+        cudaFree(p->d_hp_hfd); cudaFree(p->d_hp_hist); cudaFree(p->d_hp_x);
+        p->d_hp_hfd = p->d_hp_hist = nullptr; p->d_hp_x = nullptr;
+        return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
+                    "HPCF allocation failed: %s", cudaGetErrorString(err));
+    }
+    p->hp_P = P;
     return RTB_OK;
 }
 
@@ -825,6 +875,21 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
     const float *zprev = p->d_zring + (size_t)(p->slot ^ 1) * zhalf + zo;
     launch_analysis(p, d_in, zcur, count, st);  // a1/a2: the overlap-save state advances in every mode
     p->launches++;
+    // with an HPCF attached the renderer's binaural block goes to the filter's overlap-save state and
+    // the filter writes what the caller receives (fused into the render kernels, stand-alone otherwise)
+    HpcfParams hp = {};
+    float *const d_out_final = d_out;
+    if (p->hp_P > 0) {
+        const size_t xs = (size_t)p->S * 2 * p->B;
+        hp.x_prev = p->d_hp_x + (size_t)(p->hp_xidx ^ 1) * xs + (size_t)s0 * 2 * p->B;
+        hp.x_cur = p->d_hp_x + (size_t)p->hp_xidx * xs + (size_t)s0 * 2 * p->B;
+        hp.hist = p->d_hp_hist + (size_t)s0 * p->hp_P * 2 * p->Fp;
+        hp.hfd = p->d_hp_hfd;
+        hp.out = d_out_final;
+        hp.P = p->hp_P; hp.Fp = p->Fp; hp.slot = p->hp_slot;
+        d_out = hp.x_cur;
+    }
+    bool hp_fused = false;
     if (p->profiling && s0 == 0) cudaEventRecord(p->ev[1], st);
     if (p->passthrough) {
         p->last_render_kernel = 4;
@@ -959,6 +1024,7 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
             prm.order_max = p->order;
             prm.crossfade = p->crossfade ? 1 : 0;
             prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
+            prm.hp = hp; hp_fused = true;
             launch_render_mg(p, prm, st);
         } else {
             ShRenderParams prm;
@@ -975,10 +1041,17 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
             prm.order_max = p->order;
             prm.crossfade = p->crossfade ? 1 : 0;
             prm.tracker_dir = p->tracker_dir; prm.src_azim16 = p->src_azim16;
+            prm.hp = hp; hp_fused = true;
             launch_render(p, prm, st);
         }
     }
     p->launches++;
+    if (p->hp_P > 0 && !hp_fused) {  // passthrough / partitioned paths: the filter as its own launch
+#define RTB_HP_LAUNCH(N) fft_kernel_launch<N>(hpcf_kernel<N>, hp, count, st, 0, 0, p->d_tw, count)
+        RTB_DISPATCH_N2(p->N2, RTB_HP_LAUNCH)
+#undef RTB_HP_LAUNCH
+        p->launches++;
+    }
 }
 
 // block boundary: flip the ping-pong state once all ranges of the block are enqueued
@@ -991,6 +1064,10 @@ void advance_block(rtb_sh_plan *p) {
     }
     if (p->P > 1) p->head_cur = (p->head_cur + 1) % p->P;
     p->slot ^= 1;
+    if (p->hp_P > 0) {
+        p->hp_xidx ^= 1;
+        p->hp_slot = (p->hp_slot + 1) % p->hp_P;
+    }
 }
 
 }  // namespace
@@ -1146,6 +1223,7 @@ int rtb_sh_plan_destroy(rtb_sh_plan *p) {
     DeviceGuard guard(p->device);
     free_tables(p);
     cudaFree(p->d_tw); cudaFree(p->d_win_in); cudaFree(p->d_win_out); cudaFree(p->d_radlast);
+    cudaFree(p->d_hp_hfd); cudaFree(p->d_hp_hist); cudaFree(p->d_hp_x);
     for (auto &h : p->hslot) {
         cudaFree(h.d_in); cudaFree(h.d_yaw); cudaFree(h.d_out);
         if (h.in_done) cudaEventDestroy(h.in_done);

@@ -267,6 +267,7 @@ sh_render_kernel(const ShRenderParams prm) {
     }
     render_tail<N2>(acc, buf, tw, grp, l, prm.win_in, prm.win_out, prm.crossfade,
                     prm.out + (size_t)s * 2 * B);
+    if (prm.hp.P > 0) hpcf_stage<N2>(prm.hp, s, grp == 0, buf, tw, l);  // prm.out is the HPCF's input state then
 }
 
 }  // namespace rtb

@@ -59,6 +59,7 @@ struct ShRenderMgParams {
     int order_max;
     int crossfade;
     float tracker_dir, src_azim16;
+    HpcfParams hp;               // optional HPCF stage behind the cross-fade (hp.P == 0: none)
 };
 
 // acc += h * conj(x)
@@ -289,6 +290,7 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
 #endif
     render_tail<N2>(acc, s_buf[warp], s_tw, 0, lane, prm.win_in, prm.win_out, prm.crossfade,
                     prm.out + (size_t)s * 2 * B);
+    if (prm.hp.P > 0) hpcf_stage<N2>(prm.hp, s, true, s_buf[warp], s_tw, lane);  // prm.out is the HPCF's input state then
 }
 
 }  // namespace rtb

@@ -90,6 +90,17 @@ class ShPlan:
     def reset(self):
         check(lib.rtb_sh_plan_reset(self._h))
 
+    def set_hpcf(self, hfd):
+        """Attach a 2-channel headphone-compensation filter behind the renderer: hfd [P, 2, F]
+        complex (``FilterSet.get_filter_blocks_fd()[:, 0]``); ``None`` detaches it."""
+        if hfd is None:
+            check(lib.rtb_sh_plan_set_hpcf(self._h, None, 0))
+            return
+        hfd = np.ascontiguousarray(hfd, dtype=np.complex64)
+        if hfd.ndim != 3 or hfd.shape[1:] != (2, self.F):
+            raise ValueError(f"HPCF filter blocks shape {hfd.shape} != (P, 2, {self.F})")
+        check(lib.rtb_sh_plan_set_hpcf(self._h, np_ptr(hfd), hfd.shape[0]))
+
     def query(self, what):
         v = ctypes.c_int64()
         check(lib.rtb_sh_plan_query(self._h, what, ctypes.byref(v)))
