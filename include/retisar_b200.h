@@ -110,6 +110,15 @@ int rtb_sh_wait_block_host(rtb_sh_plan *plan, long long ticket);
  * (hfd may be NULL) detaches the filter.  Attaching resets the filter's own state only. */
 int rtb_sh_plan_set_hpcf(rtb_sh_plan *plan, const float *hfd, int n_partitions);
 
+/* Set-up time: FilterSetMiro.calculate_filter_blocks_nm (_filter_set.py:1093-1149) on the device,
+ * H_nm[p][k][e][f] = sum_c Y_w[k][c] * H[p][c][e][f] -- the SH transform of an HRIR set
+ * ([K x directions] . [directions x F] per partition and ear) on the tensor-core analysis kernel.
+ * Host pointers: yw [K][C] complex, hfd [P][C][E][F] complex (get_filter_blocks_fd layout),
+ * hnm [P][K][E][F] complex (out); F - 1 must be a power of two >= 32.  TF32 x 3: ~2e-6 relative
+ * to the numpy product of the reference. */
+int rtb_sh_transform_filter(int device, const float *yw, const float *hfd, int n_partitions,
+                            int n_coeffs, int n_dirs, int n_ears, int n_bins, float *hnm);
+
 /* introspection: what = RTB_Q_* */
 #define RTB_Q_SYMMETRIC 1   /* 1 if Y_w has the (n,-m) conjugate symmetry (real analysis path) */
 #define RTB_Q_ROWS 2        /* J: real analysis rows per stream                                */

@@ -453,7 +453,10 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         from ._compensation import Compensation
 
         Compensation.reset_config(is_plot=is_plot)
-        self._filter.calculate_filter_blocks_nm()
+        if config.IS_SH_TRANSFORM_ON_DEVICE and type(self._filter) in (FilterSetMiro, FilterSetSofa):
+            self._filter.calculate_filter_blocks_nm(device=self._device)
+        else:
+            self._filter.calculate_filter_blocks_nm()
         if self._comp_nm_override is not None:
             comp_nm = self._comp_nm_override
         else:

@@ -14,3 +14,9 @@ IS_RUNNING.set()
 
 CUDA_DEVICE = 0
 """CUDA device index new convolvers are placed on (no reference counterpart)."""
+
+IS_SH_TRANSFORM_ON_DEVICE = False
+"""Evaluate the SH transform of the HRIR set (``FilterSetMiro.calculate_filter_blocks_nm``) on the
+tensor-core GEMM instead of numpy when the renderer (re)builds its tables (no reference
+counterpart).  Off by default: the numpy product reproduces the reference's tables bit for bit,
+the device product agrees to about 2e-6 relative."""

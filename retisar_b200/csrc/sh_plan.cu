@@ -1213,6 +1213,109 @@ int rtb_sh_plan_query(rtb_sh_plan *p, int what, int64_t *value) {
     return RTB_OK;
 }
 
+// Set-up time: SH transform of an HRIR set, H_nm[p][k][e][f] = sum_c Y_w[k][c] * H[p][c][e][f]
+// (FilterSetMiro.calculate_filter_blocks_nm, _filter_set.py:1093-1149: a [K x directions] .
+// [directions x F] complex product per partition and ear; 2702 directions for the reference's
+// default HRIR set).  Runs on the tcgen05 analysis kernel: the real and imaginary parts of Y_w are
+// the analysis rows, the directions take the role of the array channels, the bins of (partition,
+// ear, re | im) the role of a stream's samples; TF32 x 3 split as everywhere (2e-6 relative).
+// The Nyquist bin (block length + 1 bins, the kernel works on powers of two) is summed on the host.
+int rtb_sh_transform_filter(int device, const float *yw, const float *hfd, int n_partitions, int n_coeffs,
+                            int n_dirs, int n_ears, int n_bins, float *hnm) {
+    if (!yw || !hfd || !hnm) return fail(RTB_ERR_INVALID, "NULL argument");
+    const int P = n_partitions, K = n_coeffs, C = n_dirs, E = n_ears, F = n_bins, Bq = n_bins - 1;
+    if (P < 1 || K < 1 || C < 1 || E < 1) return fail(RTB_ERR_INVALID, "sizes must be >= 1");
+    if (Bq < 32 || (Bq & (Bq - 1))) return fail(RTB_ERR_UNSUPPORTED, "n_bins - 1 must be a power of two >= 32 (got %d)", Bq);
+    int ndev = 0;
+    RTB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(RTB_ERR_INVALID, "no CUDA device %d", device);
+    DeviceGuard guard(device);
+    const int S = P * E * 2;  // "streams": (partition, ear, re | im)
+    const int KC = RTB_TC_KC, Kpad = (C + KC - 1) / KC * KC;
+    // input [S][C][Bq]
+    std::vector<float> x((size_t)S * C * Bq);
+    for (int p = 0; p < P; ++p)
+        for (int c = 0; c < C; ++c)
+            for (int e = 0; e < E; ++e) {
+                const float *src = hfd + 2 * ((((size_t)p * C + c) * E + e) * F);
+                float *dr = x.data() + (((size_t)(p * E + e) * 2 + 0) * C + c) * Bq;
+                float *di = x.data() + (((size_t)(p * E + e) * 2 + 1) * C + c) * Bq;
+                for (int f = 0; f < Bq; ++f) { dr[f] = src[2 * f]; di[f] = src[2 * f + 1]; }
+            }
+    float *d_x = nullptr, *d_z = nullptr, *d_b = nullptr;
+    const int rows_total = 2 * K, rows_per = 256;
+    std::vector<float> z((size_t)S * std::min(rows_total, rows_per) * Bq);
+    std::vector<float> zall((size_t)S * rows_total * Bq);
+    cudaError_t err = cudaMalloc(&d_x, sizeof(float) * x.size());
+    if (err == cudaSuccess) err = cudaMalloc(&d_z, sizeof(float) * z.size());
+    if (err == cudaSuccess) err = cudaMemcpy(d_x, x.data(), sizeof(float) * x.size(), cudaMemcpyHostToDevice);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    for (int r0 = 0; r0 < rows_total && err == cudaSuccess; r0 += rows_per) {
+        const int J = std::min(rows_per, rows_total - r0), Npad = (J + 15) / 16 * 16;
+        std::vector<float> bsrc(2 * (size_t)Kpad * Npad, 0.f);
+        for (int j = 0; j < J; ++j) {
+            const int row = r0 + j, k = row < K ? row : row - K, ri = row < K ? 0 : 1;
+            for (int c = 0; c < C; ++c) {
+                const float v = yw[2 * ((size_t)k * C + c) + ri];
+                uint32_t u;
+                memcpy(&u, &v, 4);
+                u = (u + 0x1000u) & 0xffffe000u;  // round to nearest TF32
+                float hi;
+                memcpy(&hi, &u, 4);
+                const size_t off = (((size_t)(c / 4) * (Npad / 8) + j / 8) * 8 + j % 8) * 4 + c % 4;
+                bsrc[off] = hi;
+                bsrc[(size_t)Kpad * Npad + off] = v - hi;
+            }
+        }
+        cudaFree(d_b);
+        d_b = nullptr;
+        err = cudaMalloc(&d_b, sizeof(float) * bsrc.size());
+        if (err == cudaSuccess) err = cudaMemcpy(d_b, bsrc.data(), sizeof(float) * bsrc.size(), cudaMemcpyHostToDevice);
+        if (err != cudaSuccess) break;
+        const size_t a_stage = sizeof(float) * 2 * KC * RTB_TC_M, b_stage = sizeof(float) * 2 * (size_t)KC * Npad;
+        const int nst = (216 * 1024) / (a_stage + b_stage) >= 4 ? 4 : 2;
+        const size_t smem = nst * (a_stage + b_stage);
+        const int cols = Npad <= 32 ? 32 : (Npad <= 64 ? 64 : (Npad <= 128 ? 128 : 256));
+        const long long tiles = ((long long)S * Bq + RTB_TC_M - 1) / RTB_TC_M;
+        const int grid = (int)std::min<long long>(tiles, n_sm);
+        kernel_attrs_once(sh_analysis_tc_kernel<true, RTB_TC_LG>, 224 * 1024);
+        sh_analysis_tc_kernel<true, RTB_TC_LG><<<grid, RTB_TC_THREADS_OF(RTB_TC_LG), smem, 0>>>(
+            d_x, d_b, d_z, S, C, J, Bq, Kpad, Npad, cols, nst, 0LL);
+        err = cudaGetLastError();
+        if (err == cudaSuccess) err = cudaMemcpy(z.data(), d_z, sizeof(float) * (size_t)S * J * Bq, cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess) break;
+        for (int s = 0; s < S; ++s)
+            memcpy(zall.data() + ((size_t)s * rows_total + r0) * Bq, z.data() + (size_t)s * J * Bq,
+                   sizeof(float) * (size_t)J * Bq);
+    }
+    cudaFree(d_x); cudaFree(d_z); cudaFree(d_b);
+    if (err != cudaSuccess) return fail(RTB_ERR_CUDA, "SH transform of the filter set failed: %s", cudaGetErrorString(err));
+    for (int p = 0; p < P; ++p)
+        for (int k = 0; k < K; ++k)
+            for (int e = 0; e < E; ++e) {
+                float *dst = hnm + 2 * ((((size_t)p * K + k) * E + e) * F);
+                const float *zr = zall.data() + ((size_t)((p * E + e) * 2 + 0) * rows_total) * Bq;  // input = Re H
+                const float *zi = zall.data() + ((size_t)((p * E + e) * 2 + 1) * rows_total) * Bq;  // input = Im H
+                const float *yr_hr = zr + (size_t)k * Bq, *yi_hr = zr + (size_t)(K + k) * Bq;
+                const float *yr_hi = zi + (size_t)k * Bq, *yi_hi = zi + (size_t)(K + k) * Bq;
+                for (int f = 0; f < Bq; ++f) {
+                    dst[2 * f] = yr_hr[f] - yi_hi[f];
+                    dst[2 * f + 1] = yr_hi[f] + yi_hr[f];
+                }
+                double ar = 0.0, ai = 0.0;  // Nyquist bin
+                for (int c = 0; c < C; ++c) {
+                    const double yr = yw[2 * ((size_t)k * C + c)], yi = yw[2 * ((size_t)k * C + c) + 1];
+                    const float *h = hfd + 2 * ((((size_t)p * C + c) * E + e) * F + Bq);
+                    ar += yr * h[0] - yi * h[1];
+                    ai += yr * h[1] + yi * h[0];
+                }
+                dst[2 * Bq] = (float)ar;
+                dst[2 * Bq + 1] = (float)ai;
+            }
+    return RTB_OK;
+}
+
 #ifdef RTB_TRACE_TC
 int rtb_debug_tc_trace(long long *h_out, int n) {  // trace builds only (not part of the public ABI)
     return cudaMemcpyFromSymbol(h_out, rtb::g_tc_trace, sizeof(long long) * n) == cudaSuccess ? RTB_OK : RTB_ERR_CUDA;

@@ -304,3 +304,37 @@ def test_compensation_matches_the_references_own_bookkeeping():
         Compensation.generate_by_type(["MRF"], hrir, arr.get_sh_configuration().arir_config, 6, nfft_padded=128)
     Compensation.reset_config()
     print("compensation vs reference bookkeeping: max relative error", worst)
+
+
+def test_filter_set_resampling_control_flow_and_band_limited_result(tmp_path):
+    """`FilterSet._resample` (`_filter_set.py:502-565`): no-op at equal rates, `ValueError` when
+    prevented, result length round(taps * ratio), and -- property of any band-limited converter --
+    a windowed sinusoid keeps its frequency and amplitude (the polyphase resampler is documented
+    as not sample-identical to libsamplerate's "sinc_best": parity unpinned)."""
+    from retisar_b200 import FilterSet
+
+    fs_in, fs_out, taps = 44100, 48000, 4410
+    t = np.arange(taps) / fs_in
+    tone = (np.sin(2 * np.pi * 1000.0 * t) * np.hanning(taps)).astype(np.float32)
+    from scipy.io import wavfile
+
+    wav = str(tmp_path / "hpcf_44k.wav")
+    wavfile.write(wav, fs_in, np.stack([tone, 0.5 * tone], axis=1))  # float32 WAV, 2 channels
+
+    def make():
+        return FilterSet.create_instance_by_type(wav, "FIR_MULTICHANNEL")
+
+    f = make()
+    f.load(block_length=256, is_single_precision=True, check_fs=fs_out, is_prevent_logging=True)
+    n_out = int(round(taps * fs_out / fs_in))
+    assert f._fs == fs_out and f._irs_orig_shape[-1] == n_out and f._irs_td.dtype == np.float32
+    y = f._irs_td[0, :, :n_out]
+    t2 = np.arange(n_out) / fs_out
+    want = np.sin(2 * np.pi * 1000.0 * t2) * np.interp(t2, t, np.hanning(taps))
+    assert np.abs(y[0] - want).max() < 2e-3 and np.abs(y[1] - 0.5 * want).max() < 1e-3
+    with pytest.raises(ValueError, match="prevented resampling"):
+        make().load(block_length=256, is_single_precision=True, check_fs=fs_out,
+                    is_prevent_resampling=True, is_prevent_logging=True)
+    g = make()
+    g.load(block_length=256, is_single_precision=True, check_fs=fs_in, is_prevent_logging=True)
+    assert g._irs_orig_shape[-1] == taps  # equal rates: untouched

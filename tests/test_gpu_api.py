@@ -173,3 +173,34 @@ def test_torch_device_path_and_batched_ols(tables):
         y = ols.filter_block(x)
         ref = np.stack([r.filter_block(x[s].cpu().numpy()) for s, r in enumerate(refs)])
         assert np.abs(y.cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("workload,dirs", [("c2", 2702), ("c3", 500), ("c4", 434)])
+def test_sh_transform_of_the_hrir_set_on_the_device(workload, dirs):
+    """`FilterSetMiro.calculate_filter_blocks_nm(device=0)` (tensor-core GEMM, `rtb_sh_transform_filter`)
+    against the numpy product of the reference (`_filter_set.py:1093-1149`): 2702 directions (the
+    reference's default HRIR set), 16 partitions (c3), order 12 = 338 analysis rows in two row
+    chunks (c4).  Bar: 1e-5 of the largest coefficient (measured ~1e-6)."""
+    from retisar_b200 import config
+    from retisar_b200 import workloads as wl
+
+    tb = wl.sh_tables(workload, hrir_dirs=dirs)
+    h = tb["hrir_set"]
+    h.calculate_filter_blocks_fd(tb["B"])
+    h.calculate_filter_blocks_nm()
+    ref = h.get_filter_blocks_nm().copy()
+    h.calculate_filter_blocks_nm(device=0)
+    got = h.get_filter_blocks_nm()
+    assert got.shape == ref.shape and got.dtype == np.complex64
+    err = float(np.abs(got - ref).max() / np.abs(ref).max())
+    print(workload, got.shape, "relative error", err)
+    assert err <= 1e-5
+    # the renderer picks the device transform up through the config switch
+    config.IS_SH_TRANSFORM_ON_DEVICE = True
+    try:
+        conv = wl.make_renderer(tb, 2)
+        assert np.abs(tb["hrir_set"].get_filter_blocks_nm() - ref).max() / np.abs(ref).max() <= 1e-5
+        x = (np.random.default_rng(0).standard_normal((2, tb["C"], tb["B"])) * 0.1).astype(np.float32)
+        assert np.isfinite(conv.filter_block(x, [10.0, 200.0])).all()
+    finally:
+        config.IS_SH_TRANSFORM_ON_DEVICE = False
