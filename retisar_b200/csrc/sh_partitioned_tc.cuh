@@ -24,7 +24,12 @@
 //   warps 0-15   producers: four groups of four warps, group g owns operand stage g; a warp covers
 //                32 streams x 8 steps of a unit = (tile, K-chunk of 16 reals)
 //   warp 24      MMA issuer (warp-uniform loop, one elected lane)
-//   warps 16-23  epilogue: TMEM lane quarter (warp % 4) x (current | previous yaw) accumulator
+//   warps 16-23  epilogue: TMEM lane quarter (warp % 4) x (current | previous yaw) accumulator, with the
+//                queue rows of the next batch requested ahead (see the epilogue)
+// What bounds it (ncu, profiles/r02_ncu_full_c3_partition_tc_*): HBM latency x bytes in flight.  v1
+// (serial load - wait - store chain of four batches per tile in the epilogue): 513 us for c3 / 4 096
+// streams = 3.5 TB/s; v2 (8 producer groups of 2 warps, 4 epilogue warps): 690 us, epilogue chain;
+// v3 (5 producer groups of 2 warps, 8 epilogue warps, prefetching epilogue): 801 us, producers.
 // A tile = (128 streams, one bin); CTAs take contiguous runs of tiles ordered (stream tile, bin), so
 // a CTA meets at most two stream tiles per launch and keeps both phase tables in shared memory.
 #pragma once
@@ -133,10 +138,11 @@ sh_partition_tc_kernel(const ShPartTcParams prm) {
         float *st_a = stages + g * stage_floats;
         float *st_b = st_a + a_floats;
         const size_t bunit = b_floats;              // floats of one (bin, chunk) operand block
-        for (long long n = g, k = 0; n < my_units; n += LG, ++k) {
-            const long long tile = t_begin + n / n_chunks;
-            const int h = (int)(n % n_chunks);
-            const int stile = (int)(tile / prm.F), f = (int)(tile - (long long)stile * prm.F);
+        const int t_begin_i = (int)t_begin, n_units = (int)my_units;   // < 2^31: at most F tiles x 24 chunks per CTA
+        for (int n = g, k = 0; n < n_units; n += LG, ++k) {
+            const int tl = n / n_chunks, h = n - tl * n_chunks;
+            const int tile = t_begin_i + tl;
+            const int stile = tile / prm.F, f = tile - stile * prm.F;
             const int fm = (prm.N2 - f) & (prm.N2 - 1);
             const float2 *zrow = prm.zspecT + (size_t)stile * M + r;   // + (bin * NPT + p) * Spad
             const float2 *ph = s_ph + (size_t)(stile - stile_first) * 2 * n_ph * M + r;
@@ -235,55 +241,77 @@ sh_partition_tc_kernel(const ShPartTcParams prm) {
         }
     } else {
         // ===== epilogue: warp e drains TMEM lanes 32 * (e % 4) .. of the current (e < 4) or previous
-        // yaw accumulator and adds them to the queue rows of its 32 streams
+        // yaw accumulator and adds them to the queue rows of its 32 streams.  The queue values of the
+        // NEXT batch of rows (next column chunk / next tile) are requested before the warp waits for
+        // the next accumulator -- their addresses do not depend on it -- so the read-modify-write
+        // round trips overlap the MMAs instead of forming a serial chain per tile.
+        constexpr int EB = 8;  // (partition, ear) rows per batch: 8 loads in flight per lane
         const int e = warp - LG * PW, quarter = warp & 3, cl = e / 4;
         float2 *qbase = cl ? prm.qlastT : prm.qcurT;
         const int head = cl ? prm.head_last : prm.head_cur;
         const bool idle = cl == 1 && !prm.do_last;
+        // queue row of ((partition, ear) index) in the tile whose base pointer is `qt` (nullptr: padding row)
+        auto tile_base = [&](long long it) -> float2 * {
+            const int tile = (int)(t_begin + it);           // n_tiles < 2^31
+            const int stile = tile / prm.F, f = tile - stile * prm.F;
+            const int sl = stile * M + 32 * quarter + lane; // stream inside the launch
+            if (it >= my_tiles || prm.s0 + sl >= prm.S) return nullptr;
+            return qbase + (size_t)f * prm.P * 2 * prm.Spad + sl;
+        };
+        auto qptr = [&](float2 *qt, int idx) -> float2 * {
+            const int part = idx >> 1;
+            int slot = head + part;
+            if (slot >= prm.P) slot -= prm.P;
+            if (!qt || part >= prm.P) return nullptr;
+            return qt + (size_t)(slot * 2 + (idx & 1)) * prm.Spad;
+        };
+        float2 *qt_cur = idle ? nullptr : tile_base(0), *qt_next = nullptr;
+        float2 old[EB];
+        if (!idle && my_tiles > 0) {
+#pragma unroll
+            for (int c = 0; c < EB; ++c) {
+                const float2 *q = qptr(qt_cur, c);
+                if (q) old[c] = *q;
+            }
+        }
         for (long long it = 0; it < my_tiles; ++it) {
-            const long long tile = t_begin + it;
-            const int stile = (int)(tile / prm.F), f = (int)(tile - (long long)stile * prm.F);
             const int buf = (int)(it & 1);
+            if (!idle) qt_next = tile_base(it + 1);
             mbar_wait(&tfull_bar[buf], (unsigned)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int sl = stile * M + 32 * quarter + lane;     // stream inside the launch
-            const bool row_ok = !idle && prm.s0 + sl < prm.S;
-            float2 *qrow = qbase + (size_t)f * prm.P * 2 * prm.Spad + sl;  // + (slot * 2 + ear) * Spad
             for (int cb = 0; cb < Npad && !idle; cb += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * 2 + cl) * prm.acc_cols + cb), v);
-                if (cb + 32 >= Npad) {  // the accumulator is in registers: release it to the MMA issuer
+                const bool last_chunk = cb + 32 >= Npad;
+                if (last_chunk) {  // the accumulator is in registers: release it to the MMA issuer
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[buf]);
                 }
-                // read-modify-write of the 16 (partition, ear) queue rows of this column chunk, eight
-                // at a time; a warp's access is 256 contiguous bytes per row
 #pragma unroll
-                for (int c0 = 0; c0 < 16; c0 += 8) {
-                    float2 old[8];
+                for (int c0 = 0; c0 < 16; c0 += EB) {
+                    // this batch was requested one batch ago: add, store (256 contiguous bytes per warp and row)
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int idx = cb / 2 + c0 + c;         // (partition, ear) output index
-                        const int part = idx >> 1;
-                        int slot = head + part;
-                        if (slot >= prm.P) slot -= prm.P;
-                        if (row_ok && part < prm.P) old[c] = qrow[(size_t)(slot * 2 + (idx & 1)) * prm.Spad];
-                    }
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int idx = cb / 2 + c0 + c;
-                        const int part = idx >> 1;
-                        int slot = head + part;
-                        if (slot >= prm.P) slot -= prm.P;
-                        if (row_ok && part < prm.P) {
+                    for (int c = 0; c < EB; ++c) {
+                        float2 *q = qptr(qt_cur, cb / 2 + c0 + c);
+                        if (q) {
                             old[c].x += __uint_as_float(v[2 * (c0 + c)]);
                             old[c].y += __uint_as_float(v[2 * (c0 + c) + 1]);
-                            qrow[(size_t)(slot * 2 + (idx & 1)) * prm.Spad] = old[c];
+                            *q = old[c];
                         }
+                    }
+                    // request the next batch: rest of this chunk, the next chunk, or the next tile
+                    const bool wrap = c0 + EB >= 16;
+                    float2 *qt_n = (wrap && last_chunk) ? qt_next : qt_cur;
+                    const int nidx = wrap ? (last_chunk ? 0 : (cb + 32) / 2) : cb / 2 + c0 + EB;
+#pragma unroll
+                    for (int c = 0; c < EB; ++c) {
+                        const float2 *q = qptr(qt_n, nidx + c);
+                        if (q) old[c] = *q;
                     }
                 }
             }
+            qt_cur = qt_next;
             if (idle) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[buf]);
