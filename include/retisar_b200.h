@@ -101,6 +101,19 @@ int rtb_sh_submit_block_host(rtb_sh_plan *plan, const float *h_in, const float *
                              float *h_out, long long *ticket);
 int rtb_sh_wait_block_host(rtb_sh_plan *plan, long long ticket);
 
+/* Pre-rendered mode (extension).  The array signals enter the chain only through the analysis rows
+ * z[j][t] = sum_c R[j][c] x[c][t] (R = real / imaginary parts of _sh_bases_weighted,
+ * _convolver.py:1260-1263 applied before the FFT).  When x is itself the output of the reference's
+ * ARIR pre-renderer -- a mono source convolved with one impulse response per array channel
+ * (_run.py:240-288) -- R folds into those filters at set-up time and the pre-renderer can write the J
+ * rows straight into the plan:
+ *   rtb_sh_plan_get_analysis_rows  rows [J][C] float, J = RTB_Q_ROWS
+ *   rtb_sh_plan_rows_buffer        device buffer [S][J][B] that must hold the rows of the NEXT block
+ *   rtb_sh_process_block_rows      renders that block without the analysis GEMM */
+int rtb_sh_plan_get_analysis_rows(rtb_sh_plan *plan, float *rows);
+int rtb_sh_plan_rows_buffer(rtb_sh_plan *plan, float **d_rows);
+int rtb_sh_process_block_rows(rtb_sh_plan *plan, const float *d_yaw_deg, float *d_out, void *cuda_stream);
+
 /* Optional headphone-compensation filter (HPCF) behind the renderer.  The reference chains it as a
  * separate client after the renderer (_run.py:290-338): a 2-in / 2-out channel-wise
  * OverlapSaveConvolver (_convolver.py:524-571) fed with the binaural block.  Here the warp that

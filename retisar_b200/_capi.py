@@ -34,6 +34,9 @@ SIGNATURES = {
     "rtb_sh_plan_set_crossfade": (_i, [_vp, _i]),
     "rtb_sh_plan_reset": (_i, [_vp]),
     "rtb_sh_plan_set_hpcf": (_i, [_vp, _vp, _i]),
+    "rtb_sh_plan_get_analysis_rows": (_i, [_vp, _vp]),
+    "rtb_sh_plan_rows_buffer": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "rtb_sh_process_block_rows": (_i, [_vp, _vp, _vp, _vp]),
     "rtb_sh_transform_filter": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rtb_sh_process_block": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "rtb_sh_process_blocks": (_i, [_vp, _vp, _vp, _vp, _i, ctypes.c_longlong, _i, _vp]),

@@ -366,6 +366,7 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         self._comp_mrf_limit = None
         self._comp_nm_override = None
         self._hpcf_filter = None
+        self._pre_renderer = None
 
     def __copy__(self):
         """The reference raises here ("not tested", ``_convolver.py:1051-1060``); this returns an
@@ -472,6 +473,8 @@ class AdjustableShConvolver(AdjustableFdConvolver):
     def _clear_buffers(self):
         if self._plan is not None:
             self._plan.reset()
+        if self._pre_renderer is not None:
+            self._pre_renderer._clear_buffers()
 
     def _apply_passthrough(self):
         if self._plan is not None:
@@ -506,6 +509,8 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         if yaw_deg is None:
             azim = self._tracker_deg[HeadTracker.DataIndex.AZIM] if self._tracker_deg is not None else 0.0
             yaw_deg = np.full(plan.S, azim, dtype=np.float32)
+        if self._pre_renderer is not None and input_block_td.shape[-2] == 1 and plan.C != 1:
+            return self._filter_block_pre_rendered(input_block_td, yaw_deg)
         if _is_torch_tensor(input_block_td):
             import torch
 
@@ -518,6 +523,63 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         x = np.asarray(input_block_td, dtype=np.float32)
         out = plan.process_host(x.reshape(plan.S, plan.C, plan.B), yaw_deg)
         return out if x.ndim == 3 else out[0]
+
+    def set_pre_renderer(self, arir_irs_td):
+        """Extension: fold the reference's ARIR pre-renderer into this renderer.
+
+        The reference renders a mono source through an array room impulse response with a separate
+        client (``_run.py:240-288``: ``OverlapSaveConvolver`` with a mono input and one filter per
+        array channel, ``_convolver.py:588-591``) whose C output channels feed this renderer.  The
+        array signals enter the SH chain only through the real analysis rows ``z = R x``
+        (``R`` = real / imaginary parts of ``_sh_bases_weighted``, ``:1260-1263`` applied before the
+        FFT), and the pre-renderer is linear and time invariant, so ``R`` folds into its filters
+        once: ``z_j = (sum_c R[j, c] arir_c) * source``.  The pre-renderer then produces the J rows
+        directly (169 instead of 434 channels for order 12 on a 434-channel array), and the
+        renderer skips its analysis GEMM.  Same output up to fp32 reassociation.
+
+        arir_irs_td: array impulse responses ``[channels; taps]`` (or a loaded array ``FilterSet``
+        with ``_irs_td [1; channels; taps]``); ``None`` removes the pre-renderer.  Afterwards
+        ``filter_block`` accepts the MONO source block ``[n_streams; 1; B]`` (or ``[1; B]``).
+        """
+        from ._filter_set import FilterSet
+
+        self._pre_renderer = None
+        if arir_irs_td is None:
+            return
+        if self._plan is None:
+            raise RuntimeError(self._filter._ERROR_MSG_NM)
+        irs = getattr(arir_irs_td, "_irs_td", arir_irs_td)
+        irs = np.asarray(irs, dtype=np.float64)
+        irs = irs.reshape(-1, irs.shape[-1])
+        if irs.shape[0] != self._plan.C:
+            raise ValueError(f"the array impulse responses have {irs.shape[0]} channels, the renderer expects {self._plan.C}")
+        rows = self._plan.analysis_rows().astype(np.float64)       # [J, C]
+        combined = (rows @ irs).astype(np.float32)                 # [J, taps]: the ARIR in the analysis domain
+        fs = FilterSet.create_instance_by_type(combined, "FIR_MULTICHANNEL")
+        fs.load(block_length=self._block_length, is_single_precision=True, is_prevent_logging=True)
+        pre = OverlapSaveConvolver(fs, self._block_length, n_streams=self._n_streams, device=self._device)
+        pre._make_plan(1)  # mono source, J outputs (per-bin GEMM on tensor cores for >= 32 rows)
+        self._pre_renderer = pre
+
+    def _filter_block_pre_rendered(self, source_td, yaw_deg):
+        """Mono source block(s) -> pre-renderer (writes the analysis rows into the plan) -> renderer."""
+        import torch
+
+        plan, pre = self._plan, self._pre_renderer._plan
+        was_numpy = not _is_torch_tensor(source_td)
+        dev = torch.device("cuda", self._device)
+        x = torch.as_tensor(np.asarray(source_td, dtype=np.float32), device=dev) if was_numpy else source_td
+        batched = x.dim() == 3
+        x = x.reshape(plan.S, 1, plan.B).contiguous()
+        if not _is_torch_tensor(yaw_deg):
+            yaw_deg = torch.as_tensor(np.asarray(yaw_deg, dtype=np.float32).reshape(plan.S), device=dev)
+        stream = torch.cuda.current_stream(dev)
+        out = torch.empty((plan.S, plan.E, plan.B), dtype=torch.float32, device=dev)
+        pre.process_device(x, plan.rows_buffer(), stream)
+        plan.process_rows_device(yaw_deg.contiguous(), out, stream)
+        if was_numpy:
+            out = out.cpu().numpy()
+        return out if batched else out[0]
 
     def set_hpcf(self, hpcf_filter_set):
         """Extension: run a headphone-compensation filter behind the renderer inside the renderer's

@@ -47,6 +47,7 @@ struct rtb_sh_plan {
     int mg_order = -1, mg_np = 0;
     float4 *d_mg_htab = nullptr;
     ShMgSignal *d_mg_signals = nullptr;
+    std::vector<float> h_rows;         // analysis rows [J][C] (rtb_sh_plan_get_analysis_rows)
     std::vector<ShSignal> h_sig;       // host copy of the signal list
     std::vector<float> h_hnm;          // host copy of H_nm [K][2][F] complex (P == 1)
     std::vector<int16_t> h_shm;        // sh_m[K]
@@ -607,6 +608,8 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     RTB_CUDA(cudaMemset(p->d_radlast, 0, sizeof(float) * 2 * p->S));
 
     p->symmetric = symmetric;
+    p->h_rows.assign((size_t)J * C, 0.f);
+    for (int j = 0; j < J; ++j) std::copy(rows[j].begin(), rows[j].end(), p->h_rows.begin() + (size_t)j * C);
     p->h_sig = sig;
     p->h_shm.assign(sh_m, sh_m + K);
     p->mg_enabled = p->P == 1 && (p->N2 == 256 || p->N2 == 512);
@@ -869,12 +872,14 @@ namespace {
 
 // kernels for streams [s0, s0 + count) of the current block; in/yaw/out point at stream s0
 void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const float *d_yaw_deg,
-                  float *d_out, cudaStream_t st) {
+                  float *d_out, cudaStream_t st, bool rows_given = false) {
     const size_t zhalf = (size_t)p->S * p->J * p->B, zo = (size_t)s0 * p->J * p->B;
     float *zcur = p->d_zring + (size_t)p->slot * zhalf + zo;
     const float *zprev = p->d_zring + (size_t)(p->slot ^ 1) * zhalf + zo;
-    launch_analysis(p, d_in, zcur, count, st);  // a1/a2: the overlap-save state advances in every mode
-    p->launches++;
+    if (!rows_given) {  // (pre-rendered mode: the rows of this block were written by the pre-renderer)
+        launch_analysis(p, d_in, zcur, count, st);  // a1/a2: the overlap-save state advances in every mode
+        p->launches++;
+    }
     // with an HPCF attached the renderer's binaural block goes to the filter's overlap-save state and
     // the filter writes what the caller receives (fused into the render kernels, stand-alone otherwise)
     HpcfParams hp = {};
@@ -1085,6 +1090,45 @@ int rtb_sh_process_block(rtb_sh_plan *p, const float *d_in, const float *d_yaw_d
     if (p->profiling) cudaEventRecord(p->ev[0], st);
     launch_range(p, 0, p->S, d_in, d_yaw_deg, d_out, st);
     if (p->profiling) { cudaEventRecord(p->ev[2], st); p->ev_valid = true; }
+    advance_block(p);
+    RTB_CUDA(cudaGetLastError());
+    return RTB_OK;
+}
+
+// ---- pre-rendered mode -------------------------------------------------------------------------
+// The array signals enter the chain only through the analysis rows z = R x (R = Re / Im of Y_w,
+// rtb_sh_plan_get_analysis_rows).  When they are themselves the output of a linear time-invariant
+// pre-renderer -- the reference's ARIR client, a mono source convolved with one room impulse
+// response per array channel (_run.py:240-288, OverlapSaveConvolver with a mono input) -- R can be
+// folded into its filters once at set-up time: z_j = (sum_c R[j][c] arir_c) * source.  The
+// pre-renderer then produces the J analysis rows directly (J = 169 instead of 434 channels at order
+// 12 on a 434-channel array), writes them into the plan's row buffer, and the renderer skips its
+// analysis GEMM.  Same result up to fp32 reassociation.
+int rtb_sh_plan_get_analysis_rows(rtb_sh_plan *p, float *rows) {
+    if (!p || !rows) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (!p->tables_set)
+        return fail(RTB_ERR_STATE, "blocks in spherical harmonics domain have not been calculated yet.");
+    std::copy(p->h_rows.begin(), p->h_rows.end(), rows);
+    return RTB_OK;
+}
+
+int rtb_sh_plan_rows_buffer(rtb_sh_plan *p, float **d_rows) {
+    if (!p || !d_rows) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (!p->tables_set)
+        return fail(RTB_ERR_STATE, "blocks in spherical harmonics domain have not been calculated yet.");
+    *d_rows = p->d_zring + (size_t)p->slot * ((size_t)p->S * p->J * p->B);
+    return RTB_OK;
+}
+
+int rtb_sh_process_block_rows(rtb_sh_plan *p, const float *d_yaw_deg, float *d_out, void *cuda_stream) {
+    if (!p || !d_out || !d_yaw_deg) return fail(RTB_ERR_INVALID, "NULL argument");
+    if (reinterpret_cast<uintptr_t>(d_out) & 15) return fail(RTB_ERR_INVALID, "device buffers must be 16-byte aligned");
+    if (!p->tables_set)
+        return fail(RTB_ERR_STATE, "blocks in spherical harmonics domain have not been calculated yet.");
+    if (p->passthrough)
+        return fail(RTB_ERR_UNSUPPORTED, "passthrough copies array channels to the ears; there are none in pre-rendered mode");
+    DeviceGuard guard(p->device);
+    launch_range(p, 0, p->S, nullptr, d_yaw_deg, d_out, (cudaStream_t)cuda_stream, true);
     advance_block(p);
     RTB_CUDA(cudaGetLastError());
     return RTB_OK;

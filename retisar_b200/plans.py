@@ -90,6 +90,22 @@ class ShPlan:
     def reset(self):
         check(lib.rtb_sh_plan_reset(self._h))
 
+    def analysis_rows(self):
+        """The real analysis matrix R [J, C] of the plan (z = R x; pre-rendered mode)."""
+        rows = np.empty((self.query(_capi.RTB_Q_ROWS), self.C), dtype=np.float32)
+        check(lib.rtb_sh_plan_get_analysis_rows(self._h, np_ptr(rows)))
+        return rows
+
+    def rows_buffer(self):
+        """Device address of the [S, J, B] buffer that must receive the next block's analysis rows."""
+        ptr = ctypes.c_void_p()
+        check(lib.rtb_sh_plan_rows_buffer(self._h, ctypes.byref(ptr)))
+        return ptr.value
+
+    def process_rows_device(self, d_yaw, d_out, stream=None):
+        """Render the block whose analysis rows were written into `rows_buffer()`."""
+        check(lib.rtb_sh_process_block_rows(self._h, _dev_ptr(d_yaw), _dev_ptr(d_out), _stream_ptr(stream)))
+
     def set_hpcf(self, hfd):
         """Attach a 2-channel headphone-compensation filter behind the renderer: hfd [P, 2, F]
         complex (``FilterSet.get_filter_blocks_fd()[:, 0]``); ``None`` detaches it."""

@@ -41,3 +41,61 @@ def test_c4_production_chain_matches_oracle_composition():
             peak = max(peak, float(np.abs(ref).max()))
     assert peak > 1e-3  # the chain carries signal
     assert worst <= TOL, worst
+
+
+@pytest.mark.parametrize("workload,S,arir_taps,hp_taps", [("c4", 5, 512, 1024), ("c2", 3, 1000, 0), ("c4", 130, 320, 256)])
+def test_chain_with_folded_pre_renderer_and_fused_hpcf(workload, S, arir_taps, hp_taps):
+    """The same production chain with the ARIR folded into the analysis domain
+    (`AdjustableShConvolver.set_pre_renderer`: the pre-renderer writes the analysis rows, no
+    434-channel intermediate, no analysis GEMM) and the HPCF fused into the render kernel
+    (`set_hpcf`), against the composition of the three pinned oracles on the ORIGINAL filters."""
+    import torch
+
+    from oracle import sh_chain as oc
+    from retisar_b200 import FilterSet
+    from retisar_b200 import synthetic as syn
+    from retisar_b200 import workloads as wl
+
+    tb = wl.sh_tables(workload, hrir_dirs=150)
+    B, C, order = tb["B"], tb["C"], tb["order"]
+    arir_irs = syn.decaying_noise_irs((C, arir_taps), 40)
+    rend = wl.make_renderer(tb, S)
+    rend.set_pre_renderer(arir_irs)
+    J = rend._plan.query(2)
+    assert rend._pre_renderer._plan.n_out == J and rend._pre_renderer._plan.n_in == 1
+    o_hpcf = None
+    if hp_taps:
+        hpcf_irs = syn.decaying_noise_irs((2, hp_taps), 41, scale=0.3)
+        hp = FilterSet.create_instance_by_type(hpcf_irs, "FIR_MULTICHANNEL")
+        hp.load(block_length=B, is_single_precision=True, is_prevent_logging=True)
+        rend.set_hpcf(hp)
+        o_hpcf = {}
+    cfg, hnm = tb["sh_config"], rend._filter.get_filter_blocks_nm()
+    probes = sorted({0, S // 2, S - 1})
+    o_arir = {s: oc.OlsOracle(oc.filter_blocks_fd(oc.zero_pad(arir_irs[None], B), B), B) for s in probes}
+    o_rend = {s: oc.ShOracle(cfg.sh_m, cfg.sh_bases_weighted, hnm, B, order) for s in probes}
+    if hp_taps:
+        o_hpcf = {s: oc.OlsOracle(oc.filter_blocks_fd(oc.zero_pad(hpcf_irs[None], B), B), B) for s in probes}
+    dev = torch.device("cuda", 0)
+    T = arir_taps // B + 8
+    x = syn.noise_blocks(T, S, B, 12, scale=0.5).reshape(T, S, 1, B)
+    yaw = np.stack([syn.yaw_walk(T, 60 + s, step=15.0) for s in range(S)], axis=1).astype(np.float32)
+    worst = peak = 0.0
+    for t in range(T):
+        if t == T - 3:  # pause protocol: every client clears its buffers
+            rend._clear_buffers()
+            for d in (o_arir, o_rend) + ((o_hpcf,) if o_hpcf else ()):
+                for o in d.values():
+                    o.clear()
+        y = rend.filter_block(torch.from_numpy(x[t]).to(dev), torch.from_numpy(yaw[t]).to(dev)).cpu().numpy()
+        for s in probes:
+            ref = o_rend[s].filter_block(o_arir[s].filter_block(x[t, s]), yaw[t, s])
+            if o_hpcf:
+                ref = o_hpcf[s].filter_block(ref)
+            worst = max(worst, float(np.abs(y[s] - ref).max()))
+            peak = max(peak, float(np.abs(ref).max()))
+    print(workload, "S", S, "rows", J, "max abs err", worst, "peak", peak)
+    assert peak > 1e-3 and worst <= TOL, (worst, peak)
+    # numpy in, numpy out
+    y = rend.filter_block(x[0], yaw[0])
+    assert isinstance(y, np.ndarray) and y.shape == (S, 2, B)

@@ -23,11 +23,18 @@ ap.add_argument("--steps", type=int, default=200)
 ap.add_argument("--warmup", type=int, default=20)
 ap.add_argument("--arir-taps", type=int, default=4096)
 ap.add_argument("--hpcf-taps", type=int, default=1024)
+ap.add_argument("--fused", action="store_true",
+                help="ARIR folded into the analysis domain (set_pre_renderer) and HPCF fused into the render "
+                     "kernel (set_hpcf): two convolver launches groups instead of three separate convolvers")
 a = ap.parse_args()
 
 tb = wl.sh_tables("c4", hrir_dirs=600)
 S, B, C = a.streams, tb["B"], tb["C"]
-arir, rend, hpcf, _, _ = wl.make_c4_chain(tb, S, arir_taps=a.arir_taps, hpcf_taps=a.hpcf_taps)
+arir, rend, hpcf, arir_irs, _ = wl.make_c4_chain(tb, S, arir_taps=a.arir_taps, hpcf_taps=a.hpcf_taps)
+if a.fused:
+    rend.set_pre_renderer(arir_irs)
+    rend.set_hpcf(hpcf._filter)
+    arir = hpcf = None
 dev = torch.device("cuda", 0)
 ring = 16
 x = torch.randn((ring, S, 1, B), device=dev) * 0.5
@@ -36,6 +43,13 @@ st = torch.cuda.current_stream()
 
 
 def step(i, ev=None):
+    if a.fused:
+        if ev:
+            ev[0].record(st); ev[1].record(st)
+        y = rend.filter_block(x[i % ring], yaw[i % ring])
+        if ev:
+            ev[2].record(st); ev[3].record(st)
+        return y
     if ev: ev[0].record(st)
     z = arir.filter_block(x[i % ring])
     if ev: ev[1].record(st)
@@ -70,6 +84,7 @@ print(json.dumps({
     "metric": "real-time binaural streams @48kHz/64-blk per GPU (c4 production chain)",
     "value": S * period_ms / ms, "unit": "realtime_streams", "ms_per_step": ms, "block_period_ms": period_ms,
     "config": {"workload": "c4 chain: mono source -> 434-ch ARIR pre-renderer -> SH renderer (order 12, B=64) -> HPCF",
+               "fused": bool(a.fused),
                "streams": S, "block_length": B, "channels": C, "arir_taps": a.arir_taps, "arir_partitions": P_arir,
                "hpcf_taps": a.hpcf_taps, "hpcf_partitions": P_hpcf, "input_ring_blocks": ring},
     "ms_per_convolver": {"arir_pre_renderer": float(parts[0]), "sh_renderer": float(parts[1]), "hpcf": float(parts[2])},
