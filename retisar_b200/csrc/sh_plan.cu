@@ -43,7 +43,7 @@ struct rtb_sh_plan {
     // programmatic dependent launch of the chain's kernels: RTB_PDL=1 enables.  Measured on B200:
     // 1 024 streams 55.4 -> 62.8 us per block (worse), 10 240 streams 385 -> 380 us: off by default
     bool pdl = false;
-    bool mg_enabled = false;
+    bool mg_enabled = false, mg_forced = false;
     int mg_order = -1, mg_np = 0;
     float4 *d_mg_htab = nullptr;
     ShMgSignal *d_mg_signals = nullptr;
@@ -177,13 +177,18 @@ void launch_render(const rtb_sh_plan *p, const ShRenderParams &prm, cudaStream_t
 template <int N2>
 void launch_render_mg_t(const ShRenderMgParams &prm, cudaStream_t st, bool pdl) {
     const size_t smem = RTB_MG_ACC_SMEM ? sizeof(float2) * 4 * (FftCfg<N2>::EPL / 2) * 4 * 32 : 0;
+    constexpr int per_cta = 4 * FftCfg<N2>::GROUPS;  // one stream per transform group
     kernel_attrs_once(sh_render_mg_kernel<N2>, 100 * 1024, true);
-    launch_pdl(sh_render_mg_kernel<N2>, dim3((unsigned)((prm.S + 3) / 4)), dim3(128), smem, st, pdl, prm);
+    launch_pdl(sh_render_mg_kernel<N2>, dim3((unsigned)((prm.S + per_cta - 1) / per_cta)), dim3(128), smem, st, pdl, prm);
 }
 
 void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStream_t st) {
-    if (p->N2 == 256) launch_render_mg_t<256>(prm, st, p->pdl);
-    else launch_render_mg_t<512>(prm, st, p->pdl);
+    switch (p->N2) {
+        case 64: launch_render_mg_t<64>(prm, st, p->pdl); break;
+        case 128: launch_render_mg_t<128>(prm, st, p->pdl); break;
+        case 256: launch_render_mg_t<256>(prm, st, p->pdl); break;
+        default: launch_render_mg_t<512>(prm, st, p->pdl); break;
+    }
 }
 
 // Tables of the steady-state render kernel for SH order `order`: signals sorted by m (one group
@@ -612,8 +617,11 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     for (int j = 0; j < J; ++j) std::copy(rows[j].begin(), rows[j].end(), p->h_rows.begin() + (size_t)j * C);
     p->h_sig = sig;
     p->h_shm.assign(sh_m, sh_m + K);
-    p->mg_enabled = p->P == 1 && (p->N2 == 256 || p->N2 == 512);
-    if (const char *env = getenv("RTB_RENDER_MG")) p->mg_enabled = p->mg_enabled && env[0] != '0';
+    p->mg_enabled = p->P == 1 && p->N2 <= 512;  // every warp-level transform size
+    if (const char *env = getenv("RTB_RENDER_MG")) {
+        p->mg_enabled = p->mg_enabled && env[0] != '0';
+        p->mg_forced = env[0] == '1';
+    }
     if (const char *env = getenv("RTB_PDL")) p->pdl = env[0] != '0';
     if (p->mg_enabled) {
         p->h_hnm.assign(hnm, hnm + 2 * (size_t)K * 2 * F);
@@ -1008,7 +1016,12 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         const int np_last = (p->crossfade && p->last_valid) ? signals_for_order(p, p->last_order) : 0;
         // steady state (both yaws at the same order): the m-grouped kernel; its tables follow
         // the current order (rebuilt on the first block after the order settled)
-        bool use_mg = p->mg_enabled && (np_last == 0 || np_last == np_cur);
+        // several streams share a warp below 128-sample blocks: 8 / 16 streams per CTA under-fill the GPU
+        // for small batches, where the term-wise kernel (one stream per warp) is faster (measured, c4:
+        // 1 024 streams 93 vs 86 us, 4 096 streams 0.747 vs 0.804 ms for the chain)
+        // (RTB_RENDER_MG=1 at plan creation forces the m-grouped kernel)
+        bool use_mg = p->mg_enabled && (np_last == 0 || np_last == np_cur) &&
+                      (p->N2 >= 256 || count >= 2048 || p->mg_forced);
         if (use_mg && p->mg_order != p->cur_order) {
             cudaStreamSynchronize(st);
             use_mg = build_mg_tables(p, p->cur_order) == RTB_OK && p->mg_enabled;

@@ -28,12 +28,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // inverse FFT of (left + i right), overlap-save discard, cos^2 cross-fade, coalesced store.
 // With G < 32 the current-yaw pair is transformed by group 0 and the previous-yaw pair by group 1
 // at the same time; with G == 32 the warp does them one after the other.
-template <int N2>
+// SOLO: the transform group does both yaws itself, one after the other, whatever the number of
+// groups per warp (each group of the warp renders its own stream; `store` = the stream exists).
+template <int N2, bool SOLO = false>
 __device__ __forceinline__ void render_tail(float2 (&acc)[FftCfg<N2>::EPL / 2 + 1][4], float2 *buf,
                                             const float2 *s_tw, int grp, int l, const float *win_in,
-                                            const float *win_out, int crossfade, float *o) {
+                                            const float *win_out, int crossfade, float *o, bool store = true) {
     using Cfg = FftCfg<N2>;
-    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS;
+    constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = SOLO ? 1 : Cfg::GROUPS;
     constexpr int B = N2 / 2;
     constexpr unsigned FULL = 0xffffffffu;
     fft_sync<N2>();
@@ -70,7 +72,7 @@ __device__ __forceinline__ void render_tail(float2 (&acc)[FftCfg<N2>::EPL / 2 + 
             ylast[u].y = __shfl_sync(FULL, ylast[u].y, (lane + G) & 31);
         }
     }
-    if (grp == 0) {
+    if (grp == 0 && store) {
 #pragma unroll
         for (int u = 0; u < HB; ++u) {
             const int n = l + G * u;

@@ -74,26 +74,31 @@ __device__ __forceinline__ void cfma_conj(float2 &acc, float2 h, float2 x) {
 #endif
 }
 
+// One transform group (G lanes: a whole warp for N2 = 256 / 512, half a warp for N2 = 128, a quarter
+// for N2 = 64) renders one stream; the groups of a warp are different streams walking the signal
+// list in lock step, so a CTA covers 4 * GROUPS streams and shares the staged HRIR tile among them.
 template <int N2>
 __global__ void __launch_bounds__(128, RTB_RENDER_MG_MIN_CTAS)
 sh_render_mg_kernel(const ShRenderMgParams prm) {
     using Cfg = FftCfg<N2>;
-    static_assert(Cfg::GROUPS == 1, "one transform per warp");
-    constexpr int EPL = Cfg::EPL, HB = EPL / 2;
+    static_assert(!Cfg::BIG, "warp-level transforms only");
+    constexpr int G = Cfg::G, GROUPS = Cfg::GROUPS, EPL = Cfg::EPL, HB = EPL / 2;
     constexpr int B = N2 / 2, F = B + 1;
     constexpr int HSIG = 2 * F;
     constexpr unsigned FULL = 0xffffffffu;
 
     __shared__ __align__(16) float2 s_tw[N2];
-    __shared__ __align__(128) float2 s_buf[4][Cfg::REGION];
+    __shared__ __align__(128) float2 s_buf[4][GROUPS * Cfg::REGION];
     __shared__ __align__(16) float4 s_h[2][HSIG];
-    __shared__ float2 s_cs[4][2][RTB_MAX_ORDER + 1];
+    __shared__ float2 s_cs[4 * GROUPS][2][RTB_MAX_ORDER + 1];
     __shared__ ShMgSignal s_sig[RTB_MG_MAX_SIGNALS];  // the signal list: no dependent global load per round
 #if RTB_MG_ACC_SMEM
     extern __shared__ __align__(128) unsigned char dyn_smem[];  // [4 warps][HB][4][32 lanes] float2
 #endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, l = lane % G;        // transform group of the lane, lane inside the group
+    const int sw = warp * GROUPS + grp;            // stream slot inside the CTA
     // twiddles arrive asynchronously with the first tile (waited for at the top of the first round)
     for (int i = threadIdx.x; i < N2 / 2; i += 128) cp_async16_ca(&s_tw[2 * i], prm.tw + 2 * i);
     for (int i = threadIdx.x; i < prm.np * (int)(sizeof(ShMgSignal) / sizeof(int2)); i += 128)
@@ -105,11 +110,11 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     for (int i = 0; i < HB * 4; ++i) sacc[i * 32] = make_float2(0.f, 0.f);
 #endif
 
-    const int s = blockIdx.x * 4 + warp;
+    const int s = blockIdx.x * (4 * GROUPS) + sw;
     const bool active = s < prm.S;
-    float2 *buf = s_buf[warp];
+    float2 *buf = s_buf[warp] + grp * Cfg::REGION;
     float *zrow = reinterpret_cast<float *>(buf);
-    const int partner = (32 - lane) & 31;
+    const int partner = (G - l) & (G - 1);
     const int np = prm.np;
     const size_t zoff = (size_t)(active ? s : 0) * prm.J * B;
 
@@ -124,23 +129,24 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     auto prefetch_z = [&](int p) {
         if (!active) return;
         const int row_re = s_sig[p].row_re, row_im = s_sig[p].row_im;
-        constexpr int NCH = B / 128;  // chunks per lane and row half
+        constexpr int NCH = B / (4 * G);  // 16-byte chunks per lane and row half
+        static_assert(NCH >= 1, "a row half has at least one chunk per lane");
 #pragma unroll
         for (int im = 0; im < 2; ++im) {
             const int row = im ? row_im : row_re;
-            float *dst = zrow + im * N2 + lane * 4;
+            float *dst = zrow + im * N2 + l * 4;
             if (row >= 0) {
-                const size_t o = zoff + (size_t)row * B + lane * 4;
+                const size_t o = zoff + (size_t)row * B + l * 4;
                 const float *sp = prm.zprev + o, *sc = prm.zcur + o;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
-                    cp_async16_cg(dst + 128 * c, sp + 128 * c);
-                    cp_async16_cg(dst + B + 128 * c, sc + 128 * c);
+                    cp_async16_cg(dst + 4 * G * c, sp + 4 * G * c);
+                    cp_async16_cg(dst + B + 4 * G * c, sc + 4 * G * c);
                 }
             } else {
 #pragma unroll
                 for (int c = 0; c < 2 * NCH; ++c)
-                    *reinterpret_cast<float4 *>(dst + 128 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4 *>(dst + 4 * G * c) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     };
@@ -155,14 +161,14 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     if (active) {  // a4: (cos, sin)(m alpha) for the current and the previous yaw
         const float rad_cur = yaw_deg_to_rad16(prm.yaw_deg[s], prm.tracker_dir, prm.src_azim16);
         const float rad_last = prm.rad_last_in[s];
-        if (lane <= prm.order_max) {
+        for (int m = l; m <= prm.order_max; m += G) {
             float sn, cs;
-            sincosf((float)lane * rad_cur, &sn, &cs);
-            s_cs[warp][0][lane] = make_float2(cs, sn);
-            sincosf((float)lane * rad_last, &sn, &cs);
-            s_cs[warp][1][lane] = prm.last_on ? make_float2(cs, sn) : make_float2(0.f, 0.f);
+            sincosf((float)m * rad_cur, &sn, &cs);
+            s_cs[sw][0][m] = make_float2(cs, sn);
+            sincosf((float)m * rad_last, &sn, &cs);
+            s_cs[sw][1][m] = prm.last_on ? make_float2(cs, sn) : make_float2(0.f, 0.f);
         }
-        if (prm.crossfade && lane == 0) prm.rad_last_out[s] = rad_cur;
+        if (prm.crossfade && l == 0) prm.rad_last_out[s] = rad_cur;
     }
 
     // ear spectra [bin slot][cur ear0, cur ear1, last ear0, last ear1]; group sums U (bins
@@ -189,17 +195,17 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
         __syncthreads();
         if (p + 1 < np) prefetch_h(p + 1, stage ^ 1);
         cp_async_commit();
-        if (!active) continue;
+        if (GROUPS == 1 && !active) continue;   // (with several streams per warp the whole warp stays in step)
         const ShMgSignal sg = s_sig[p];
 
         float2 X[EPL];
 #pragma unroll
         for (int u = 0; u < EPL; ++u) {
-            X[u].x = zrow[lane + 32 * u];
-            X[u].y = zrow[N2 + lane + 32 * u];
+            X[u].x = active ? zrow[l + G * u] : 0.f;
+            X[u].y = active ? zrow[N2 + l + G * u] : 0.f;
         }
         __syncwarp();
-        warp_fft_hook<N2, false>(X, buf, s_tw, lane, [&] {
+        warp_fft_hook<N2, false>(X, buf, s_tw, l, [&] {
             if (p + 1 < np) prefetch_z(p + 1);  // the exchange buffer is idle from here on
             cp_async_commit();
         });
@@ -207,26 +213,26 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
         const float4 *h1 = s_h[stage], *h2 = h1 + F;
 #pragma unroll
         for (int u = 0; u <= HB; ++u) {
-            const float4 h = h1[(u < HB) ? (lane + 32 * u) : B];
+            const float4 h = h1[(u < HB) ? (l + G * u) : B];
             cfma(U[u][0], make_float2(h.x, h.y), X[u]);
             cfma(U[u][1], make_float2(h.z, h.w), X[u]);
         }
         if (sg.has2) {
 #pragma unroll
             for (int v = 0; v <= HB; ++v) {
-                const float4 h = h2[(v < HB) ? (lane + 32 * v) : B];
+                const float4 h = h2[(v < HB) ? (l + G * v) : B];
                 const float2 x = (v < HB) ? X[HB + v] : X[0];
                 cfma_conj(V[v][0], make_float2(h.x, h.y), x);
                 cfma_conj(V[v][1], make_float2(h.z, h.w), x);
             }
         }
         if (sg.flush) {  // rotate the group sums by the two yaws and add them to the ear spectra
-            const float2 p1c = phase_of(s_cs[warp][0], sg.m1), p1l = phase_of(s_cs[warp][1], sg.m1);
+            const float2 p1c = phase_of(s_cs[sw][0], sg.m1), p1l = phase_of(s_cs[sw][1], sg.m1);
             const bool hasV = sg.m2 != RTB_MG_NO_TERM;
             float2 p2c = make_float2(0.f, 0.f), p2l = p2c;
             if (hasV) {
-                p2c = phase_of(s_cs[warp][0], sg.m2);
-                p2l = phase_of(s_cs[warp][1], sg.m2);
+                p2c = phase_of(s_cs[sw][0], sg.m2);
+                p2l = phase_of(s_cs[sw][1], sg.m2);
             }
 #pragma unroll
             for (int u = 0; u <= HB; ++u) {
@@ -235,11 +241,11 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
                 float2 v0 = make_float2(0.f, 0.f), v1 = v0;
                 if (hasV) {
                     if (u < HB) {
-                        v0.x = __shfl_sync(FULL, V[HB - 1 - u][0].x, partner);
-                        v0.y = __shfl_sync(FULL, V[HB - 1 - u][0].y, partner);
-                        v1.x = __shfl_sync(FULL, V[HB - 1 - u][1].x, partner);
-                        v1.y = __shfl_sync(FULL, V[HB - 1 - u][1].y, partner);
-                        if (lane == 0) { v0 = V[HB - u][0]; v1 = V[HB - u][1]; }
+                        v0.x = __shfl_sync(FULL, V[HB - 1 - u][0].x, partner, G);
+                        v0.y = __shfl_sync(FULL, V[HB - 1 - u][0].y, partner, G);
+                        v1.x = __shfl_sync(FULL, V[HB - 1 - u][1].x, partner, G);
+                        v1.y = __shfl_sync(FULL, V[HB - 1 - u][1].y, partner, G);
+                        if (l == 0) { v0 = V[HB - u][0]; v1 = V[HB - u][1]; }
                     } else {
                         v0 = V[0][0]; v1 = V[0][1];
                     }
@@ -280,7 +286,8 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     }
     cp_async_wait_all();
     if (np == 0) __syncthreads();
-    if (!active) return;
+    if (GROUPS == 1 && !active) return;
+    if (!__any_sync(FULL, active)) return;
 #if RTB_MG_ACC_SMEM
     float2 acc[HB + 1][4];
 #pragma unroll
@@ -288,9 +295,10 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[u][q] = (u < HB) ? sacc[(u * 4 + q) * 32] : accn[q];
 #endif
-    render_tail<N2>(acc, s_buf[warp], s_tw, 0, lane, prm.win_in, prm.win_out, prm.crossfade,
-                    prm.out + (size_t)s * 2 * B);
-    if (prm.hp.P > 0) hpcf_stage<N2>(prm.hp, s, true, s_buf[warp], s_tw, lane);  // prm.out is the HPCF's input state then
+    // every group renders its own stream: both yaws one after the other inside the group
+    render_tail<N2, true>(acc, buf, s_tw, 0, l, prm.win_in, prm.win_out, prm.crossfade,
+                          prm.out + (size_t)(active ? s : 0) * 2 * B, active);
+    if (prm.hp.P > 0) hpcf_stage<N2>(prm.hp, active ? s : 0, active, buf, s_tw, l);  // prm.out is the HPCF's input state then
 }
 
 }  // namespace rtb

@@ -43,3 +43,27 @@ def test_variant_matches_reference_golden(env, monkeypatch):
         plan2.process_device(x, yaw, out, torch.cuda.current_stream())
         torch.cuda.synchronize()
         assert np.abs(out.cpu().numpy() - g["y"][t][None]).max() <= TOL, (env, "device", t)
+
+
+@pytest.mark.parametrize("name", ["sh_em32_n4_b64_events", "sh_rnd50_n3_b32", "sh_em32_n2_b64_general",
+                                  "sh_rnd434_n12_b64"])
+def test_m_grouped_kernel_on_small_blocks(name, monkeypatch):
+    """Below 128-sample blocks several streams share a warp in the m-grouped render kernel (it is the
+    default only for batches of 2 048 streams and more): forced here on the small-block goldens of the
+    unmodified reference, with more streams than one CTA holds and a ragged last warp."""
+    from retisar_b200 import _capi
+
+    monkeypatch.setenv("RTB_RENDER_MG", "1")
+    g = load_golden(name)
+    S = 21
+    plan = make_plan(g, S)
+    used = set()
+    for t in range(g["x"].shape[0]):
+        apply_event(plan, *g["events"][t])
+        x = np.repeat(g["x"][t][None], S, axis=0)
+        yaw = np.repeat(g["yaw"][t:t + 1], S)
+        y = plan.process_host(x, yaw)
+        used.add(_capi.RENDER_KERNEL_NAMES[plan.query(_capi.RTB_Q_RENDER_KERNEL)])
+        assert np.abs(y - g["y"][t][None]).max() <= TOL, (name, t)
+    assert "sh_render_mg_kernel" in used, used
+
