@@ -133,42 +133,66 @@ fd_render_kernel(const FdParams prm) {
         }
         const bool use_last = do_last && prm.last_valid;
         const size_t dstride = (size_t)prm.P * 2 * Fp;
-        for (int p = 0; p < prm.P; ++p) {
-            const float2 *hc0 = prm.hfd + dc0 * dstride + (size_t)p * 2 * Fp;
-            const float2 *hc1 = prm.hfd + dc1 * dstride + (size_t)p * 2 * Fp;
-            const float2 *hl0 = prm.hfd + dl0 * dstride + (size_t)p * 2 * Fp;
-            const float2 *hl1 = prm.hfd + dl1 * dstride + (size_t)p * 2 * Fp;
-            float2 *qcp = qc + (size_t)((prm.head_cur + p) % prm.P) * 2 * Fp;
-            float2 *qlp = ql + (size_t)((prm.head_last + p) % prm.P) * 2 * Fp;
+        // Bin slot outermost, partitions in batches of PB: the filter spectra (4 directions x 2 ears)
+        // and the queue values of a whole batch are requested before the first one is used, so a lane
+        // has 12 * PB loads in flight (the first version walked partition by partition and waited for
+        // every load where it was issued: ncu 44 long-scoreboard stall cycles per issue, issue-active
+        // 0.04, 0.71 ms for 4 096 streams x 2 sources x 8 partitions).
+        constexpr int PB = 4;
+        const float2 *hd[4] = {prm.hfd + dc0 * dstride, prm.hfd + dc1 * dstride,
+                               prm.hfd + dl0 * dstride, prm.hfd + dl1 * dstride};
 #pragma unroll
-            for (int u = 0; u <= HB; ++u) {
-                const int f = (u < HB) ? (l + G * u) : B;
-                const bool own = (u < HB) || (l == 0);
-                const float2 a0 = make_float2(X0[u].x * prm.inv_ns, X0[u].y * prm.inv_ns);
-                const float2 a1 = make_float2(X1[u].x * prm.inv_ns, X1[u].y * prm.inv_ns);
-                float2 c[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        for (int u = 0; u <= HB; ++u) {
+            const int f = (u < HB) ? (l + G * u) : B;
+            const bool own = (u < HB) || (l == 0);
+            const float2 a0 = make_float2(X0[u].x * prm.inv_ns, X0[u].y * prm.inv_ns);
+            const float2 a1 = make_float2(X1[u].x * prm.inv_ns, X1[u].y * prm.inv_ns);
+            for (int p0 = 0; p0 < prm.P; p0 += PB) {
+                float2 h[PB][4][2], q[PB][4];
+                float2 *qp[PB][2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    cfma(c[e], __ldg(hc0 + (size_t)e * Fp + f), a0);
-                    if (has1) cfma(c[e], __ldg(hc1 + (size_t)e * Fp + f), a1);
-                    if (use_last) {
-                        cfma(c[2 + e], __ldg(hl0 + (size_t)e * Fp + f), a0);
-                        if (has1) cfma(c[2 + e], __ldg(hl1 + (size_t)e * Fp + f), a1);
-                    }
-                }
-                if (p == 0) {  // the head stays in registers
+                for (int i = 0; i < PB; ++i) {
+                    const int p = min(p0 + i, prm.P - 1);  // clamped: surplus batch entries are not used
+                    qp[i][0] = qc + (size_t)((prm.head_cur + p) % prm.P) * 2 * Fp + f;
+                    qp[i][1] = ql + (size_t)((prm.head_last + p) % prm.P) * 2 * Fp + f;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { acc[u][q].x += c[q].x; acc[u][q].y += c[q].y; }
-                } else if (own && grp == 0) {
+                    for (int d = 0; d < 4; ++d)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const bool need = (d < 2 || use_last) && ((d & 1) == 0 || has1);
+                            h[i][d][e] = need ? __ldg(hd[d] + (size_t)p * 2 * Fp + (size_t)e * Fp + f)
+                                              : make_float2(0.f, 0.f);
+                        }
+                    const bool rmw = own && grp == 0 && p0 + i > 0 && p0 + i < prm.P;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        float2 v = qcp[(size_t)e * Fp + f];
-                        v.x += c[e].x; v.y += c[e].y;
-                        qcp[(size_t)e * Fp + f] = v;
+                        q[i][e] = rmw ? qp[i][0][(size_t)e * Fp] : make_float2(0.f, 0.f);
+                        q[i][2 + e] = (rmw && use_last) ? qp[i][1][(size_t)e * Fp] : make_float2(0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < PB; ++i) {
+                    const int p = p0 + i;
+                    if (p >= prm.P) break;
+                    float2 c[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        cfma(c[e], h[i][0][e], a0);
+                        if (has1) cfma(c[e], h[i][1][e], a1);
                         if (use_last) {
-                            float2 w = qlp[(size_t)e * Fp + f];
-                            w.x += c[2 + e].x; w.y += c[2 + e].y;
-                            qlp[(size_t)e * Fp + f] = w;
+                            cfma(c[2 + e], h[i][2][e], a0);
+                            if (has1) cfma(c[2 + e], h[i][3][e], a1);
+                        }
+                    }
+                    if (p == 0) {  // the head stays in registers
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { acc[u][k].x += c[k].x; acc[u][k].y += c[k].y; }
+                    } else if (own && grp == 0) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            qp[i][0][(size_t)e * Fp] = make_float2(q[i][e].x + c[e].x, q[i][e].y + c[e].y);
+                            if (use_last)
+                                qp[i][1][(size_t)e * Fp] = make_float2(q[i][2 + e].x + c[2 + e].x, q[i][2 + e].y + c[2 + e].y);
                         }
                     }
                 }

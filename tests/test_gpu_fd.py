@@ -3,7 +3,7 @@ fixtures produced by the unmodified reference.  Bar: 1e-5 of full scale."""
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import check_regression_bar, load_golden
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -47,7 +47,7 @@ def test_fd_convolver_matches_reference_golden(name):
         err = np.abs(y - g["y"][t]).max()
         worst = max(worst, err)
         assert err <= TOL, (name, t, err)
-    print(name, "max abs err", worst)
+    check_regression_bar(float(worst), float(np.abs(g["y"]).max()), name)
 
 
 def test_fd_batched_streams_vs_oracle():

@@ -3,7 +3,7 @@ through the reference-shaped OverlapSaveConvolver class.  Bar: 1e-5 of full scal
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import check_regression_bar, load_golden
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -33,7 +33,7 @@ def test_ols_plan_matches_reference_golden(name):
         err = np.abs(y - g["y"][t]).max()
         worst = max(worst, err)
         assert err <= TOL, (name, t, err)
-    print(name, "max abs err", worst)
+    check_regression_bar(float(worst), float(np.abs(g["y"]).max()), name)
 
 
 @pytest.mark.parametrize("name", ["ols_2ch_1024_b256", "ols_arir_mono_6ch_b64"])

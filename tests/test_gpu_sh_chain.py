@@ -6,7 +6,7 @@ them (tests/test_oracle_vs_golden.py)."""
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import check_regression_bar, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -48,7 +48,7 @@ def test_sh_chain_matches_reference_golden(name):
         err = np.abs(y - g["y"][t]).max()
         worst = max(worst, err)
         assert err <= TOL, (name, t, err)
-    print(name, "max abs err", worst, "peak", np.abs(g["y"]).max())
+    check_regression_bar(float(worst), float(np.abs(g["y"]).max()), name)
 
 
 def test_symmetric_mode_detected():

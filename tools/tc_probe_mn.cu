@@ -16,9 +16,11 @@
 
 constexpr int M = 128, N = 32, K = 32;
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout,
+                                              uint32_t lbo_mode = 0) {
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+           ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(lbo_mode & 1) << 52) |
+           ((uint64_t)layout << 61);
 }
 
 __global__ void __launch_bounds__(128) probe(const float *x, const float *bsrc, float *d_out, int variant) {
@@ -32,7 +34,8 @@ __global__ void __launch_bounds__(128) probe(const float *x, const float *bsrc, 
     for (int i = tid; i < K * M; i += 128) {
         const int c = i / M, t = i % M, mb = t / 32, s = t % 32;
         uint32_t off = mb * BLK + (c / 8) * 1024 + (c % 8) * 128 + (((s / 4) ^ (c % 8)) * 16) + (s % 4) * 4;
-        if (variant >= 5)  // un-swizzled MN-major core matrices: 4 samples x 8 channels, 128 B each
+        const int lay_variant = variant == 7 ? 5 : (variant == 8 ? 0 : variant);
+        if (lay_variant >= 5)  // un-swizzled MN-major core matrices: 4 samples x 8 channels, 128 B each
             off = (c / 8) * (M / 4) * 128 + (t / 4) * 128 + (c % 8) * 16 + (t % 4) * 4;
         a[off / 4] = x[i];
     }
@@ -51,6 +54,9 @@ __global__ void __launch_bounds__(128) probe(const float *x, const float *bsrc, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
     if (tid == 0) {
+        const uint32_t lbo_mode = variant >= 7 ? 1u : 0u;  // round 2: same layouts with the descriptor's lbo_mode bit
+        if (variant == 7) variant = 5;
+        if (variant == 8) variant = 0;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (variant == 4 ? 0u : (1u << 15)) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
         // A: per MMA (K = 8 channels) the start address advances by 1024 B (one 8-channel row group)
         uint32_t lbo_a = BLK, sbo_a = 1024;
@@ -66,7 +72,7 @@ __global__ void __launch_bounds__(128) probe(const float *x, const float *bsrc, 
             sbo_a = (variant == 5) ? 128 : kstep;
         }
         for (int s = 0; s < K / 8; ++s) {
-            const uint64_t da = make_desc(smem_u32(a) + s * kstep, lbo_a, sbo_a, layout);
+            const uint64_t da = make_desc(smem_u32(a) + s * kstep, lbo_a, sbo_a, layout, lbo_mode);
             const uint64_t db = make_desc(smem_u32(b) + s * 2 * lbo_b, lbo_b, sbo_b, 0);
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -110,7 +116,7 @@ int main() {
     const int smem = (K * M + K * N) * 4 + 1024;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     std::vector<float> d((size_t)M * N);
-    for (int variant = 0; variant < 7; ++variant) {
+    for (int variant = 0; variant < 9; ++variant) {
         cudaMemset(dd, 0, (size_t)M * N * 4);
         probe<<<1, 128, smem>>>(dx, db, dd, variant);
         cudaError_t e = cudaDeviceSynchronize();
