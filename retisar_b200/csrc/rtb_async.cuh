@@ -22,6 +22,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
+// same with a suspend-time hint (ns): the waiting warp may sleep that long before it polls again, which
+// leaves the issue slots to the warps that work (spin loops were 18 % of the issued instructions of the
+// partition kernel)
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, unsigned parity, unsigned hint_ns = 2000) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity), "r"(hint_ns) : "memory");
+}
 __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),

@@ -61,6 +61,15 @@ struct ShPartTcParams {
     float tracker_dir, src_azim16;
 };
 
+// TF32 split with the conversion instruction (round to nearest, ties away): hi has 10 mantissa bits,
+// lo = v - hi is exact in fp32; one instruction less per value than the integer rounding trick
+__device__ __forceinline__ void split_tf32_cvt(float v, float &hi, float &lo) {
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    hi = __uint_as_float(u);
+    lo = v - hi;
+}
+
 __device__ __forceinline__ float2 ldg_stream_v2(const float2 *p) {  // streamed once: keep it out of L1
     float2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
@@ -153,7 +162,7 @@ sh_partition_tc_kernel(const ShPartTcParams prm) {
                 const ShStep stp = s_steps[j];
                 z[jj] = ldg_stream_v2(zrow + ((size_t)(stp.term ? fm : f) * prm.NPT + stp.p) * prm.Spad);
             }
-            mbar_wait(&empty_bar[g], (unsigned)((k & 1) ^ 1));
+            mbar_wait_sleepy(&empty_bar[g], (unsigned)((k & 1) ^ 1));
             if (wq == 0 && lane == 0) {  // this unit's block of the split H operand -> stage
                 const unsigned bytes = (unsigned)(bunit * sizeof(float));
                 mbar_expect_tx(&full_bar[g], bytes);
@@ -181,10 +190,10 @@ sh_partition_tc_kernel(const ShPartTcParams prm) {
                 for (int cl = 0; cl < 2; ++cl) {
                     if (cl == 1 && !prm.do_last) break;
                     float hi[4], lo[4];
-                    split_tf32(a[cl][0].x, hi[0], lo[0]);
-                    split_tf32(a[cl][0].y, hi[1], lo[1]);
-                    split_tf32(a[cl][1].x, hi[2], lo[2]);
-                    split_tf32(a[cl][1].y, hi[3], lo[3]);
+                    split_tf32_cvt(a[cl][0].x, hi[0], lo[0]);
+                    split_tf32_cvt(a[cl][0].y, hi[1], lo[1]);
+                    split_tf32_cvt(a[cl][1].x, hi[2], lo[2]);
+                    split_tf32_cvt(a[cl][1].y, hi[3], lo[3]);
                     float *dst = st_a + (size_t)cl * 2 * KC * M + (size_t)kq * (4 * M) + 4 * r;
                     *reinterpret_cast<float4 *>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<float4 *>(dst + KC * M) = make_float4(lo[0], lo[1], lo[2], lo[3]);
@@ -203,12 +212,12 @@ sh_partition_tc_kernel(const ShPartTcParams prm) {
         long long mm = 0;
         for (long long it = 0; it < my_tiles; ++it) {
             const int buf = (int)(it & 1);
-            mbar_wait(&tempty_bar[buf], (unsigned)(((it >> 1) & 1) ^ 1));
+            mbar_wait_sleepy(&tempty_bar[buf], (unsigned)(((it >> 1) & 1) ^ 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int h = 0; h < n_chunks; ++h, ++mm) {
                 const int g = (int)(mm % LG);
                 const int ksteps = min(KC / 8, (2 * nsteps - h * KC + 7) / 8);  // the last chunk may be short
-                mbar_wait(&full_bar[g], (unsigned)((mm / LG) & 1));
+                mbar_wait_sleepy(&full_bar[g], (unsigned)((mm / LG) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a0 = smem_u32(stages + g * stage_floats);
                 const uint32_t b0 = a0 + (uint32_t)(a_floats * sizeof(float));
@@ -277,7 +286,7 @@ sh_partition_tc_kernel(const ShPartTcParams prm) {
         for (long long it = 0; it < my_tiles; ++it) {
             const int buf = (int)(it & 1);
             if (!idle) qt_next = tile_base(it + 1);
-            mbar_wait(&tfull_bar[buf], (unsigned)((it >> 1) & 1));
+            mbar_wait_sleepy(&tfull_bar[buf], (unsigned)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int cb = 0; cb < Npad && !idle; cb += 32) {
                 uint32_t v[32];
