@@ -338,3 +338,70 @@ def test_filter_set_resampling_control_flow_and_band_limited_result(tmp_path):
     g = make()
     g.load(block_length=256, is_single_precision=True, check_fs=fs_in, is_prevent_logging=True)
     assert g._irs_orig_shape[-1] == taps  # equal rates: untouched
+
+
+def test_result_pool_hands_out_fresh_arrays_and_recycles_dropped_ones(monkeypatch):
+    """`plans.PinnedPool` (the result buffers of the host entry points): an array the caller still
+    holds -- or a view of it -- is never handed out again; a dropped one is.  Without a CUDA device
+    the page-locked allocation fails and the pool degrades to plain `np.empty` arrays."""
+    from retisar_b200 import plans
+
+    class FakePinned:  # stands in for cudaHostAlloc-backed memory (no GPU in the CPU test run)
+        def __init__(self, shape, dtype=np.float32, write_combined=False):
+            self._raw = bytearray(int(np.prod(shape)) * np.dtype(dtype).itemsize)
+            self.array = np.frombuffer(self._raw, dtype=dtype).reshape(shape)
+
+    monkeypatch.setattr(plans, "PinnedBuffer", FakePinned)
+    pool = plans.PinnedPool(max_bytes=3 << 20, min_bytes=1 << 10)
+    shape = (64, 2, 256)  # 128 KB
+    a = pool.take(shape)
+    b = pool.take(shape)
+    assert a.shape == shape and not np.shares_memory(a, b)
+    row = a[3]            # a view keeps the buffer busy
+    addr_a = a.ctypes.data
+    del a
+    c = pool.take(shape)
+    assert c.ctypes.data != addr_a and not np.shares_memory(c, row)
+    del row
+    d = pool.take(shape)  # now the first buffer is free again
+    assert d.ctypes.data == addr_a
+    assert pool.take((4, 2, 8)).flags.owndata  # below min_bytes: a plain array
+    keep = [pool.take((1 << 18,)) for _ in range(8)]  # 1 MB each: beyond max_bytes the pool stops growing
+    assert sum(k.flags.owndata for k in keep) >= 5
+
+    def failing(*a, **k):
+        raise RuntimeError("no CUDA device")
+
+    monkeypatch.setattr(plans, "PinnedBuffer", failing)
+    e = plans.PinnedPool().take(shape)
+    assert e.shape == shape and e.flags.owndata and e.flags.writeable
+
+
+def test_numa_binding_helpers_and_identical_bench_config():
+    import bench
+    from retisar_b200.distributed import _parse_cpulist, bind_to_gpu_numa_node
+
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    info = bind_to_gpu_numa_node(0)  # no GPU here: nothing is changed, nothing raises
+    assert info["node"] is None
+    # both arms of bench.py describe the workload with the very same dictionary
+    assert bench.workload_config("c2", 1024) == bench.workload_config("c2", 1024)
+    assert set(bench.workload_config("c2", 1024)) == {"workload", "streams_per_gpu", "block_length", "fs",
+                                                       "sh_order", "hrir_directions", "crossfade"}
+
+
+def test_staged_reference_is_byte_identical_to_the_reference_tree():
+    """`oracle/stage_ref.py` copies the reference package unmodified (what the GPU box imports)."""
+    import filecmp
+
+    from oracle import stage_ref
+
+    if not os.path.isdir("/root/reference/ReTiSAR"):
+        pytest.skip("the reference tree exists only in the build container")
+    root = stage_ref.stage()
+    assert root and os.path.isfile(os.path.join(root, "STAGED_FROM"))
+    names = [n for n in os.listdir("/root/reference/ReTiSAR") if n.endswith(".py")]
+    assert len(names) >= 20
+    for n in names:
+        assert filecmp.cmp(os.path.join("/root/reference/ReTiSAR", n), os.path.join(root, "ReTiSAR", n), shallow=False), n
