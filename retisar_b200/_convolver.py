@@ -367,6 +367,7 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         self._comp_nm_override = None
         self._hpcf_filter = None
         self._pre_renderer = None
+        self._pre_renderer_irs = None
 
     def __copy__(self):
         """The reference raises here ("not tested", ``_convolver.py:1051-1060``); this returns an
@@ -382,6 +383,10 @@ class AdjustableShConvolver(AdjustableFdConvolver):
             new.set_passthrough(self._is_passthrough)
             if self._sh_cur_order != self._filter._sh_max_order:
                 new.update_sh_processing(self._sh_cur_order)
+            if self._hpcf_filter is not None:
+                new.set_hpcf(self._hpcf_filter)
+            if self._pre_renderer_irs is not None:
+                new.set_pre_renderer(self._pre_renderer_irs)
         return new
 
     def __str__(self):
@@ -544,6 +549,7 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         from ._filter_set import FilterSet
 
         self._pre_renderer = None
+        self._pre_renderer_irs = None
         if arir_irs_td is None:
             return
         if self._plan is None:
@@ -560,6 +566,7 @@ class AdjustableShConvolver(AdjustableFdConvolver):
         pre = OverlapSaveConvolver(fs, self._block_length, n_streams=self._n_streams, device=self._device)
         pre._make_plan(1)  # mono source, J outputs (per-bin GEMM on tensor cores for >= 32 rows)
         self._pre_renderer = pre
+        self._pre_renderer_irs = irs
 
     def _filter_block_pre_rendered(self, source_td, yaw_deg):
         """Mono source block(s) -> pre-renderer (writes the analysis rows into the plan) -> renderer."""

@@ -306,7 +306,10 @@ class PinnedBuffer:
     def close(self):
         if getattr(self, "_ptr", None) is not None and self._ptr.value:
             self.array = None
-            lib.rtb_host_free(self._ptr)
+            try:
+                lib.rtb_host_free(self._ptr)
+            except Exception:  # interpreter shutdown: the library may be gone already
+                pass
             self._ptr = ctypes.c_void_p()
 
     __del__ = close
