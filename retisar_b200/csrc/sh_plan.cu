@@ -44,6 +44,7 @@ struct rtb_sh_plan {
     // 1 024 streams 55.4 -> 62.8 us per block (worse), 10 240 streams 385 -> 380 us: off by default
     bool pdl = false;
     bool mg_enabled = false, mg_forced = false;
+    int n_sm = 148;
     int mg_order = -1, mg_np = 0;
     float4 *d_mg_htab = nullptr;
     ShMgSignal *d_mg_signals = nullptr;
@@ -174,18 +175,21 @@ void launch_render(const rtb_sh_plan *p, const ShRenderParams &prm, cudaStream_t
 #undef RTB_SH_LAUNCH
 }
 
-template <int N2>
+template <int N2, int NW = 4>
 void launch_render_mg_t(const ShRenderMgParams &prm, cudaStream_t st, bool pdl) {
-    const size_t smem = RTB_MG_ACC_SMEM ? sizeof(float2) * 4 * (FftCfg<N2>::EPL / 2) * 4 * 32 : 0;
-    constexpr int per_cta = 4 * FftCfg<N2>::GROUPS;  // one stream per transform group
-    kernel_attrs_once(sh_render_mg_kernel<N2>, 100 * 1024, true);
-    launch_pdl(sh_render_mg_kernel<N2>, dim3((unsigned)((prm.S + per_cta - 1) / per_cta)), dim3(128), smem, st, pdl, prm);
+    const size_t smem = RTB_MG_ACC_SMEM ? sizeof(float2) * NW * (FftCfg<N2>::EPL / 2) * 4 * 32 : 0;
+    constexpr int per_cta = NW * FftCfg<N2>::GROUPS;  // one stream per transform group
+    kernel_attrs_once(sh_render_mg_kernel<N2, NW>, 100 * 1024, true);
+    launch_pdl(sh_render_mg_kernel<N2, NW>, dim3((unsigned)((prm.S + per_cta - 1) / per_cta)), dim3(32 * NW), smem, st, pdl, prm);
 }
 
 void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStream_t st) {
+    // short blocks put 2 or 4 streams on a warp: CTAs of two warps while 4-warp CTAs would not give every
+    // SM two of them
+    const bool narrow = prm.S < 2 * p->n_sm * 4 * (512 / p->N2 > 2 ? 4 : 2);
     switch (p->N2) {
-        case 64: launch_render_mg_t<64>(prm, st, p->pdl); break;
-        case 128: launch_render_mg_t<128>(prm, st, p->pdl); break;
+        case 64: narrow ? launch_render_mg_t<64, 2>(prm, st, p->pdl) : launch_render_mg_t<64>(prm, st, p->pdl); break;
+        case 128: narrow ? launch_render_mg_t<128, 2>(prm, st, p->pdl) : launch_render_mg_t<128>(prm, st, p->pdl); break;
         case 256: launch_render_mg_t<256>(prm, st, p->pdl); break;
         default: launch_render_mg_t<512>(prm, st, p->pdl); break;
     }
@@ -618,6 +622,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     p->h_sig = sig;
     p->h_shm.assign(sh_m, sh_m + K);
     p->mg_enabled = p->P == 1 && p->N2 <= 512;  // every warp-level transform size
+    cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, p->device);
     if (const char *env = getenv("RTB_RENDER_MG")) {
         p->mg_enabled = p->mg_enabled && env[0] != '0';
         p->mg_forced = env[0] == '1';

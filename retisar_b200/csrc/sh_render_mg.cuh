@@ -77,8 +77,10 @@ __device__ __forceinline__ void cfma_conj(float2 &acc, float2 h, float2 x) {
 // One transform group (G lanes: a whole warp for N2 = 256 / 512, half a warp for N2 = 128, a quarter
 // for N2 = 64) renders one stream; the groups of a warp are different streams walking the signal
 // list in lock step, so a CTA covers 4 * GROUPS streams and shares the staged HRIR tile among them.
-template <int N2>
-__global__ void __launch_bounds__(128, RTB_RENDER_MG_MIN_CTAS)
+// NW warps per CTA: 4 (NW * GROUPS streams share the staged HRIR tile), or 2 for small batches of
+// short blocks, where 8 - 16 streams per CTA would leave SMs idle.
+template <int N2, int NW = 4>
+__global__ void __launch_bounds__(32 * NW, RTB_RENDER_MG_MIN_CTAS * (4 / NW))
 sh_render_mg_kernel(const ShRenderMgParams prm) {
     using Cfg = FftCfg<N2>;
     static_assert(!Cfg::BIG, "warp-level transforms only");
@@ -88,9 +90,10 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     constexpr unsigned FULL = 0xffffffffu;
 
     __shared__ __align__(16) float2 s_tw[N2];
-    __shared__ __align__(128) float2 s_buf[4][GROUPS * Cfg::REGION];
+    constexpr int NT = 32 * NW;
+    __shared__ __align__(128) float2 s_buf[NW][GROUPS * Cfg::REGION];
     __shared__ __align__(16) float4 s_h[2][HSIG];
-    __shared__ float2 s_cs[4 * GROUPS][2][RTB_MAX_ORDER + 1];
+    __shared__ float2 s_cs[NW * GROUPS][2][RTB_MAX_ORDER + 1];
     __shared__ ShMgSignal s_sig[RTB_MG_MAX_SIGNALS];  // the signal list: no dependent global load per round
 #if RTB_MG_ACC_SMEM
     extern __shared__ __align__(128) unsigned char dyn_smem[];  // [4 warps][HB][4][32 lanes] float2
@@ -100,8 +103,8 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     const int grp = lane / G, l = lane % G;        // transform group of the lane, lane inside the group
     const int sw = warp * GROUPS + grp;            // stream slot inside the CTA
     // twiddles arrive asynchronously with the first tile (waited for at the top of the first round)
-    for (int i = threadIdx.x; i < N2 / 2; i += 128) cp_async16_ca(&s_tw[2 * i], prm.tw + 2 * i);
-    for (int i = threadIdx.x; i < prm.np * (int)(sizeof(ShMgSignal) / sizeof(int2)); i += 128)
+    for (int i = threadIdx.x; i < N2 / 2; i += NT) cp_async16_ca(&s_tw[2 * i], prm.tw + 2 * i);
+    for (int i = threadIdx.x; i < prm.np * (int)(sizeof(ShMgSignal) / sizeof(int2)); i += NT)
         reinterpret_cast<int2 *>(s_sig)[i] = __ldg(reinterpret_cast<const int2 *>(prm.signals) + i);
     __syncthreads();
 #if RTB_MG_ACC_SMEM
@@ -110,7 +113,7 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
     for (int i = 0; i < HB * 4; ++i) sacc[i * 32] = make_float2(0.f, 0.f);
 #endif
 
-    const int s = blockIdx.x * (4 * GROUPS) + sw;
+    const int s = blockIdx.x * (NW * GROUPS) + sw;
     const bool active = s < prm.S;
     float2 *buf = s_buf[warp] + grp * Cfg::REGION;
     float *zrow = reinterpret_cast<float *>(buf);
@@ -122,8 +125,8 @@ sh_render_mg_kernel(const ShRenderMgParams prm) {
         const float4 *src = prm.htab + (size_t)p * HSIG + threadIdx.x;
         float4 *dst = &s_h[stage][threadIdx.x];
 #pragma unroll
-        for (int i = 0; i < HSIG / 128; ++i) cp_async16_ca(dst + 128 * i, src + 128 * i);
-        if (threadIdx.x < HSIG % 128) cp_async16_ca(dst + (HSIG / 128) * 128, src + (HSIG / 128) * 128);
+        for (int i = 0; i < HSIG / NT; ++i) cp_async16_ca(dst + NT * i, src + NT * i);
+        if (threadIdx.x < HSIG % NT) cp_async16_ca(dst + (HSIG / NT) * NT, src + (HSIG / NT) * NT);
     };
     // rows of the signal -> landing zone [re: prev | cur][im: prev | cur]; lane-contiguous 16-byte chunks
     auto prefetch_z = [&](int p) {
