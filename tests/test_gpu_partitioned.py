@@ -229,3 +229,33 @@ def test_c3_p16_fixed_yaw_equals_reference_pinned_oracle_on_long_block():
             worst = max(worst, err)
             assert err <= TOL, (t, s, err)
     print("c3 P = 16 vs reference-pinned B = 4096 oracle: max abs err", worst)
+
+
+def test_partitioned_tensor_core_path_beyond_one_launch():
+    """More than 128 stream tiles (16 384 streams): the tensor-core partition MAC runs as several
+    launches over stream ranges; probes in the first and in the second launch, ragged last tile."""
+    import torch
+
+    from oracle import sh_chain as oc
+    from retisar_b200 import Convolver, _capi
+
+    S, B, order = 16384 + 200, 64, 4
+    arr, hrir, C = build("em32", order, B, 2 * B, 100, 91)   # P = 2
+    conv = Convolver.create_instance_by_filter_set(hrir, B, [(0, 0)], None, n_streams=S)
+    cfg = arr.get_sh_configuration()
+    conv.prepare_sh_processing(cfg, 0, None, comp_nm=np.ones(((order + 1) ** 2, 1, B + 1), np.complex64))
+    hnm = hrir.get_filter_blocks_nm()
+    probes = [0, 16383, 16384, 16384 + 127, S - 1]
+    oracles = {s: oc.ShPartitionedOracle(cfg.sh_m, cfg.sh_bases_weighted, hnm, B, order) for s in probes}
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(8)
+    idx = torch.as_tensor(probes, device=dev)
+    for t in range(6):
+        x = torch.randn((S, C, B), generator=gen, device=dev) * 0.1
+        yaw = torch.rand((S,), generator=gen, device=dev) * 360.0
+        y = conv.filter_block(x, yaw)
+        assert _capi.RENDER_KERNEL_NAMES[conv._plan.query(_capi.RTB_Q_RENDER_KERNEL)] == "sh_partition_tc_kernel"
+        xs, ys, yaws = x[idx].cpu().numpy(), y[idx].cpu().numpy(), yaw[idx].cpu().numpy()
+        for i, s in enumerate(probes):
+            assert np.abs(ys[i] - oracles[s].filter_block(xs[i], yaws[i])).max() <= TOL, (t, s)
