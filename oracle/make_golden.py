@@ -299,6 +299,44 @@ def golden_compensation(name="compensation_em32_le110"):
     np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), **out)
 
 
+def golden_production_chain(name="chain_em32_n4_b64"):
+    """The reference's production topology run with its own classes end to end
+    (`_run.py:240-338`): mono source -> ARIR pre-renderer (`OverlapSaveConvolver`, mono input
+    broadcast, `_convolver.py:588-591`) -> `AdjustableShConvolver` -> HPCF (`OverlapSaveConvolver`,
+    2 channels).  Pins the folded forms of this repository (`set_pre_renderer`, `set_hpcf`) directly
+    to the unmodified reference."""
+    ref = rh.import_reference()
+    em32 = syn.load_array_grid("em32")
+    order, B, T = 4, 64, 22
+    arr, hrir = _array_and_hrir(em32, order, B, 120, 64, 700)
+    C = len(em32[0])
+    arir_irs = syn.decaying_noise_irs((C, 200), 701)
+    hpcf_irs = syn.decaying_noise_irs((2, 300), 702, scale=0.3)
+    tracker = rh.make_tracker()
+    rend = rh.make_sh_convolver(hrir, arr, B, tracker)
+    arir = ref._convolver.OverlapSaveConvolver(rh.make_multichannel_filter_set(arir_irs, B), B)
+    hpcf = ref._convolver.OverlapSaveConvolver(rh.make_multichannel_filter_set(hpcf_irs, B, is_hpcf=False), B)
+    x = syn.noise_blocks(T, 1, B, 703, scale=0.5)
+    yaws = syn.yaw_walk(T, 704, step=20.0)
+    mid = np.zeros((T, 2, B), dtype=np.float32)
+    out = np.zeros((T, 2, B), dtype=np.float32)
+    for t in range(T):
+        if t == 15:  # the pipeline is paused: every client clears its buffers (`_convolver.py:383-386`)
+            for c in (arir, rend, hpcf):
+                c._clear_buffers()
+        tracker[ref.HeadTracker.DataIndex.AZIM] = float(yaws[t])
+        a = arir.filter_block(x[t].copy())
+        r = rend.filter_block(np.array(a, copy=True))
+        mid[t] = r
+        out[t] = hpcf.filter_block(np.array(r, copy=True))
+    cfg = arr.get_sh_configuration()
+    np.savez_compressed(
+        os.path.join(GOLD, f"{name}.npz"), kind="chain", order=order, B=B, x=x, yaw=yaws, y_renderer=mid, y=out,
+        arir_irs=arir_irs, hpcf_irs=hpcf_irs, sh_m=cfg.sh_m, Yw=cfg.sh_bases_weighted, Hnm=hrir._irs_blocks_nm,
+        rev=np.asarray(rend._sh_m_rev_id), w_in=rend._window_in_td, w_out=rend._window_out_td, clear_at=15)
+    print(name, "max|y|", np.abs(out).max(), "max|renderer|", np.abs(mid).max())
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     extract_grids()
@@ -352,6 +390,8 @@ def main():
     golden_levels("levels_4ch_b256")
     # compensation bookkeeping (row f1)
     golden_compensation()
+    # the production chain ARIR -> renderer -> HPCF with the reference's own classes
+    golden_production_chain()
 
 
 if __name__ == "__main__":

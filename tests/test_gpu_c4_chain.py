@@ -99,3 +99,45 @@ def test_chain_with_folded_pre_renderer_and_fused_hpcf(workload, S, arir_taps, h
     # numpy in, numpy out
     y = rend.filter_block(x[0], yaw[0])
     assert isinstance(y, np.ndarray) and y.shape == (S, 2, B)
+
+
+def test_folded_chain_matches_the_references_own_three_convolvers():
+    """Golden `chain_em32_n4_b64`: mono source -> ARIR pre-renderer -> SH renderer -> HPCF rendered by
+    the UNMODIFIED reference's three convolver objects (`oracle/make_golden.golden_production_chain`).
+    Here: one `AdjustableShConvolver` with the pre-renderer folded into the analysis domain and the
+    HPCF fused into the render kernel, 5 identical streams, pause / clear in the middle."""
+    import torch
+
+    from conftest import load_golden
+    from retisar_b200 import Convolver, FilterSet
+    from retisar_b200 import synthetic as syn
+    from retisar_b200._filter_set import FilterSetMiro
+
+    g = load_golden("chain_em32_n4_b64")
+    B, order, S = int(g["B"]), int(g["order"]), 5
+    az, co, w = syn.load_array_grid("em32")
+    arr = FilterSetMiro.from_arrays(np.zeros((1, len(az), B), np.float32), az, co, w, order, False)
+    arr.load(B, True, is_prevent_logging=True)
+    haz, hco = syn.random_sphere_grid(120, 701)   # as oracle/make_golden._array_and_hrir(seed = 700)
+    hrir = FilterSetMiro.from_arrays(syn.decaying_noise_irs((120, 2, 64), 702), haz, hco, None, order, True)
+    hrir.load(B, True, is_prevent_logging=True)
+    rend = Convolver.create_instance_by_filter_set(hrir, B, [(0, 0)], None, n_streams=S)
+    rend.prepare_sh_processing(arr.get_sh_configuration(), 0, None,
+                               comp_nm=np.ones(((order + 1) ** 2, 1, B + 1), np.complex64))
+    assert np.array_equal(rend._filter.get_filter_blocks_nm(), g["Hnm"])  # same tables as the reference built
+    rend.set_pre_renderer(g["arir_irs"])
+    hp = FilterSet.create_instance_by_type(g["hpcf_irs"], "FIR_MULTICHANNEL")
+    hp.load(block_length=B, is_single_precision=True, is_prevent_logging=True)
+    rend.set_hpcf(hp)
+    dev = torch.device("cuda", 0)
+    worst = 0.0
+    for t in range(g["x"].shape[0]):
+        if t == int(g["clear_at"]):
+            rend._clear_buffers()
+        x = torch.from_numpy(np.repeat(g["x"][t][None], S, axis=0)).to(dev)
+        yaw = torch.full((S,), float(g["yaw"][t]), device=dev)
+        y = rend.filter_block(x, yaw).cpu().numpy()
+        err = float(np.abs(y - g["y"][t][None]).max())
+        worst = max(worst, err)
+        assert err <= TOL, (t, err)
+    print("folded chain vs the reference's three convolvers: max abs err", worst, "peak", np.abs(g["y"]).max())

@@ -142,3 +142,21 @@ def test_fd_oracle_matches_reference(name):
             o.clear()
         y = o.filter_block(g["x"][t], g["yaw"][t])
         assert np.array_equal(y, g["y"][t]), (t, np.abs(y - g["y"][t]).max())
+
+
+def test_oracle_composition_matches_the_references_production_chain():
+    """ARIR pre-renderer -> SH renderer -> HPCF run with the reference's own three convolvers
+    (`oracle/make_golden.golden_production_chain`): the composition of the oracles reproduces it bit
+    for bit, including the pause / clear in the middle."""
+    g = load_golden("chain_em32_n4_b64")
+    B, order = int(g["B"]), int(g["order"])
+    arir = oc.OlsOracle(oc.filter_blocks_fd(oc.zero_pad(g["arir_irs"][None], B), B), B)
+    hpcf = oc.OlsOracle(oc.filter_blocks_fd(oc.zero_pad(g["hpcf_irs"][None], B), B), B)
+    rend = oc.ShOracle(g["sh_m"], g["Yw"], g["Hnm"], B, order)
+    for t in range(g["x"].shape[0]):
+        if t == int(g["clear_at"]):
+            for o in (arir, rend, hpcf):
+                o.clear()
+        r = rend.filter_block(arir.filter_block(g["x"][t]), float(g["yaw"][t]))
+        assert np.array_equal(r, g["y_renderer"][t]), t
+        assert np.array_equal(hpcf.filter_block(r), g["y"][t]), t
