@@ -124,7 +124,8 @@ def test_folded_chain_matches_the_references_own_three_convolvers():
     rend = Convolver.create_instance_by_filter_set(hrir, B, [(0, 0)], None, n_streams=S)
     rend.prepare_sh_processing(arr.get_sh_configuration(), 0, None,
                                comp_nm=np.ones(((order + 1) ** 2, 1, B + 1), np.complex64))
-    assert np.array_equal(rend._filter.get_filter_blocks_nm(), g["Hnm"])  # same tables as the reference built
+    # same tables as the reference built (to the last bits: the host BLAS of the box may order the sums differently)
+    assert np.abs(rend._filter.get_filter_blocks_nm() - g["Hnm"]).max() <= 1e-6 * np.abs(g["Hnm"]).max()
     rend.set_pre_renderer(g["arir_irs"])
     hp = FilterSet.create_instance_by_type(g["hpcf_irs"], "FIR_MULTICHANNEL")
     hp.load(block_length=B, is_single_precision=True, is_prevent_logging=True)
