@@ -381,6 +381,7 @@ def run_gpu_arm(args):
     flush = torch.empty(int(256e6) // 4, device=dev, dtype=torch.float32)
     rig = Rig(tb, S, dev, 1234 + rank)
     plan, conv = rig.plan, rig.conv
+    rig_stream = rig.stream
 
     # ---- device-resident throughput: W warm-up, then exactly K steps between barriers
     rig.run(W)
@@ -539,6 +540,51 @@ def run_gpu_arm(args):
                 "filter_block_host_p99_ms": float(np.percentile(host_lat, 99)),
                 "note": "one stream, block latency; filter_block_host = wall time of the synchronous "
                         "reference-shaped call with a [32,256] numpy block (H2D + 2 kernels + D2H)"}
+            # BASELINE config 3: order 8, 4096-tap HRIR as 16 partitions (extension a-X), 4 096 streams
+            from retisar_b200 import config as rcfg
+
+            rcfg.IS_SH_TRANSFORM_ON_DEVICE = True  # 2 702 directions x 16 partitions: set-up on the tensor cores
+            try:
+                ms3, p3, _ = quick("c3", 4096, 30, 100, 9)
+            finally:
+                rcfg.IS_SH_TRANSFORM_ON_DEVICE = False
+            extras["c3_partitioned"] = {
+                "workload": "c3: " + wl.CONFIGS["c3"]["desc"], "streams_per_gpu": 4096, "ms_per_step": ms3,
+                "value": 4096 / (ms3 * 1e-3) / block_rate, "unit": UNIT, "p99_block_latency_ms": p3["p99"],
+                "steps": 30, "latency_steps": 100,
+                "note": "partition MAC on tcgen05 (sh_partition_tc_kernel); SH transform of the HRIR set on the device"}
+            # BASELINE config 4 as the reference chains it in production: mono source -> 434-channel ARIR
+            # (4096 taps) -> renderer (order 12, 64-sample blocks) -> HPCF (1024 taps), folded into one renderer
+            tb4 = wl.sh_tables("c4", hrir_dirs=HRIR_DIRS)
+            from retisar_b200 import FilterSet
+            from retisar_b200 import synthetic as syn
+
+            rend4 = wl.make_renderer(tb4, 1024, device=dev.index)
+            rend4.set_pre_renderer(syn.decaying_noise_irs((tb4["C"], 4096), 40))
+            hp4 = FilterSet.create_instance_by_type(syn.decaying_noise_irs((2, 1024), 41, scale=0.3), "FIR_MULTICHANNEL")
+            hp4.load(block_length=tb4["B"], is_single_precision=True, is_prevent_logging=True)
+            rend4.set_hpcf(hp4)
+            x4 = torch.randn((16, 1024, 1, tb4["B"]), device=dev) * 0.5
+            y4 = torch.rand((16, 1024), device=dev) * 360.0
+            for i in range(80):
+                rend4.filter_block(x4[i % 16], y4[i % 16])
+            torch.cuda.synchronize(dev)
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(rig_stream)
+            for i in range(100):
+                rend4.filter_block(x4[i % 16], y4[i % 16])
+            eb.record(rig_stream)
+            torch.cuda.synchronize(dev)
+            ms4 = ea.elapsed_time(eb) / 100
+            extras["c4_chain"] = {
+                "workload": "c4 production chain: mono source -> 434-ch ARIR pre-renderer (4096 taps, 64 partitions) -> "
+                            "SH renderer (order 12, 64-sample blocks) -> HPCF (1024 taps, 16 partitions)",
+                "streams_per_gpu": 1024, "ms_per_step": ms4, "block_period_ms": 1e3 * tb4["B"] / wl.FS,
+                "value": 1024 / (ms4 * 1e-3) / (wl.FS / tb4["B"]), "unit": "realtime_streams @48kHz/64-blk",
+                "steps": 100,
+                "note": "ARIR folded into the analysis domain (set_pre_renderer), HPCF fused into the render kernel "
+                        "(set_hpcf); the three separate convolvers take 0.449 ms (profiles/r02_c4_chain_*)"}
+            del rend4, x4, y4
             extras["fdl"] = {
                 "target": ">= 60 % of the measured HBM peak on the FDL kernel (north star)",
                 "taps4096_b256": measure_fdl(dev, peaks, 16384, 4096, 256),
