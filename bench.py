@@ -18,6 +18,9 @@ with their own head yaw.  One JSON line is printed by rank 0:
              (the reference's own criterion "no dropouts", `_run_benchmark.py:311-321`)
   fdl        roofline of the FDL kernel `ols_fdl_kernel` (north-star target: >= 60 % of HBM)
   scaling_c5 BASELINE config 5 (order 8, 8192 streams per GPU) measured in the same run
+  c3_partitioned / c4_chain / c1_single_stream
+             BASELINE configs 3 (16-partition HRIR, 4096 streams), 4 (production chain ARIR ->
+             renderer -> HPCF, 1024 streams) and 1 (one stream) measured in the same run
   cpu_baseline / --impl reference
              the UNMODIFIED reference's `AdjustableShConvolver.filter_block` (staged into
              oracle/_ref by build(); kind "reference") on the host cores, one process per core;
