@@ -33,6 +33,8 @@ struct FdParams {
     const float2 *tw;
     const float *win_in, *win_out;
     float *out;                // [S][2][B]
+    float2 *spec;              // [S][NS][Fp] scaled source spectra (split launch: head kernel -> queue kernel)
+    int *dir_cur;              // [S][NS] direction index of this block (split launch)
     int S, NS, P, Fp, n_dirs, head_cur, head_last, crossfade, last_valid, passthrough;
     float tracker_dir, inv_ns;
 };
@@ -49,8 +51,12 @@ __device__ __forceinline__ int direction_index(float yaw_deg, float tracker_dir,
     return k == 0 ? 0 : n_dirs - k;
 }
 
-template <int N2>
-__global__ void __launch_bounds__(FftCfg<N2>::THREADS)
+// PB = partitions whose loads are requested together, MINB = resident CTAs per SM the register
+// allocation is limited to (two shapes are launched, see fd_dense below)
+// HEAD_ONLY: only partition 0 (the queue heads, which stay in registers) is computed here and the
+// scaled source spectra + direction indices are left for fd_queue_kernel
+template <int N2, int PB, int MINB, bool HEAD_ONLY = false>
+__global__ void __launch_bounds__(FftCfg<N2>::THREADS, MINB)
 fd_render_kernel(const FdParams prm) {
     using Cfg = FftCfg<N2>;
     constexpr int G = Cfg::G, EPL = Cfg::EPL, HB = EPL / 2, GROUPS = Cfg::GROUPS, B = N2 / 2;
@@ -131,6 +137,11 @@ fd_render_kernel(const FdParams prm) {
             prm.dir_last_out[(size_t)s * NS + s0] = dc0;
             if (has1) prm.dir_last_out[(size_t)s * NS + s0 + 1] = dc1;
         }
+        if (HEAD_ONLY && (BIG ? threadIdx.x == 0 : lane == 0)) {
+            prm.dir_cur[(size_t)s * NS + s0] = dc0;
+            if (has1) prm.dir_cur[(size_t)s * NS + s0 + 1] = dc1;
+        }
+        const int Pend = HEAD_ONLY ? 1 : prm.P;
         const bool use_last = do_last && prm.last_valid;
         const size_t dstride = (size_t)prm.P * 2 * Fp;
         // Bin slot outermost, partitions in batches of PB: the filter spectra (4 directions x 2 ears)
@@ -138,7 +149,6 @@ fd_render_kernel(const FdParams prm) {
         // has 12 * PB loads in flight (the first version walked partition by partition and waited for
         // every load where it was issued: ncu 44 long-scoreboard stall cycles per issue, issue-active
         // 0.04, 0.71 ms for 4 096 streams x 2 sources x 8 partitions).
-        constexpr int PB = 4;
         const float2 *hd[4] = {prm.hfd + dc0 * dstride, prm.hfd + dc1 * dstride,
                                prm.hfd + dl0 * dstride, prm.hfd + dl1 * dstride};
 #pragma unroll
@@ -147,12 +157,17 @@ fd_render_kernel(const FdParams prm) {
             const bool own = (u < HB) || (l == 0);
             const float2 a0 = make_float2(X0[u].x * prm.inv_ns, X0[u].y * prm.inv_ns);
             const float2 a1 = make_float2(X1[u].x * prm.inv_ns, X1[u].y * prm.inv_ns);
-            for (int p0 = 0; p0 < prm.P; p0 += PB) {
+            if (HEAD_ONLY && own && grp == 0) {
+                float2 *sp = prm.spec + ((size_t)s * NS + s0) * Fp + f;
+                sp[0] = a0;
+                if (has1) sp[Fp] = a1;
+            }
+            for (int p0 = 0; p0 < Pend; p0 += PB) {
                 float2 h[PB][4][2], q[PB][4];
                 float2 *qp[PB][2];
 #pragma unroll
                 for (int i = 0; i < PB; ++i) {
-                    const int p = min(p0 + i, prm.P - 1);  // clamped: surplus batch entries are not used
+                    const int p = min(p0 + i, Pend - 1);  // clamped: surplus batch entries are not used
                     qp[i][0] = qc + (size_t)((prm.head_cur + p) % prm.P) * 2 * Fp + f;
                     qp[i][1] = ql + (size_t)((prm.head_last + p) % prm.P) * 2 * Fp + f;
 #pragma unroll
@@ -163,7 +178,7 @@ fd_render_kernel(const FdParams prm) {
                             h[i][d][e] = need ? __ldg(hd[d] + (size_t)p * 2 * Fp + (size_t)e * Fp + f)
                                               : make_float2(0.f, 0.f);
                         }
-                    const bool rmw = own && grp == 0 && p0 + i > 0 && p0 + i < prm.P;
+                    const bool rmw = own && grp == 0 && p0 + i > 0 && p0 + i < Pend;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         q[i][e] = rmw ? qp[i][0][(size_t)e * Fp] : make_float2(0.f, 0.f);
@@ -173,7 +188,7 @@ fd_render_kernel(const FdParams prm) {
 #pragma unroll
                 for (int i = 0; i < PB; ++i) {
                     const int p = p0 + i;
-                    if (p >= prm.P) break;
+                    if (p >= Pend) break;
                     float2 c[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
@@ -201,7 +216,8 @@ fd_render_kernel(const FdParams prm) {
     }
     // the heads leave the queues
     fft_sync<N2>();
-    if (grp == 0) {
+    // (split launch: the consumed slots stay as they are; the next block's queue kernel overwrites them)
+    if (!HEAD_ONLY && grp == 0) {
 #pragma unroll
         for (int u = 0; u <= HB; ++u) {
             const int f = (u < HB) ? (l + G * u) : B;
@@ -219,6 +235,99 @@ fd_render_kernel(const FdParams prm) {
                     prm.out + (size_t)s * 2 * B);
 }
 
+// Split launch, second kernel: the partitions 1 .. P-1 of both output-side queues,
+//   q[(head + p) % P][ear][f] += sum_src H[dir_src][p][ear][f] * A_src[f],
+// as a streaming read-modify-write: one thread owns two adjacent bins (one float4) of one stream and
+// walks the partitions with the source spectra in registers; the filter spectra come from L2 (the
+// whole table is 360 x P x 2 x Fp x 8 B).  Every queue byte is read and written once per block
+// regardless of the number of sources (the fused kernel passes over the queues once per source pair).
+// The slot of partition P-1 is the head the previous block consumed: it is overwritten, not
+// accumulated into, so nobody has to clear a consumed head (saves one write and one read of a slot
+// per queue and block; the plan clears the slot when a block of another launch variant follows).
+// NST = number of sources kept in registers (0: any number, spectra re-read per partition).
+#ifndef RTB_FD_HEAD_MINB
+#define RTB_FD_HEAD_MINB 3   // resident CTAs per SM of the head kernel of the split launch (164 registers)
+#endif
+#ifndef RTB_FDQ_QB
+#define RTB_FDQ_QB 2
+#endif
+#ifndef RTB_FDQ_MINB
+#define RTB_FDQ_MINB 1
+#endif
+template <int NST>
+__global__ void __launch_bounds__(128, RTB_FDQ_MINB)
+fd_queue_kernel(const FdParams prm) {
+    const int half = prm.Fp / 2;  // float4 per spectrum row
+    const long long item = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (item >= (long long)prm.S * half) return;
+    const int s = (int)(item / half), i = (int)(item % half);
+    const int NS = prm.NS, Fp = prm.Fp, P = prm.P;
+    const bool do_last = prm.crossfade != 0, use_last = do_last && prm.last_valid;
+    const size_t dstride = (size_t)P * 2 * Fp;
+    constexpr int NR = NST > 0 ? NST : 1;
+    float4 a[NR];
+    const float4 *hc[NR], *hl[NR];
+    const float4 *spec = reinterpret_cast<const float4 *>(prm.spec + (size_t)s * NS * Fp) + i;
+    if (NST > 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            a[k] = spec[(size_t)k * half];
+            hc[k] = reinterpret_cast<const float4 *>(prm.hfd + prm.dir_cur[(size_t)s * NS + k] * dstride) + i;
+            hl[k] = reinterpret_cast<const float4 *>(prm.hfd + prm.dir_last_in[(size_t)s * NS + k] * dstride) + i;
+        }
+    }
+    float4 *qc = reinterpret_cast<float4 *>(prm.qcur + (size_t)s * P * 2 * Fp) + i;
+    float4 *ql = reinterpret_cast<float4 *>(prm.qlast + (size_t)s * P * 2 * Fp) + i;
+    auto mac2 = [](float4 &c, const float4 h, const float4 x) {  // two complex products
+        c.x = fmaf(h.x, x.x, c.x); c.x = fmaf(-h.y, x.y, c.x);
+        c.y = fmaf(h.x, x.y, c.y); c.y = fmaf(h.y, x.x, c.y);
+        c.z = fmaf(h.z, x.z, c.z); c.z = fmaf(-h.w, x.w, c.z);
+        c.w = fmaf(h.z, x.w, c.w); c.w = fmaf(h.w, x.z, c.w);
+    };
+    // (partition, ear) rows, QB at a time so that QB * (2 + 2 * NST) 16-byte loads are in flight
+    constexpr int QB = RTB_FDQ_QB;
+    const int rows = (P - 1) * 2;
+    for (int r0 = 0; r0 < rows; r0 += QB) {
+        float4 vq[QB][2], c[QB][2];
+        float4 *pq[QB][2];
+#pragma unroll
+        for (int j = 0; j < QB; ++j) {
+            const int r = min(r0 + j, rows - 1), p = 1 + (r >> 1), e = r & 1;
+            pq[j][0] = qc + ((size_t)((prm.head_cur + p) % P) * 2 + e) * half;
+            pq[j][1] = ql + ((size_t)((prm.head_last + p) % P) * 2 + e) * half;
+            const bool fresh = p == P - 1;
+            vq[j][0] = fresh ? make_float4(0.f, 0.f, 0.f, 0.f) : *pq[j][0];
+            vq[j][1] = (use_last && !fresh) ? *pq[j][1] : make_float4(0.f, 0.f, 0.f, 0.f);
+            c[j][0] = c[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const size_t ho = ((size_t)p * 2 + e) * half;
+            if (NST > 0) {
+#pragma unroll
+                for (int k = 0; k < NR; ++k) {
+                    mac2(c[j][0], __ldg(hc[k] + ho), a[k]);
+                    if (use_last) mac2(c[j][1], __ldg(hl[k] + ho), a[k]);
+                }
+            } else {
+                for (int k = 0; k < NS; ++k) {
+                    const float4 ak = spec[(size_t)k * half];
+                    const float4 *hck = reinterpret_cast<const float4 *>(prm.hfd + prm.dir_cur[(size_t)s * NS + k] * dstride) + i;
+                    mac2(c[j][0], __ldg(hck + ho), ak);
+                    if (use_last) {
+                        const float4 *hlk = reinterpret_cast<const float4 *>(prm.hfd + prm.dir_last_in[(size_t)s * NS + k] * dstride) + i;
+                        mac2(c[j][1], __ldg(hlk + ho), ak);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < QB; ++j) {
+            if (r0 + j >= rows) break;
+            *pq[j][0] = make_float4(vq[j][0].x + c[j][0].x, vq[j][0].y + c[j][0].y, vq[j][0].z + c[j][0].z, vq[j][0].w + c[j][0].w);
+            if (use_last || (do_last && r0 + j >= rows - 2))  // rows - 2, rows - 1: partition P-1
+                *pq[j][1] = make_float4(vq[j][1].x + c[j][1].x, vq[j][1].y + c[j][1].y, vq[j][1].z + c[j][1].z, vq[j][1].w + c[j][1].w);
+        }
+    }
+}
+
 }  // namespace
 
 struct rtb_fd_plan {
@@ -229,6 +338,8 @@ struct rtb_fd_plan {
     float2 *d_hfd = nullptr;              // [n_dirs][P][2][Fp]
     float2 *d_qcur = nullptr, *d_qlast = nullptr;
     int *d_dirlast = nullptr;             // [2][S][NS]
+    float2 *d_spec = nullptr;             // [S][NS][Fp] (split launch)
+    int *d_dircur = nullptr;              // [S][NS]     (split launch)
     float *d_src = nullptr;               // [NS]
     float2 *d_tw = nullptr;
     float *d_win_in = nullptr, *d_win_out = nullptr;
@@ -238,6 +349,9 @@ struct rtb_fd_plan {
     bool crossfade = true, passthrough = false, last_valid = false;
     float tracker_dir = 1.f;
     long long launches = 0;
+    int n_sm = 148, dense_forced = -1;    // RTB_FD_DENSE=0/1 forces one kernel shape (A/B runs)
+    int split_forced = -1;                // RTB_FD_SPLIT=0/1 forces the fused / the two-kernel launch
+    int stale_cur = -1, stale_last = -1;  // consumed head slots a split block left uncleared
 };
 
 namespace {
@@ -270,12 +384,18 @@ int rtb_fd_plan_create(rtb_fd_plan **out, int device, int n_streams, int block_l
     p->device = device; p->S = n_streams; p->B = block_length; p->NS = n_sources; p->n_dirs = n_dirs;
     p->P = n_partitions; p->F = block_length + 1; p->Fp = (p->F + 3) / 4 * 4; p->N2 = 2 * block_length;
     DeviceGuard guard(device);
+    cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (const char *env = getenv("RTB_FD_DENSE")) p->dense_forced = env[0] != '0';
+    if (const char *env = getenv("RTB_FD_SPLIT")) p->split_forced = env[0] != '0';
     cudaError_t err = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_xstate, sizeof(float) * 2 * fd_state_elems(p));
     if (err == cudaSuccess) err = cudaMalloc(&p->d_hfd, sizeof(float2) * (size_t)n_dirs * p->P * 2 * p->Fp);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_qcur, sizeof(float2) * fd_queue_elems(p));
     if (err == cudaSuccess) err = cudaMalloc(&p->d_qlast, sizeof(float2) * fd_queue_elems(p));
     if (err == cudaSuccess) err = cudaMalloc(&p->d_dirlast, sizeof(int) * 2 * (size_t)p->S * p->NS);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_spec, sizeof(float2) * (size_t)p->S * p->NS * p->Fp);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_dircur, sizeof(int) * (size_t)p->S * p->NS);
+    if (err == cudaSuccess) err = cudaMemset(p->d_spec, 0, sizeof(float2) * (size_t)p->S * p->NS * p->Fp);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_src, sizeof(float) * p->NS);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_tw, sizeof(float2) * p->N2);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_win_in, sizeof(float) * p->B);
@@ -354,6 +474,7 @@ int rtb_fd_plan_set_crossfade(rtb_fd_plan *p, int on) {
         RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * fd_queue_elems(p)));
         RTB_CUDA(cudaDeviceSynchronize());
         p->last_valid = false;
+        p->stale_last = -1;
     }
     return RTB_OK;
 }
@@ -366,6 +487,7 @@ int rtb_fd_plan_reset(rtb_fd_plan *p) {
     RTB_CUDA(cudaMemset(p->d_qcur, 0, sizeof(float2) * fd_queue_elems(p)));
     RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * fd_queue_elems(p)));
     RTB_CUDA(cudaDeviceSynchronize());
+    p->stale_cur = p->stale_last = -1;
     return RTB_OK;
 }
 
@@ -390,9 +512,52 @@ int rtb_fd_process_block(rtb_fd_plan *p, const float *d_in, const float *d_yaw_d
     prm.crossfade = p->crossfade ? 1 : 0; prm.last_valid = p->last_valid ? 1 : 0;
     prm.passthrough = p->passthrough ? 1 : 0;
     prm.tracker_dir = p->tracker_dir; prm.inv_ns = 1.0f / (float)p->NS;
-#define RTB_FD_LAUNCH(N) fft_kernel_launch<N>(fd_render_kernel<N>, prm, p->S, st, 0, 4)
+    prm.spec = p->d_spec; prm.dir_cur = p->d_dircur;
+    // Two shapes of the same kernel (4 096 streams x 2 sources x 8 partitions at B = 256, one B200):
+    //   3 partitions per load batch, registers unlimited (243, 2 CTAs/SM):
+    //       0.0486 ms @1024, 0.104 @2048, 0.154 @3072, 0.202 @4096, 0.364 @8192 streams
+    //   2 partitions per batch, 128 registers (4 CTAs/SM, 200 B stack):
+    //       0.0647 ms @1024, 0.094 @2048, 0.159 @3072, 0.182 @4096, 0.351 @8192
+    // (4 per batch, the first version: 255 registers + spill, 0.348 ms @4096; 1 per batch 0.285 ms;
+    // 8 per batch 0.72 ms.)  The dense shape pays off once most SMs hold their four CTAs.
+    const bool dense = p->dense_forced >= 0 ? p->dense_forced != 0
+                                            : (p->N2 <= 512 && (long long)(p->S + 3) / 4 * 10 >= 34LL * p->n_sm);
+    // Split launch (default whenever there are partitions behind the head): head kernel + streaming
+    // queue kernel.  Same workload as above, fused -> split: 0.0329 -> 0.0185 ms @256 streams,
+    // 0.0492 -> 0.0376 @1024, 0.182 -> 0.124 @4096, 0.350 -> 0.227 @8192; 32 partitions @4096
+    // 0.894 -> 0.499 ms.  (Queue kernel 2 rows per batch / 94 registers; 4 rows 0.147 vs 0.137 ms,
+    // 8 rows 0.159; head kernel 3 CTAs per SM 0.124 vs 0.127 with 2.)
+    const bool split = !p->passthrough && p->P > 1 &&
+                       (p->split_forced >= 0 ? p->split_forced != 0 : true);
+    if (!split) {  // the fused kernel accumulates into every slot: clear what a split block left behind
+        const size_t pitch = sizeof(float2) * (size_t)p->P * 2 * p->Fp, width = sizeof(float2) * 2 * p->Fp;
+        if (p->stale_cur >= 0)
+            RTB_CUDA(cudaMemset2DAsync(p->d_qcur + (size_t)p->stale_cur * 2 * p->Fp, pitch, 0, width, p->S, st));
+        if (p->stale_last >= 0)
+            RTB_CUDA(cudaMemset2DAsync(p->d_qlast + (size_t)p->stale_last * 2 * p->Fp, pitch, 0, width, p->S, st));
+        p->stale_cur = p->stale_last = -1;
+    } else {
+        p->stale_cur = p->head_cur;
+        if (p->crossfade) p->stale_last = p->head_last;
+    }
+#define RTB_FD_LAUNCH(N)                                                                             \
+    if (split) fft_kernel_launch<N>(fd_render_kernel<N, 1, FftCfg<N>::BIG ? 1 : RTB_FD_HEAD_MINB, true>, prm, p->S, st, 0, 4); \
+    else if (FftCfg<N>::BIG || !dense) fft_kernel_launch<N>(fd_render_kernel<N, 3, 1>, prm, p->S, st, 0, 4); \
+    else fft_kernel_launch<N>(fd_render_kernel<N, 2, FftCfg<N>::BIG ? 1 : 4>, prm, p->S, st, 0, 4);
     RTB_DISPATCH_N2(p->N2, RTB_FD_LAUNCH)
 #undef RTB_FD_LAUNCH
+    if (split) {
+        const long long items = (long long)p->S * (p->Fp / 2);
+        const unsigned grid = (unsigned)((items + 127) / 128);
+        switch (p->NS) {
+            case 1: fd_queue_kernel<1><<<grid, 128, 0, st>>>(prm); break;
+            case 2: fd_queue_kernel<2><<<grid, 128, 0, st>>>(prm); break;
+            case 3: fd_queue_kernel<3><<<grid, 128, 0, st>>>(prm); break;
+            case 4: fd_queue_kernel<4><<<grid, 128, 0, st>>>(prm); break;
+            default: fd_queue_kernel<0><<<grid, 128, 0, st>>>(prm); break;
+        }
+        p->launches++;
+    }
     p->launches++;
     p->par ^= 1;
     p->head_cur = (p->head_cur + 1) % p->P;
@@ -443,7 +608,7 @@ int rtb_fd_plan_destroy(rtb_fd_plan *p) {
     DeviceGuard guard(p->device);
     cudaFree(p->d_xstate); cudaFree(p->d_hfd); cudaFree(p->d_qcur); cudaFree(p->d_qlast);
     cudaFree(p->d_dirlast); cudaFree(p->d_src); cudaFree(p->d_tw); cudaFree(p->d_win_in); cudaFree(p->d_win_out);
-    cudaFree(p->d_in); cudaFree(p->d_yaw); cudaFree(p->d_out);
+    cudaFree(p->d_in); cudaFree(p->d_yaw); cudaFree(p->d_out); cudaFree(p->d_spec); cudaFree(p->d_dircur);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
     return RTB_OK;

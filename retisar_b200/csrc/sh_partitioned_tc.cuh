@@ -336,18 +336,21 @@ sh_partition_tc_kernel(const ShPartTcParams prm) {
 // zspecT[bin][signal][stream].  One warp per stream, 8 streams per CTA; the spectra of a signal
 // round are transposed through shared memory so that a bin row of the 8 streams leaves as 64
 // contiguous bytes.
+#ifndef RTB_SPEC_NW
+#define RTB_SPEC_NW 8   // streams (warps) per CTA of the spectra kernel
+#endif
 template <int N2>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * RTB_SPEC_NW)
 sh_spectra_soa_kernel(const ShPartParams prm, float2 *__restrict__ zspecT, long long Spad) {
     using Cfg = FftCfg<N2>;
     constexpr int G = Cfg::G, EPL = Cfg::EPL, GROUPS = Cfg::GROUPS, B = N2 / 2;
-    constexpr int NW = 8, ROWS = GROUPS * N2, RS = NW + 1;   // tile rows = (signal of the round, bin), padded
+    constexpr int NW = RTB_SPEC_NW, ROWS = GROUPS * N2, RS = NW + 1;   // tile rows = (signal of the round, bin), padded
     __shared__ float2 s_tw[N2];
     __shared__ __align__(128) float2 s_buf[NW][GROUPS * Cfg::REGION];
     extern __shared__ __align__(16) float2 s_t[];   // [ROWS][RS] transposition tile (dynamic: > 48 KB in total)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, l = lane % G;
-    for (int i = threadIdx.x; i < N2; i += 256) s_tw[i] = prm.tw[i];
+    for (int i = threadIdx.x; i < N2; i += 32 * NW) s_tw[i] = prm.tw[i];
     __syncthreads();
     const int s0 = blockIdx.x * NW, s = s0 + warp;
     const bool active = s < prm.S;
@@ -393,7 +396,7 @@ sh_spectra_soa_kernel(const ShPartParams prm, float2 *__restrict__ zspecT, long 
 #pragma unroll
         for (int u = 0; u < EPL; ++u) s_t[(grp * N2 + l + G * u) * RS + warp] = X[u];
         __syncthreads();
-        for (int i = threadIdx.x; i < ROWS * NW; i += 256) {
+        for (int i = threadIdx.x; i < ROWS * NW; i += 32 * NW) {
             const int row = i / NW, w = i % NW;
             const int pg = row / N2, bin = row % N2;
             if (p0 + pg < np && s0 + w < prm.S)

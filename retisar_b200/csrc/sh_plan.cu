@@ -951,12 +951,12 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         const dim3 gmac2((unsigned)((p->F + 31) / 32), (unsigned)((count + 2 * RTB_MAC_WARPS - 1) / (2 * RTB_MAC_WARPS)));
         if (p->pt_enabled) {  // tensor-core partition MAC on the stream-minor layout (whole plan: s0 == 0)
             p->last_render_kernel = 6;
-            const unsigned gs = (unsigned)((count + 7) / 8);
+            const unsigned gs = (unsigned)((count + RTB_SPEC_NW - 1) / RTB_SPEC_NW);
 #define RTB_PT_LAUNCH(N)                                                                                     \
     {                                                                                                        \
-        const size_t sm = sizeof(float2) * (size_t)(FftCfg<N>::GROUPS * N) * 9;                              \
+        const size_t sm = sizeof(float2) * (size_t)(FftCfg<N>::GROUPS * N) * (RTB_SPEC_NW + 1);              \
         kernel_attrs_once(sh_spectra_soa_kernel<N>, 100 * 1024, true);                                       \
-        sh_spectra_soa_kernel<N><<<gs, 256, sm, st>>>(prm, p->d_zspec, p->pt_Spad);                          \
+        sh_spectra_soa_kernel<N><<<gs, 32 * RTB_SPEC_NW, sm, st>>>(prm, p->d_zspec, p->pt_Spad);             \
     }
             switch (p->N2) {
                 case 64: RTB_PT_LAUNCH(64) break;

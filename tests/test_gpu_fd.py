@@ -21,11 +21,20 @@ def filter_set(g):
     return fs
 
 
+# the launch variants of the renderer: head kernel + queue kernel (default), and the fused kernel in
+# its two shapes (RTB_FD_SPLIT / RTB_FD_DENSE are read when the plan is created)
+FD_LAUNCHES = {"split": {"RTB_FD_SPLIT": "1"}, "fused": {"RTB_FD_SPLIT": "0", "RTB_FD_DENSE": "0"},
+               "fused_dense": {"RTB_FD_SPLIT": "0", "RTB_FD_DENSE": "1"}}
+
+
+@pytest.mark.parametrize("launch", list(FD_LAUNCHES))
 @pytest.mark.parametrize("name", FD_CASES)
-def test_fd_convolver_matches_reference_golden(name):
+def test_fd_convolver_matches_reference_golden(name, launch, monkeypatch):
     from retisar_b200 import Convolver, HeadTracker
     from retisar_b200._convolver import AdjustableFdConvolver
 
+    for k, v in FD_LAUNCHES[launch].items():
+        monkeypatch.setenv(k, v)
     g = load_golden(name)
     B = int(g["B"])
     tracker = HeadTracker.create_shared_array()
@@ -50,19 +59,38 @@ def test_fd_convolver_matches_reference_golden(name):
     check_regression_bar(float(worst), float(np.abs(g["y"]).max()), name)
 
 
-def test_fd_batched_streams_vs_oracle():
+@pytest.mark.parametrize("launch", list(FD_LAUNCHES))
+@pytest.mark.parametrize("n_src", [2, 5])  # 5 sources: three source pairs, the queue kernel's generic path
+def test_fd_batched_streams_vs_oracle(n_src, launch, monkeypatch):
     from oracle import sh_chain as oc
     from retisar_b200 import Convolver
 
+    for k, v in FD_LAUNCHES[launch].items():
+        monkeypatch.setenv(k, v)
     g = load_golden("fd_brir_2src_b128")
-    B, S, T = int(g["B"]), 5, 8
+    B, S, T = int(g["B"]), 5, 14
     fs = filter_set(g)
     sources = [tuple(map(float, s)) for s in g["sources"]]
+    if n_src > 2:
+        sources = sources + [(75.0, 0.0), (-120.0, 0.0), (200.0, 0.0)][: n_src - 2]
     conv = Convolver.create_instance_by_filter_set(fs, B, sources, None, n_streams=S)
-    oracles = [oc.FdOracle(fs._irs_blocks_fd, B, g["sources"], bool(g["is_hrir"])) for _ in range(S)]
+    oracles = [oc.FdOracle(fs._irs_blocks_fd, B, np.array(sources), bool(g["is_hrir"])) for _ in range(S)]
     rng = np.random.default_rng(4)
+    # state changes between blocks: the split launch leaves consumed queue heads for the next block
+    # to overwrite, so every change of launch variant (passthrough) or of the queues in use
+    # (cross-fade) in mid-stream has to keep the queues consistent
+    events = {4: ("passthrough", True), 5: ("passthrough", False), 7: ("crossfade", False),
+              9: ("crossfade", True), 11: ("passthrough", True), 12: ("passthrough", False)}
     for t in range(T):
-        x = (rng.standard_normal((S, 2, B)) * 0.1).astype(np.float32)
+        if t in events:
+            what, state = events[t]
+            getattr(conv, "set_" + what)(state)
+            for o in oracles:
+                if what == "crossfade":
+                    o.set_crossfade(state)
+                else:
+                    o.is_passthrough = state
+        x = (rng.standard_normal((S, n_src, B)) * 0.1).astype(np.float32)
         yaw = rng.uniform(-500, 500, S).astype(np.float32)
         y = conv.filter_block(x, yaw)
         ref = np.stack([o.filter_block(x[s], yaw[s]) for s, o in enumerate(oracles)])

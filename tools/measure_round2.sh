@@ -171,6 +171,10 @@ final)
   tail -3 $o/final_bench.err
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/final_launches_bench_c2.csv \
       python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > $o/final_ncu_list.log 2>&1
+  timeout 200 python tools/profile_fd.py --streams 4096 --steps 200 > $o/final_fd_split_s4096.json 2>> $o/final_bench.err
+  timeout 200 python tools/profile_fd.py --streams 4096 --taps 8192 --steps 100 > $o/final_fd_split_s4096_p32.json 2>> $o/final_bench.err
+  RTB_FD_SPLIT=0 timeout 200 python tools/profile_fd.py --streams 4096 --steps 200 > $o/final_fd_fused_s4096.json 2>> $o/final_bench.err
+  tail -qn1 $o/final_fd_*.json | cut -c1-260
   ls -la $o | grep final
   ;;
 *) echo "unknown pass $pass"; exit 2 ;;

@@ -42,6 +42,13 @@ ms = e0.elapsed_time(e1) / a.steps
 # both output-side queues read + written, input blocks (previous + current) in, state + output out
 Fp = (F + 3) // 4 * 4
 bytes_per = 2 * 2 * 8 * P * 2 * Fp + 4 * B * (3 * NS + 2)
-print(json.dumps({"kernel": "fd_render_kernel", "streams": S, "sources": NS, "partitions": P, "block": B,
+# the split launch (head kernel + queue kernel) moves less: a consumed head is overwritten by the
+# next block instead of cleared and re-read (2P - 2 slot transfers per queue and ear instead of 2P),
+# plus the scaled source spectra written by the head kernel and read by the queue kernel
+split = os.environ.get("RTB_FD_SPLIT", "1") != "0" and P > 1
+moved_per = 2 * 8 * (2 * P - 2) * 2 * Fp + 2 * 8 * NS * Fp + 4 * B * (3 * NS + 2) if split else bytes_per
+print(json.dumps({"kernel": "fd_render_kernel + fd_queue_kernel" if split else "fd_render_kernel",
+                  "streams": S, "sources": NS, "partitions": P, "block": B,
                   "ms_per_step": ms, "algorithmic_GBps": S * bytes_per / (ms * 1e-3) / 1e9,
-                  "bytes_per_launch": S * bytes_per, "finite": bool(torch.isfinite(out).all())}))
+                  "bytes_per_launch": S * bytes_per, "moved_GBps": S * moved_per / (ms * 1e-3) / 1e9,
+                  "moved_bytes_per_step": S * moved_per, "finite": bool(torch.isfinite(out).all())}))
