@@ -525,7 +525,7 @@ int rtb_fd_process_block(rtb_fd_plan *p, const float *d_in, const float *d_yaw_d
     // Split launch (default whenever there are partitions behind the head): head kernel + streaming
     // queue kernel.  Same workload as above, fused -> split: 0.0329 -> 0.0185 ms @256 streams,
     // 0.0492 -> 0.0376 @1024, 0.182 -> 0.124 @4096, 0.350 -> 0.227 @8192; 32 partitions @4096
-    // 0.894 -> 0.499 ms.  (Queue kernel 2 rows per batch / 94 registers; 4 rows 0.147 vs 0.137 ms,
+    // 0.894 -> 0.456 ms.  (Queue kernel 2 rows per batch / 94 registers; 4 rows 0.147 vs 0.137 ms,
     // 8 rows 0.159; head kernel 3 CTAs per SM 0.124 vs 0.127 with 2.)
     const bool split = !p->passthrough && p->P > 1 &&
                        (p->split_forced >= 0 ? p->split_forced != 0 : true);

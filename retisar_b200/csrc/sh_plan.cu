@@ -69,6 +69,8 @@ struct rtb_sh_plan {
     float *d_pt_b = nullptr;
     const float *pt_hnm_src = nullptr;
     int head_cur = 0, head_last = 0;
+    int pt_stale_cur = -1, pt_stale_last = -1;  // consumed heads the tcgen05 partition path left uncleared
+    bool pt_overwrite = true;                   // RTB_PT_OVERWRITE=0: clear consumed heads in the tail kernel instead
     // staging for the host-buffer entry points: RTB_HOST_SLOTS device copies of (input block, yaw,
     // output block) so that the input copy of block t+1 overlaps the kernels and the result copy
     // of block t (rtb_sh_submit_block_host / rtb_sh_wait_block_host)
@@ -549,6 +551,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
         // two phase tables next to four operand stages in shared memory
         p->pt_enabled = false;
         const int Npad = (4 * p->P + 15) / 16 * 16;
+        if (const char *e2 = getenv("RTB_PT_OVERWRITE")) p->pt_overwrite = e2[0] != '0';
         const char *env = getenv("RTB_PART_TC");
         const bool want = env ? env[0] != '0' : p->S >= 64;
         const size_t stage_bytes = sizeof(float) * ((size_t)2 * 2 * RTB_PT_KC * 128 + (size_t)2 * RTB_PT_KC * Npad);
@@ -746,6 +749,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
     }
     p->slot = 0; p->rad_idx = 0;
     p->head_cur = p->head_last = 0;
+    p->pt_stale_cur = p->pt_stale_last = -1;
     p->cur_order = p->last_order = p->order;
     p->last_valid = false;
     p->tables_set = true;
@@ -806,6 +810,7 @@ int rtb_sh_plan_set_crossfade(rtb_sh_plan *p, int on) {
             RTB_CUDA(cudaDeviceSynchronize());
             RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * queue_elems(p)));
             RTB_CUDA(cudaDeviceSynchronize());
+            p->pt_stale_last = -1;
         }
     }
     return RTB_OK;
@@ -832,6 +837,7 @@ int rtb_sh_plan_reset(rtb_sh_plan *p) {
     if (p->P > 1) {  // _blocks_fd.fill(0); _last_blocks_fd.fill(0)
         RTB_CUDA(cudaMemset(p->d_qcur, 0, sizeof(float2) * queue_elems(p)));
         RTB_CUDA(cudaMemset(p->d_qlast, 0, sizeof(float2) * queue_elems(p)));
+        p->pt_stale_cur = p->pt_stale_last = -1;
     }
     if (p->hp_P > 0) {  // the HPCF client's own _clear_buffers (_convolver.py:500-505)
         RTB_CUDA(cudaMemset(p->d_hp_x, 0, sizeof(float) * 2 * (size_t)p->S * 2 * p->B));
@@ -883,6 +889,17 @@ int rtb_sh_plan_set_hpcf(rtb_sh_plan *p, const float *hfd, int n_partitions) {
 
 namespace {
 
+// stream-minor queues [F][P][2][Spad]: clear the slots whose consumed heads were left for the next
+// partition MAC to overwrite (a block that does not run that kernel follows)
+void clear_pt_stale(rtb_sh_plan *p, cudaStream_t st) {
+    const size_t width = sizeof(float2) * 2 * (size_t)p->pt_Spad, pitch = width * p->P;
+    if (p->pt_stale_cur >= 0)
+        cudaMemset2DAsync(p->d_qcur + (size_t)p->pt_stale_cur * 2 * p->pt_Spad, pitch, 0, width, p->F, st);
+    if (p->pt_stale_last >= 0)
+        cudaMemset2DAsync(p->d_qlast + (size_t)p->pt_stale_last * 2 * p->pt_Spad, pitch, 0, width, p->F, st);
+    p->pt_stale_cur = p->pt_stale_last = -1;
+}
+
 // kernels for streams [s0, s0 + count) of the current block; in/yaw/out point at stream s0
 void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const float *d_yaw_deg,
                   float *d_out, cudaStream_t st, bool rows_given = false) {
@@ -914,6 +931,7 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         const long long total = (long long)count * p->E * p->B;
         sh_passthrough_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_in, d_out, count, p->C, p->E, p->B);
         if (p->P > 1 && p->pt_enabled) {
+            clear_pt_stale(p, st);
             const long long n = (long long)p->F * 2 * count;
             sh_queue_clear_head_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
                 p->d_qcur, count, p->F, p->P, p->pt_Spad, p->head_cur);
@@ -977,6 +995,8 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
             tp.n_chunks_max = p->pt_chunks_max;
             tp.order_max = p->order; tp.do_last = p->crossfade ? 1 : 0;
             tp.head_cur = p->head_cur; tp.head_last = p->head_last;
+            tp.overwrite_tail = (tp.n_chunks > 0 && p->pt_overwrite) ? 1 : 0;
+            if (!tp.overwrite_tail) clear_pt_stale(p, st);
             tp.tracker_dir = p->tracker_dir; tp.src_azim16 = p->src_azim16;
             kernel_attrs_once(sh_partition_tc_kernel, 220 * 1024);  // + 3 KB static (barriers, step list)
             const int n_stiles_total = (count + 127) / 128;
@@ -993,7 +1013,7 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
                     sh_partition_tc_kernel<<<grid, RTB_PT_THREADS, p->pt_smem, st>>>(q);
                     p->launches++;
                 }
-#define RTB_PT_TAIL(N) sh_partition_tail_soa_kernel<N><<<gw, 128, 0, st>>>(prm, p->d_qcur, p->d_qlast, p->pt_Spad);
+#define RTB_PT_TAIL(N) sh_partition_tail_soa_kernel<N><<<gw, 128, 0, st>>>(prm, p->d_qcur, p->d_qlast, p->pt_Spad, tp.overwrite_tail ? 0 : 1);
             switch (p->N2) {
                 case 64: RTB_PT_TAIL(64) break;
                 case 128: RTB_PT_TAIL(128) break;
@@ -1001,6 +1021,10 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
                 default: RTB_PT_TAIL(512) break;
             }
 #undef RTB_PT_TAIL
+            if (tp.overwrite_tail) {  // the consumed heads stay; the next block's MAC overwrites them
+                p->pt_stale_cur = p->head_cur;
+                if (p->crossfade) p->pt_stale_last = p->head_last;
+            }
             p->launches++;
         } else {
 #define RTB_PART_LAUNCH(N)                                                                  \
