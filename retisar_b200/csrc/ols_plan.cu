@@ -229,7 +229,8 @@ ols_fdl_kernel(const OlsParams prm) {
 struct OlsMonoParams {
     const float *x, *xprev;    // [S][B]
     float *xnext;
-    float *histT;              // [F][Kpad][Spad]: rows 0 / 1 of every bin = Re / Im of X_t
+    float *histT;              // [F][Kpad][Spad]: rows 2*slot, 2*slot + 1 of every bin = Re / Im of X_t
+    int slot;                  // ring slot of this block (the delay line ages by moving the slot, not the data)
     const float2 *tw;
     int S, Spad, Kpad, passthrough;
 };
@@ -273,8 +274,9 @@ ols_mono_spectrum_kernel(const OlsMonoParams prm) {
                 // the input is real, so bin f of the transform is the spectrum itself; the Nyquist
                 // bin sits in element HB of lane 0
                 const float2 z = (u < HB) ? X[u] : X[HB];
-                prm.histT[(size_t)f * fstride + s] = z.x * keep;
-                prm.histT[(size_t)f * fstride + prm.Spad + s] = z.y * keep;
+                float *h = prm.histT + (size_t)f * fstride + (size_t)(2 * prm.slot) * prm.Spad + s;
+                h[0] = z.x * keep;
+                h[prm.Spad] = z.y * keep;
             }
         }
     }
@@ -390,7 +392,7 @@ struct rtb_ols_plan {
     bool tc_mono = false;
     int tc_Spad = 0, tc_Kpad = 0, tc_nchunks = 0, tc_hpar = 0;
     int tc_nch[8] = {0}, tc_Jc[8] = {0}, tc_Npad[8] = {0}, tc_cols[8] = {0}, tc_smem[8] = {0};
-    float *d_histT[2] = {nullptr, nullptr};   // [F][Kpad][Spad], ping-pong (aged by one partition per block)
+    float *d_histT[2] = {nullptr, nullptr};   // [0]: [F][Kpad][Spad] delay line, a ring over the partition rows (tc_hpar = slot of the newest block)
     float *d_bmat[8] = {nullptr};             // per chunk: [F][hi, lo][Kpad/4][Npad/8][8][4]
     float *d_Y[8] = {nullptr};                // per chunk: [F][Jc][Spad]
 };
@@ -402,16 +404,16 @@ size_t state_elems(const rtb_ols_plan *p) { return (size_t)p->S * p->Cin * p->B;
 // one block of the mono-in / many-out convolver on the tensor cores (see ols_mono_* above)
 int process_mono_tc(rtb_ols_plan *p, const float *d_in, float *d_out, cudaStream_t st) {
     const int F = p->F, Kpad = p->tc_Kpad, Spad = p->tc_Spad;
-    float *cur = p->d_histT[p->tc_hpar], *nxt = p->d_histT[p->tc_hpar ^ 1];
-    // age the delay line by one partition: rows (2p, 2p+1) -> (2p+2, 2p+3) of every bin
-    const size_t row = sizeof(float) * (size_t)Spad, pitch = row * Kpad;
-    RTB_CUDA(cudaMemcpy2DAsync(nxt + 2 * (size_t)Spad, pitch, cur, pitch, row * (Kpad - 2), F,
-                               cudaMemcpyDeviceToDevice, st));
+    // The delay line ages by moving the ring slot: the newest spectrum goes to slot head, partition p
+    // (age p) is read from slot (head + p) % P -- the GEMM's loaders rotate the K rows by 2 * head.
+    // (Until round 2 the whole [F][Kpad][Spad] line was copied by one partition every block.)
+    const int head = p->tc_hpar = (p->tc_hpar + p->P - 1) % p->P;
+    float *nxt = p->d_histT[0];
     OlsMonoParams mp;
     mp.x = d_in;
     mp.xprev = p->d_xstate + (size_t)p->par * state_elems(p);
     mp.xnext = p->d_xstate + (size_t)(p->par ^ 1) * state_elems(p);
-    mp.histT = nxt; mp.tw = p->d_tw; mp.S = p->S; mp.Spad = Spad; mp.Kpad = Kpad;
+    mp.histT = nxt; mp.slot = head; mp.tw = p->d_tw; mp.S = p->S; mp.Spad = Spad; mp.Kpad = Kpad;
     mp.passthrough = p->passthrough ? 1 : 0;
 #define RTB_MONO_SPEC(N) fft_kernel_launch<N>(ols_mono_spectrum_kernel<N>, mp, (long long)p->S, st)
     switch (p->N2) {
@@ -419,7 +421,6 @@ int process_mono_tc(rtb_ols_plan *p, const float *d_in, float *d_out, cudaStream
         case 256: RTB_MONO_SPEC(256); break; default: RTB_MONO_SPEC(512); break;
     }
 #undef RTB_MONO_SPEC
-    p->tc_hpar ^= 1;
     p->launches++;
     if (p->passthrough) {
         ols_mono_passthrough_kernel<<<1184, 256, 0, st>>>(d_in, d_out, p->S, p->Cout, p->B);
@@ -435,7 +436,7 @@ int process_mono_tc(rtb_ols_plan *p, const float *d_in, float *d_out, cudaStream
         const int Npad = p->tc_Npad[ch];
         sh_analysis_tc_kernel<true><<<grid, RTB_TC_THREADS, p->tc_smem[ch], st>>>(
             nxt, p->d_bmat[ch], p->d_Y[ch], F, Kpad, p->tc_Jc[ch], Spad, Kpad, Npad, p->tc_cols[ch], 2,
-            (long long)2 * Kpad * Npad);
+            (long long)2 * Kpad * Npad, 2 * head, 2 * p->P);
         OlsMonoIfftParams ip;
         ip.Y = p->d_Y[ch]; ip.x = d_in; ip.tw = p->d_tw; ip.out = d_out;
         ip.S = p->S; ip.Spad = Spad; ip.Jc = p->tc_Jc[ch]; ip.Cout = p->Cout; ip.c0 = c0; ip.nch = p->tc_nch[ch];
@@ -480,9 +481,7 @@ int rtb_ols_plan_create(rtb_ols_plan **out, int device, int n_streams, int block
     DeviceGuard guard(device);
     cudaError_t err = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_xstate, sizeof(float) * 2 * state_elems(p));
-    if (err == cudaSuccess) err = cudaMalloc(&p->d_hist, sizeof(float2) * hist_elems(p));
     if (err == cudaSuccess) err = cudaMalloc(&p->d_hfd, sizeof(float2) * (size_t)p->P * p->Cout * p->Fp);
-    if (err == cudaSuccess) err = cudaMalloc(&p->d_incl, p->P);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_tw, sizeof(float2) * p->N2);
     if (err != cudaSuccess) {
         rtb_ols_plan_destroy(p);
@@ -502,7 +501,7 @@ int rtb_ols_plan_create(rtb_ols_plan **out, int device, int n_streams, int block
             if (p->tc_nchunks <= 8) {
                 p->tc_mono = true;
                 const size_t hbytes = sizeof(float) * (size_t)p->F * p->tc_Kpad * spad;
-                for (int i = 0; i < 2 && err == cudaSuccess; ++i) err = cudaMalloc(&p->d_histT[i], hbytes);
+                err = cudaMalloc(&p->d_histT[0], hbytes);
                 for (int ch = 0; ch < p->tc_nchunks && err == cudaSuccess; ++ch) {
                     const int nch = std::min(per_chunk, p->Cout - ch * per_chunk);
                     p->tc_nch[ch] = nch;
@@ -525,6 +524,15 @@ int rtb_ols_plan_create(rtb_ols_plan **out, int device, int n_streams, int block
                     err = cudaSuccess;
                 }
             }
+        }
+    }
+    if (!p->tc_mono) {  // delay line and partition mask of the FDL kernel (the tensor-core path has its own line)
+        err = cudaMalloc(&p->d_hist, sizeof(float2) * hist_elems(p));
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_incl, p->P);
+        if (err != cudaSuccess) {
+            rtb_ols_plan_destroy(p);
+            return fail(err == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA,
+                        "plan allocation failed: %s", cudaGetErrorString(err));
         }
     }
     std::vector<float2> tw(p->N2);
@@ -599,11 +607,12 @@ int rtb_ols_plan_reset(rtb_ols_plan *p) {
     // wait for the blocks in flight first and for the memsets afterwards.
     RTB_CUDA(cudaDeviceSynchronize());
     RTB_CUDA(cudaMemset(p->d_xstate, 0, sizeof(float) * 2 * state_elems(p)));
-    RTB_CUDA(cudaMemset(p->d_hist, 0, sizeof(float2) * hist_elems(p)));
-    RTB_CUDA(cudaMemset(p->d_incl, 0, p->P));
-    if (p->tc_mono)
-        for (int i = 0; i < 2; ++i)
-            RTB_CUDA(cudaMemset(p->d_histT[i], 0, sizeof(float) * (size_t)p->F * p->tc_Kpad * p->tc_Spad));
+    if (p->d_hist) RTB_CUDA(cudaMemset(p->d_hist, 0, sizeof(float2) * hist_elems(p)));
+    if (p->d_incl) RTB_CUDA(cudaMemset(p->d_incl, 0, p->P));
+    if (p->tc_mono) {
+        RTB_CUDA(cudaMemset(p->d_histT[0], 0, sizeof(float) * (size_t)p->F * p->tc_Kpad * p->tc_Spad));
+        p->tc_hpar = 0;
+    }
     RTB_CUDA(cudaDeviceSynchronize());
     return RTB_OK;
 }

@@ -137,7 +137,8 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                       const float *__restrict__ bsrc,  // [2][Kpad/4][Npad/8][8][4]: hi then lo
                       float *__restrict__ zcur,        // [S][J][B]
                       int S, int C, int J, int B, int Kpad, int Npad, int acc_cols, int nst,
-                      long long bmat_stride) {  // STREAM_B: floats between the matrices of consecutive streams (0: one matrix)
+                      long long bmat_stride,   // STREAM_B: floats between the matrices of consecutive streams (0: one matrix)
+                      int krot = 0, int kmod = 0) {  // ring of input rows: channel c < kmod is read from row (c + krot) % kmod
     constexpr int KC = RTB_TC_KC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *a_stage = reinterpret_cast<float *>(smem_raw);   // [nst stages][hi, lo][KC/4][16][8][4]
@@ -233,7 +234,15 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[q][i] = ldg_nc_v4_pred(xp + (size_t)(4 * q + i) * B, 4 * q + i < cmax);
+                for (int i = 0; i < 4; ++i) {
+                    int off = 4 * q + i;  // channel c0 + off; with a ring (mono convolver's delay line) its row rotates
+                    if (kmod && c0 + off < kmod) {
+                        int r = c0 + off + krot;
+                        if (r >= kmod) r -= kmod;
+                        off = r - c0;
+                    }
+                    v[q][i] = ldg_nc_v4_pred(xp + (long long)off * B, 4 * q + i < cmax);
+                }
             const int st = (int)(n % nst);
             // k-th unit of this group: its stage was last used by unit n - nst, whose completion is
             // commit number k (groups that start on a fresh stage) or k + 1 (the others) on this

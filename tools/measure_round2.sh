@@ -175,6 +175,7 @@ final)
   timeout 200 python tools/profile_fd.py --streams 4096 --taps 8192 --steps 100 > $o/final_fd_split_s4096_p32.json 2>> $o/final_bench.err
   RTB_FD_SPLIT=0 timeout 200 python tools/profile_fd.py --streams 4096 --steps 200 > $o/final_fd_fused_s4096.json 2>> $o/final_bench.err
   tail -qn1 $o/final_fd_*.json | cut -c1-260
+  for S in 1024 4096; do timeout 300 python tools/bench_c4_chain.py --fused --streams $S > $o/final_c4_chain_s${S}_fused.json 2>> $o/final_bench.err; tail -n1 $o/final_c4_chain_s${S}_fused.json | cut -c1-200; done
   ls -la $o | grep final
   ;;
 *) echo "unknown pass $pass"; exit 2 ;;
