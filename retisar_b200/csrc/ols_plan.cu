@@ -295,6 +295,9 @@ struct OlsMonoIfftParams {
 // streams): 8 -> 0.2425 / 0.762 ms, 16 -> 0.2334 / 0.698 ms, 32 -> 0.2416 / 0.730 ms, 64 -> 0.2586 / 0.807 ms
 #define RTB_OLS_MONO_ST 16
 #endif
+#ifndef RTB_OLS_MONO_LB
+#define RTB_OLS_MONO_LB 5   // gather loads in flight per thread
+#endif
 
 template <int N2>
 __global__ void __launch_bounds__(128)
@@ -316,14 +319,29 @@ ols_mono_ifft_kernel(const OlsMonoIfftParams prm) {
     // coalesced gather: for every bin the four rows of the pair, ST consecutive streams each, as
     // 16-byte loads (Spad is a multiple of ST); the scalar stores into the padded rows are
     // conflict free (bank = 33 r + 4 sl4 + j)
-    for (int i = threadIdx.x; i < F * 4 * (ST / 4); i += 128) {
-        const int sl4 = i % (ST / 4), r = (i / (ST / 4)) & 3, f = i / ST;
-        const int row = 2 * cl0 + r;  // rows of channel cl0 then cl1
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < 2 || has1)
-            v = __ldcs(reinterpret_cast<const float4 *>(prm.Y + ((size_t)f * prm.Jc + row) * prm.Spad + s0) + sl4);
-        float *d = tile + (f * 4 + r) * (ST + 1) + 4 * sl4;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    // (all loads of a batch are requested before the first one is stored: ncu showed 15 long-scoreboard
+    // stall cycles per issue with one load in flight per thread)
+    constexpr int NLD = F * 4 * (ST / 4), PER = (NLD + 127) / 128;
+    for (int k0 = 0; k0 < PER; k0 += RTB_OLS_MONO_LB) {
+        float4 v[RTB_OLS_MONO_LB];
+#pragma unroll
+        for (int k = 0; k < RTB_OLS_MONO_LB; ++k) {
+            const int i = threadIdx.x + 128 * (k0 + k);
+            const int sl4 = i % (ST / 4), r = (i / (ST / 4)) & 3, f = i / ST;
+            const int row = 2 * cl0 + r;  // rows of channel cl0 then cl1
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < NLD && (r < 2 || has1))
+                v[k] = __ldcs(reinterpret_cast<const float4 *>(prm.Y + ((size_t)f * prm.Jc + row) * prm.Spad + s0) + sl4);
+        }
+#pragma unroll
+        for (int k = 0; k < RTB_OLS_MONO_LB; ++k) {
+            const int i = threadIdx.x + 128 * (k0 + k);
+            const int sl4 = i % (ST / 4), r = (i / (ST / 4)) & 3, f = i / ST;
+            if (i < NLD) {
+                float *d = tile + (f * 4 + r) * (ST + 1) + 4 * sl4;
+                d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
+            }
+        }
     }
     __syncthreads();
     float2 *buf = s_buf + (warp * GROUPS + grp) * Cfg::REGION;
