@@ -154,9 +154,14 @@ def run_reference_arm(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    n_blocks = 4000  # bounded sample: about one second of rendering per core plus set-up
+    # One step = a bounded sample: every core renders `per_step` consecutive blocks of its own stream.
+    # W warm-up steps run untimed, K steps are timed; the sample shrinks when K is large so that the
+    # whole run stays below about a minute of wall time (the set-up of the 2702-direction HRIR set is
+    # a few seconds on top).
+    per_step = max(20, min(1000, 200000 // max(args.steps, 1)))
+    n_blocks, warm = args.steps * per_step, max(args.warmup, 1) * per_step
     t0 = time.perf_counter()
-    streams, sec, kind, sample = cpu_arm(args.workload, cores, n_blocks, warm=max(args.warmup, 3) * 10)
+    streams, sec, kind, sample = cpu_arm(args.workload, cores, n_blocks, warm=warm)
     wall = time.perf_counter() - t0
     line = {
         "impl": "reference", "metric": METRIC, "value": streams, "unit": UNIT,
@@ -166,8 +171,9 @@ def run_reference_arm(args):
         "config": workload_config(args.workload, args.streams),
         "cpu_baseline": {"value": streams, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": streams, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "step_definition": f"one bounded sample = {n_blocks} blocks of one stream per core; "
-                           f"ms_per_step = mean time of one block of one stream",
+        "step_definition": f"one step = a bounded sample of {per_step} consecutive blocks of one stream on "
+                           f"every core ({args.warmup} untimed + {args.steps} timed steps); ms_per_step = mean "
+                           f"time of ONE block of one stream, as in the GPU arm (there: one block of the batch)",
         "wall_s": wall,
     }
     print(json.dumps(line), flush=True)
@@ -646,7 +652,8 @@ def run_gpu_arm(args):
             if orig_affinity is not None:  # every core the process started with (undo the NUMA binding)
                 os.sched_setaffinity(0, orig_affinity)
             cores = len(orig_affinity) if orig_affinity is not None else (os.cpu_count() or 1)
-            cb_streams, cb_sec, kind, sample = cpu_arm(args.workload, cores, 2000)
+            # about 1 s of wall time per core: 16 cores -> ~18 s of CPU work (bounded sample)
+            cb_streams, cb_sec, kind, sample = cpu_arm(args.workload, cores, 8000)
             line["cpu_baseline"] = {"value": cb_streams, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": sample}
         print(json.dumps(line), flush=True)
