@@ -449,10 +449,10 @@ int process_mono_tc(rtb_ols_plan *p, const float *d_in, float *d_out, cudaStream
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device);
     const long long tiles = (long long)F * Spad / RTB_TC_M;
     const int grid = (int)std::min<long long>(tiles, n_sm);
-    kernel_attrs_once(sh_analysis_tc_kernel<true>, 224 * 1024);
+    kernel_attrs_once(sh_analysis_tc_kernel<true, RTB_TC_LG, true>, 224 * 1024);
     for (int ch = 0, c0 = 0; ch < p->tc_nchunks; c0 += p->tc_nch[ch], ++ch) {
         const int Npad = p->tc_Npad[ch];
-        sh_analysis_tc_kernel<true><<<grid, RTB_TC_THREADS, p->tc_smem[ch], st>>>(
+        sh_analysis_tc_kernel<true, RTB_TC_LG, true><<<grid, RTB_TC_THREADS, p->tc_smem[ch], st>>>(
             nxt, p->d_bmat[ch], p->d_Y[ch], F, Kpad, p->tc_Jc[ch], Spad, Kpad, Npad, p->tc_cols[ch], 2,
             (long long)2 * Kpad * Npad, 2 * head, 2 * p->P);
         OlsMonoIfftParams ip;

@@ -131,7 +131,10 @@ __device__ __forceinline__ float4 ldg_nc_v4_pred(const float *p, bool pred) {
     return __ldg(reinterpret_cast<const float4 *>(pred ? p : reinterpret_cast<const float *>(&g_tc_zero4)));
 }
 
-template <bool STREAM_B, int LG = RTB_TC_LG>
+// RING: the input rows form a ring (the mono convolver's delay line): channel c < kmod is read from
+// row (c + krot) % kmod.  A template flag, not a run-time test: the extra address arithmetic in the
+// loaders cost the analysis launches 2 us of 20 (c2, 1 024 streams) when it was one.
+template <bool STREAM_B, int LG = RTB_TC_LG, bool RING = false>
 __global__ void __launch_bounds__(RTB_TC_THREADS_OF(LG), 1)
 sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
                       const float *__restrict__ bsrc,  // [2][Kpad/4][Npad/8][8][4]: hi then lo
@@ -235,13 +238,17 @@ sh_analysis_tc_kernel(const float *__restrict__ x,     // [S][C][B]
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    int off = 4 * q + i;  // channel c0 + off; with a ring (mono convolver's delay line) its row rotates
-                    if (kmod && c0 + off < kmod) {
-                        int r = c0 + off + krot;
-                        if (r >= kmod) r -= kmod;
-                        off = r - c0;
+                    if constexpr (RING) {
+                        int off = 4 * q + i;  // channel c0 + off: its row rotates
+                        if (c0 + off < kmod) {
+                            int r = c0 + off + krot;
+                            if (r >= kmod) r -= kmod;
+                            off = r - c0;
+                        }
+                        v[q][i] = ldg_nc_v4_pred(xp + (long long)off * B, 4 * q + i < cmax);
+                    } else {
+                        v[q][i] = ldg_nc_v4_pred(xp + (size_t)(4 * q + i) * B, 4 * q + i < cmax);
                     }
-                    v[q][i] = ldg_nc_v4_pred(xp + (long long)off * B, 4 * q + i < cmax);
                 }
             const int st = (int)(n % nst);
             // k-th unit of this group: its stage was last used by unit n - nst, whose completion is
