@@ -17,7 +17,8 @@ for line in txt.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
         cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        cur = re.sub(r"\(.*", "", cur).replace("rtb::", "").replace("(anonymous namespace)::", "")
+        cur = cur.replace("(anonymous namespace)::", "").replace("rtb::", "")
+        cur = re.sub(r"\(.*", "", cur)
         per[cur] = collections.Counter()
         continue
     if cur:
