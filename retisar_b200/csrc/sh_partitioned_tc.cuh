@@ -362,7 +362,11 @@ sh_spectra_soa_kernel(const ShPartParams prm, float2 *__restrict__ zspecT, long 
     const bool active = s < prm.S;
     float2 *buf = s_buf[warp] + grp * Cfg::REGION;
     float *zrow = reinterpret_cast<float *>(buf);
-    const int np = max(prm.np_cur, prm.np_last);
+    // blockIdx.y takes a contiguous share of the signal rounds: with one CTA walking all rounds the grid
+    // of c3 (512 CTAs of 8 streams, 444 resident) ran as one full wave and a tail of 68 CTAs
+    const int np_all = max(prm.np_cur, prm.np_last);
+    const int share = ((np_all + (int)gridDim.y - 1) / (int)gridDim.y + GROUPS - 1) / GROUPS * GROUPS;
+    const int p_first = (int)blockIdx.y * share, np = min(np_all, p_first + share);
     const size_t zoff = (size_t)(active ? s : 0) * prm.J * B;
 
     auto prefetch_z = [&](int p0) {
@@ -380,9 +384,9 @@ sh_spectra_soa_kernel(const ShPartParams prm, float2 *__restrict__ zspecT, long 
                 *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    if (np > 0) prefetch_z(0);
+    if (np > p_first) prefetch_z(p_first);
     cp_async_commit();
-    for (int p0 = 0; p0 < np; p0 += GROUPS) {
+    for (int p0 = p_first; p0 < np; p0 += GROUPS) {
         cp_async_wait_all();
         __syncwarp();
         const int p = p0 + grp;

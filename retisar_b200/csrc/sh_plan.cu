@@ -71,6 +71,7 @@ struct rtb_sh_plan {
     int head_cur = 0, head_last = 0;
     int pt_stale_cur = -1, pt_stale_last = -1;  // consumed heads the tcgen05 partition path left uncleared
     bool pt_overwrite = true;                   // RTB_PT_OVERWRITE=0: clear consumed heads in the tail kernel instead
+    int spec_split_forced = 0;                  // RTB_SPEC_SPLIT=n: grid y of the spectra kernel (A/B runs)
     // staging for the host-buffer entry points: RTB_HOST_SLOTS device copies of (input block, yaw,
     // output block) so that the input copy of block t+1 overlaps the kernels and the result copy
     // of block t (rtb_sh_submit_block_host / rtb_sh_wait_block_host)
@@ -552,6 +553,7 @@ int rtb_sh_plan_set_tables(rtb_sh_plan *p, const float *yw, const float *hnm, co
         p->pt_enabled = false;
         const int Npad = (4 * p->P + 15) / 16 * 16;
         if (const char *e2 = getenv("RTB_PT_OVERWRITE")) p->pt_overwrite = e2[0] != '0';
+        if (const char *e3 = getenv("RTB_SPEC_SPLIT")) p->spec_split_forced = atoi(e3);
         const char *env = getenv("RTB_PART_TC");
         const bool want = env ? env[0] != '0' : p->S >= 64;
         const size_t stage_bytes = sizeof(float) * ((size_t)2 * 2 * RTB_PT_KC * 128 + (size_t)2 * RTB_PT_KC * Npad);
@@ -970,11 +972,18 @@ void launch_range(rtb_sh_plan *p, int s0, int count, const float *d_in, const fl
         if (p->pt_enabled) {  // tensor-core partition MAC on the stream-minor layout (whole plan: s0 == 0)
             p->last_render_kernel = 6;
             const unsigned gs = (unsigned)((count + RTB_SPEC_NW - 1) / RTB_SPEC_NW);
+            // shares of the signal rounds per stream group (grid y): enough CTAs for >= 8 waves of the
+            // three resident CTAs per SM, at least 6 rounds per CTA (RTB_SPEC_SPLIT overrides)
+            const int np_spec = std::max(prm.np_cur, prm.np_last);
+            int spec_split = (int)std::min<long long>(std::max(1, np_spec / 6),
+                                                      (8LL * 3 * p->n_sm + gs - 1) / gs);
+            if (p->spec_split_forced > 0) spec_split = p->spec_split_forced;
+            spec_split = std::max(1, std::min(spec_split, std::max(1, np_spec)));
 #define RTB_PT_LAUNCH(N)                                                                                     \
     {                                                                                                        \
         const size_t sm = sizeof(float2) * (size_t)(FftCfg<N>::GROUPS * N) * (RTB_SPEC_NW + 1);              \
         kernel_attrs_once(sh_spectra_soa_kernel<N>, 100 * 1024, true);                                       \
-        sh_spectra_soa_kernel<N><<<gs, 32 * RTB_SPEC_NW, sm, st>>>(prm, p->d_zspec, p->pt_Spad);             \
+        sh_spectra_soa_kernel<N><<<dim3(gs, spec_split), 32 * RTB_SPEC_NW, sm, st>>>(prm, p->d_zspec, p->pt_Spad); \
     }
             switch (p->N2) {
                 case 64: RTB_PT_LAUNCH(64) break;
