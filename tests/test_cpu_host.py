@@ -405,3 +405,32 @@ def test_staged_reference_is_byte_identical_to_the_reference_tree():
     assert len(names) >= 20
     for n in names:
         assert filecmp.cmp(os.path.join("/root/reference/ReTiSAR", n), os.path.join(root, "ReTiSAR", n), shallow=False), n
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver times beside the GPU arm) needs no GPU: one JSON
+    line, the reference-arm keys of the contract, the steps / warm-up it was asked for, and the same
+    `config` dictionary as the GPU arm."""
+    import json
+    import subprocess
+    import sys
+
+    import bench
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+    cp = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1",
+                         "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600,
+                        env=env, cwd=root, stdin=subprocess.DEVNULL)
+    assert cp.returncode == 0, cp.stderr[-2000:]
+    lines = [ln for ln in cp.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["higher_is_better"] is True
+    assert d["config"] == bench.workload_config("c2", 1024)
+    assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
+                                           "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["value"] == d["value"] and cb["cores"] >= 1 and cb["kind"] in ("reference", "port")
+    assert "2 timed steps" in d["step_definition"] and "blocks" in cb["sample"]
