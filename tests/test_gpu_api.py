@@ -249,3 +249,46 @@ def test_async_host_blocks_and_block_runs_match_the_synchronous_path():
     runs._plan.process_blocks_device(xr, yr, out, 3, 1, torch.cuda.current_stream())
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), want[3])
+
+
+def test_runs_of_blocks_replayed_as_cuda_graph_equal_single_blocks(monkeypatch):
+    """`rtb_sh_process_blocks` replays a run that comes back with the same buffers, ring phase, length
+    and plan state as one CUDA graph launch (recorded on the second occurrence).  Five identical runs
+    and a sixth after a cross-fade toggle must equal block-by-block processing of a second plan; the
+    launch counter keeps counting kernels."""
+    import torch
+
+    from retisar_b200 import _capi
+    from retisar_b200 import workloads as wl
+
+    tb = wl.sh_tables("c2", hrir_dirs=200)
+    S, C, B, ring, count = 6, tb["C"], tb["B"], 4, 8
+    rng = np.random.default_rng(33)
+    x = (rng.standard_normal((ring, S, C, B)) * 0.1).astype(np.float32)
+    yaw = rng.uniform(0, 360, (ring, S)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    xr, yr = torch.from_numpy(x).to(dev), torch.from_numpy(yaw).to(dev)
+    st = torch.cuda.Stream(device=dev)
+    results = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RTB_GRAPH", mode)
+        conv = wl.make_renderer(tb, S)
+        out = torch.empty((S, 2, B), device=dev)
+        outs, launches = [], []
+        torch.cuda.synchronize()
+        first = 0
+        for run in range(7):
+            if run == 5:
+                conv.set_crossfade(False)
+            if run == 6:
+                conv.set_crossfade(True)
+            l0 = conv._plan.query(_capi.RTB_Q_LAUNCHES)
+            conv._plan.process_blocks_device(xr, yr, out, first, count, st)
+            st.synchronize()
+            outs.append(out.cpu().numpy().copy())
+            launches.append(conv._plan.query(_capi.RTB_Q_LAUNCHES) - l0)
+            first += count
+        results[mode] = (outs, launches)
+    for a, b in zip(results["1"][0], results["0"][0]):
+        assert np.array_equal(a, b)
+    assert results["1"][1] == results["0"][1] and results["1"][1][0] == 2 * count
