@@ -218,6 +218,7 @@ void launch_render_mg(const rtb_sh_plan *p, const ShRenderMgParams &prm, cudaStr
 // Tables of the steady-state render kernel for SH order `order`: signals sorted by m (one group
 // per phase pair), real m = 0 rows paired two per FFT, term-2 spectra stored mirrored.
 int build_mg_tables(rtb_sh_plan *p, int order) {
+    drop_graphs(p);  // recorded runs hold the pointers of the tables that are replaced here
     const int F = p->F, B = p->B, K = p->K;
     auto H = [&](int k, int e, int f) {
         const size_t o = 2 * (((size_t)k * 2 + e) * F + f);

@@ -277,11 +277,15 @@ def test_runs_of_blocks_replayed_as_cuda_graph_equal_single_blocks(monkeypatch):
         outs, launches = [], []
         torch.cuda.synchronize()
         first = 0
-        for run in range(7):
+        for run in range(13):
             if run == 5:
                 conv.set_crossfade(False)
             if run == 6:
                 conv.set_crossfade(True)
+            if run == 8:    # lower order: the grouped tables are rebuilt (recorded runs must be dropped)
+                conv._plan.set_order(2)
+            if run == 10:   # back to the order the first recordings were made for
+                conv._plan.set_order(tb["order"])
             l0 = conv._plan.query(_capi.RTB_Q_LAUNCHES)
             conv._plan.process_blocks_device(xr, yr, out, first, count, st)
             st.synchronize()
