@@ -417,10 +417,12 @@ def run_gpu_arm(args):
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = plan.query(_capi.RTB_Q_LAUNCHES)
+    replays0 = plan.query(_capi.RTB_Q_GRAPH_REPLAYS)
     e0, e1 = rig.timed(K, primed=True)
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = plan.query(_capi.RTB_Q_LAUNCHES) - launches0
+    graph_replays = plan.query(_capi.RTB_Q_GRAPH_REPLAYS) - replays0
     value = world * S * K / (dev_ms * 1e-3) / block_rate
 
     # ---- block latency: per-step events, L2 flushed before every step
@@ -668,9 +670,10 @@ def run_gpu_arm(args):
                              "reps_ms_per_step": [t / K_e2e * 1e3 for t in sync_reps],
                              "api": "AdjustableShConvolver.filter_block(numpy pinned [S,C,B], yaw[S])"}},
             "gpu_launches": int(launches),
-            "launch_mode": ("the K timed steps are ONE CUDA graph launch (run recorded by the library during two "
-                            "untimed occurrences of the same run after the W warm-up steps); RTB_GRAPH=0: "
-                            "2 K kernel launches enqueued by one C call"),
+            "launch_mode": ("the K timed steps were ONE CUDA graph launch (run recorded by the library during two "
+                            "untimed occurrences of the same run after the W warm-up steps)" if graph_replays == 1
+                            else "the kernels of the K timed steps were launched one by one from one C call"),
+            "graph_replays_in_timed_region": int(graph_replays),
             "roofline": {"bound": "hbm", "kernel": render_name, "achieved": achieved,
                          "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
                          "traffic": traffic, "peak_source": peaks["source"],

@@ -145,6 +145,8 @@ int rtb_sh_transform_filter(int device, const float *yw, const float *hfd, int n
                                  1 sh_render_mg_kernel (grouped by m),
                                  3 partitioned (spectra + SIMT partition MAC + tail), 4 passthrough,
                                  6 partitioned on tensor cores (sh_partition_tc_kernel)            */
+#define RTB_Q_GRAPH_REPLAYS 10 /* runs of blocks replayed as one CUDA graph launch so far
+                                  (rtb_sh_process_blocks)                                        */
 int rtb_sh_plan_query(rtb_sh_plan *plan, int what, int64_t *value);
 /* record CUDA events around each kernel of process_block (measurement aid, no reference
  * counterpart; the reference reports load through JACK, _jack_client.py:869-895) */

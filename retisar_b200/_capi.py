@@ -14,6 +14,7 @@ _LIB_PATH = os.environ.get("RTB_LIB_PATH") or os.path.join(
 RTB_OK, RTB_ERR_INVALID, RTB_ERR_STATE, RTB_ERR_UNSUPPORTED, RTB_ERR_CUDA, RTB_ERR_NOMEM = range(6)
 RTB_Q_SYMMETRIC, RTB_Q_ROWS, RTB_Q_SIGNALS, RTB_Q_LAUNCHES, RTB_Q_STATE_BYTES = 1, 2, 3, 4, 5
 RTB_Q_ANALYSIS_NS, RTB_Q_RENDER_NS, RTB_Q_TENSOR_CORE, RTB_Q_RENDER_KERNEL = 6, 7, 8, 9
+RTB_Q_GRAPH_REPLAYS = 10
 RENDER_KERNEL_NAMES = {0: "sh_render_kernel", 1: "sh_render_mg_kernel", 2: "sh_render_split_kernel",
                        3: "sh_partition_mac2_kernel", 4: "sh_passthrough_kernel", 6: "sh_partition_tc_kernel"}
 

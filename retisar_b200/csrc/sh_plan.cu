@@ -82,6 +82,7 @@ struct rtb_sh_plan {
     };
     std::vector<BlockGraph> graphs;
     bool graphs_enabled = true;                 // RTB_GRAPH=0: every block of a run is launched by the host
+    long long graph_replays = 0;
     // staging for the host-buffer entry points: RTB_HOST_SLOTS device copies of (input block, yaw,
     // output block) so that the input copy of block t+1 overlaps the kernels and the result copy
     // of block t (rtb_sh_submit_block_host / rtb_sh_wait_block_host)
@@ -1289,6 +1290,7 @@ int rtb_sh_process_blocks(rtb_sh_plan *p, const float *d_in_ring, const float *d
     RTB_CUDA(cudaGraphLaunch(g->exec, st));
     for (int i = 0; i < count; ++i) advance_block(p);
     p->launches += g->launches;
+    p->graph_replays++;
     g->seen++;
     return RTB_OK;
 }
@@ -1382,6 +1384,7 @@ int rtb_sh_plan_query(rtb_sh_plan *p, int what, int64_t *value) {
         case RTB_Q_LAUNCHES: *value = p->launches; break;
         case RTB_Q_TENSOR_CORE: *value = p->tc_enabled ? 1 : 0; break;
         case RTB_Q_RENDER_KERNEL: *value = p->last_render_kernel; break;
+        case RTB_Q_GRAPH_REPLAYS: *value = p->graph_replays; break;
         case RTB_Q_STATE_BYTES: *value = (int64_t)sizeof(float) * (2 * (int64_t)p->J * p->B + 2); break;
         case RTB_Q_ANALYSIS_NS:
         case RTB_Q_RENDER_NS: {

@@ -292,7 +292,9 @@ def test_runs_of_blocks_replayed_as_cuda_graph_equal_single_blocks(monkeypatch):
             outs.append(out.cpu().numpy().copy())
             launches.append(conv._plan.query(_capi.RTB_Q_LAUNCHES) - l0)
             first += count
-        results[mode] = (outs, launches)
+        results[mode] = (outs, launches, conv._plan.query(_capi.RTB_Q_GRAPH_REPLAYS))
     for a, b in zip(results["1"][0], results["0"][0]):
         assert np.array_equal(a, b)
     assert results["1"][1] == results["0"][1] and results["1"][1][0] == 2 * count
+    # runs 0-4 share a key (replayed from the third on), the later ones follow a state change each
+    assert results["0"][2] == 0 and results["1"][2] >= 3
