@@ -1263,24 +1263,28 @@ int rtb_sh_process_blocks(rtb_sh_plan *p, const float *d_in_ring, const float *d
         return run_direct();
     }
     if (!g->exec) {  // second occurrence: record the run (the recording does not execute), then launch it
+        // host state the recording advances; put back if the recording fails, and the run is launched
+        // kernel by kernel instead (graphs off for this plan from then on)
+        const int s_slot = p->slot, s_rad = p->rad_idx, s_lo = p->last_order, s_hps = p->hp_slot, s_hpx = p->hp_xidx;
+        const bool s_lv = p->last_valid;
         const long long l0 = p->launches;
         cudaGraph_t graph = nullptr;
-        RTB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        const int rc = run_direct();
-        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (rc != RTB_OK || ce != cudaSuccess || !graph) {
-            if (graph) cudaGraphDestroy(graph);
-            (void)cudaGetLastError();
-            p->graphs_enabled = false;
-            return fail(RTB_ERR_CUDA, "recording a run of blocks as a CUDA graph failed (%s); set RTB_GRAPH=0",
-                        cudaGetErrorString(ce));
+        cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        int rc = RTB_OK;
+        if (ce == cudaSuccess) {
+            rc = run_direct();
+            ce = cudaStreamEndCapture(st, &graph);
         }
-        const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
-        cudaGraphDestroy(graph);
+        cudaError_t ie = cudaErrorUnknown;
+        if (rc == RTB_OK && ce == cudaSuccess && graph) ie = cudaGraphInstantiate(&g->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
         if (ie != cudaSuccess) {
+            (void)cudaGetLastError();
             g->exec = nullptr;
             p->graphs_enabled = false;
-            return fail(RTB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+            p->slot = s_slot; p->rad_idx = s_rad; p->last_order = s_lo; p->hp_slot = s_hps; p->hp_xidx = s_hpx;
+            p->last_valid = s_lv; p->launches = l0;
+            return run_direct();
         }
         g->launches = p->launches - l0;
         g->seen = 2;
